@@ -1,0 +1,164 @@
+/*
+ * hbird_b200.h — C-ABI of the B200-native dense nearest-neighbour evaluation path.
+ *
+ * This is the drop-in boundary for ONE hot path of vpariza/open-hummingbird-eval:
+ * memory-bank construction -> exact inner-product kNN -> soft label transfer ->
+ * upsample/argmax -> mIoU confusion matrix.  Every entry point names the reference
+ * interface it replaces (file:line into the reference tree).  Only plain pointers,
+ * sizes and an opaque handle cross this boundary: no torch types.
+ *
+ * Conventions
+ *   - every `*_dev` pointer is a DEVICE pointer on the bank's CUDA device;
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream);
+ *   - all entry points return an `hb_status` (0 = ok, negative = error); the message of
+ *     the last error on the calling thread is returned by hb_last_error();
+ *   - all launches are asynchronous on `stream`; no entry point synchronises the device
+ *     unless stated;
+ *   - there is NO CPU fallback: without an sm_100 device every compute call fails with
+ *     HB_ERR_UNSUPPORTED.
+ *   - a handle is not thread-safe (the reference drives its backend from one Python
+ *     thread, hbird_eval.py:214-246).
+ */
+#ifndef HBIRD_B200_H_
+#define HBIRD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HB_ABI_VERSION 1
+
+typedef enum hb_status {
+  HB_OK = 0,
+  HB_ERR_INVALID = -1,     /* bad argument (maps to ValueError, search_faiss.py:25,48) */
+  HB_ERR_CUDA = -2,        /* CUDA runtime/driver error (maps to RuntimeError)          */
+  HB_ERR_OOM = -3,         /* device allocation failed (maps to MemoryError)            */
+  HB_ERR_UNSUPPORTED = -4, /* no sm_100 device (maps to RuntimeError, search_faiss.py:15-16) */
+  HB_ERR_STATE = -5        /* call order violated, e.g. search before finalize          */
+} hb_status;
+
+/* hb_bank_create flags */
+#define HB_BANK_KEEP_F32 1u   /* keep an fp32 copy of the normalised rows for the exact re-rank */
+#define HB_BANK_L2 2u         /* reserved: L2 metric (search_faiss.py:45-46), not implemented   */
+
+typedef struct hb_bank hb_bank_t; /* opaque: one HBM-resident shard of the memory bank */
+
+/* ---- library ------------------------------------------------------------------- */
+
+int hb_abi_version(void);
+/* Message of the last failing call on this thread ("" if none). */
+const char* hb_last_error(void);
+/* HB_OK iff `device` exists and is compute capability 10.x (replaces the
+ * faiss.get_num_gpus() < 1 check, search_faiss.py:14-16).  Writes the SM count. */
+int hb_device_check(int device, int* num_sms_out);
+
+/* ---- K1: memory-bank construction ------------------------------------------------
+ * Replaces hbird_eval.py:309-329 (mask decode, _patchify_gt :554-573, one_hot+mean
+ * :319-320, L2 normalise :324, append :328-329) and the faiss index build + index.add
+ * (search_faiss.py:50-81).  The bank owns its HBM: bf16 rows (row pitch padded to a
+ * multiple of 64 elements, zero filled), optionally an fp32 copy, and one label record
+ * per row: the per-patch class histogram as uint16[num_classes] (the reference's soft
+ * label is histogram / patch_pixels, hbird_eval.py:319-320). */
+int hb_bank_create(int device, int d, int num_classes, int patch_pixels,
+                   int64_t capacity_rows, unsigned flags, hb_bank_t** bank_out);
+int hb_bank_destroy(hb_bank_t* bank);
+
+/* Append n rows.  feats_dev: fp32 (src_rows, d) raw ViT features of B images with an
+ * S x S patch grid (src_rows = B*S*S), NOT normalised.  mask_dev: uint8 (B, S*ps, S*ps)
+ * class ids already decoded (hb_decode_mask) — patch (b, py, px) covers pixels
+ * [py*ps, (py+1)*ps) x [px*ps, (px+1)*ps).  sel_dev: optional int32 (n,) source-row
+ * indices (the bounded-memory sampler's picks, hbird_eval.py:332-355); NULL = all
+ * src_rows rows in order (then n must equal B*S*S).  Row i of the bank receives
+ * feats[src]/||feats[src]||_2 (no epsilon, hbird_eval.py:324). */
+int hb_bank_append(hb_bank_t* bank, const float* feats_dev, const uint8_t* mask_dev,
+                   int B, int S, int ps, const int32_t* sel_dev, int64_t n, void* stream);
+
+/* Append n rows whose soft labels are already known as fp32 (n, num_classes) rows that
+ * are multiples of 1/patch_pixels (load_memory path, hbird_eval.py:380-400): counts are
+ * recovered as rint(label*patch_pixels).  normalise != 0 re-normalises the features. */
+int hb_bank_append_soft(hb_bank_t* bank, const float* feats_dev, const float* soft_dev,
+                        int64_t n, int normalise, void* stream);
+
+/* Freeze the bank (builds the TMA tensor map).  Must precede hb_search. */
+int hb_bank_finalize(hb_bank_t* bank);
+int64_t hb_bank_rows(const hb_bank_t* bank);
+int64_t hb_bank_capacity(const hb_bank_t* bank);
+/* Device pointer to the uint16 (rows, num_classes) label histogram table. */
+const uint16_t* hb_bank_label_table(const hb_bank_t* bank);
+/* Export rows [row0, row0+n) as the reference's tensors: feats_out_dev fp32 (n, d)
+ * unit-norm rows (fp32 copy if kept, else widened bf16) and/or labels_out_dev fp32
+ * (n, num_classes) soft labels (feature_memory / label_memory, hbird_eval.py:357-366).
+ * Either output may be NULL. */
+int hb_bank_export(const hb_bank_t* bank, int64_t row0, int64_t n, float* feats_out_dev,
+                   float* labels_out_dev, void* stream);
+
+/* ---- K2 + K2b: search ----------------------------------------------------------------
+ * Replaces NearestNeighborSearchFaiss.find_nearest_neighbors (search_faiss.py:83-90),
+ * i.e. GpuIndexFlatIP.search: exact top-k by inner product of the raw (un-normalised)
+ * queries against the unit-norm bank rows, sorted by descending score.
+ * q_dev: fp32 (Q, d).  k <= k_prime, k_prime in {32, 64, 128}: the tcgen05 bf16 pass keeps
+ * k_prime candidates per query, the fp32 pass re-scores them exactly and keeps k.
+ * out_scores_dev fp32 (Q, k); out_idx_dev int64 (Q, k) = row index + idx_offset (the
+ * shard's first global row); out_qnorm_dev fp32 (Q,) = ||q||_2 or NULL.  If the bank
+ * holds fewer than k rows the tail is (-inf, -1), as faiss pads. */
+int hb_search(hb_bank_t* bank, const float* q_dev, int64_t Q, int k, int k_prime,
+              int64_t idx_offset, float* out_scores_dev, int64_t* out_idx_dev,
+              float* out_qnorm_dev, void* stream);
+
+/* Tuning/diagnostics for hb_search: cta_group (1 or 2; 0 = library default),
+ * max_chunks (bank split per query block; 0 = auto). */
+int hb_search_config(hb_bank_t* bank, int cta_group, int max_chunks);
+/* Number of kernel launches the last hb_search on this bank issued. */
+int hb_search_last_launches(const hb_bank_t* bank);
+
+/* Debug/validation: full bf16-input fp32-accumulate score matrix of the tcgen05 pass,
+ * out_dev fp32 (Q, rows).  Small problems only (Q*rows*4 bytes are written). */
+int hb_search_dump_scores(hb_bank_t* bank, const float* q_dev, int64_t Q, float* out_dev,
+                          int cta_group, void* stream);
+
+/* ---- K3: cross-shard merge -------------------------------------------------------------
+ * Replaces the host-side merge of faiss.IndexShards (search_faiss.py:53-63,89).
+ * shard_scores_dev fp32 (G, Q, k) and shard_idx_dev int64 (G, Q, k) are the all-gathered
+ * per-shard results (each sorted descending, global indices).  Writes the top-k of the
+ * union per query, sorted descending (ties: smaller index first). */
+int hb_merge_topk(const float* shard_scores_dev, const int64_t* shard_idx_dev, int G,
+                  int64_t Q, int k, float* out_scores_dev, int64_t* out_idx_dev,
+                  void* stream);
+
+/* ---- K4: label transfer ------------------------------------------------------------------
+ * Replaces the neighbour gather (hbird_eval.py:611-637) and _cross_attention
+ * (hbird_eval.py:575-609): label_hat[q] = sum_j softmax_j(cos(q, m_j)/beta) * soft_label[idx_j]
+ * with cos(q, m_j) = score_j / ||q|| (bank rows are unit norm), soft_label = hist/patch_pixels.
+ * label_table_dev: uint16 (table_rows, C) indexed by the (global) indices in idx_dev.
+ * Entries with idx < 0 are skipped.  out_label_hat_dev fp32 (Q, C). */
+int hb_label_transfer(const uint16_t* label_table_dev, int64_t table_rows, int C,
+                      int patch_pixels, const float* scores_dev, const int64_t* idx_dev,
+                      const float* qnorm_dev, int64_t Q, int k, float beta,
+                      float* out_label_hat_dev, void* stream);
+
+/* Replaces hbird_eval.py:235-243: label_hat (B, S*S, C) viewed as (B, C, S, S),
+ * F.interpolate(size=(H, W), mode="bilinear", align_corners=False), argmax over C
+ * (first maximum wins).  out_pred_dev uint8 (B, H, W). */
+int hb_upsample_argmax(const float* label_hat_dev, int B, int S, int C, int H, int W,
+                       uint8_t* out_pred_dev, void* stream);
+
+/* ---- K5: scoring --------------------------------------------------------------------------
+ * Replaces the loader-contract decode `(y*255).long()` (hbird_eval.py:219,309-310):
+ * out[i] = (uint8) trunc(y[i]*255); remap_255_to_0 applies `y[y==255]=0` (bank side only). */
+int hb_decode_mask(const float* y_dev, int64_t n, int remap_255_to_0, uint8_t* out_dev,
+                   void* stream);
+
+/* Replaces PredsmIoU.update (eval_metrics.py:73-109): for every pixel with
+ * gt != ignore_index (ignore_index < 0: none), gt < C_gt and pred < C_pred,
+ * conf[gt*C_pred + pred] += 1.  conf_dev: int64 (C_gt, C_pred), accumulated in place. */
+int hb_confusion_accumulate(const uint8_t* gt_dev, const uint8_t* pred_dev, int64_t n,
+                            int C_gt, int C_pred, int ignore_index, int64_t* conf_dev,
+                            void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HBIRD_B200_H_ */

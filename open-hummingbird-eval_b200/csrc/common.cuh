@@ -1,0 +1,121 @@
+// Shared host/device helpers for the hbird_b200 C-ABI library (sm_100a only).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "hbird_b200.h"
+
+namespace hb {
+
+// ---- host: error reporting ------------------------------------------------------
+void set_error(const char* fmt, ...);
+void clear_error();
+
+#define HB_CHECK_CUDA(expr)                                                              \
+  do {                                                                                   \
+    cudaError_t e__ = (expr);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      hb::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr,                   \
+                    cudaGetErrorString(e__));                                            \
+      return (e__ == cudaErrorMemoryAllocation) ? HB_ERR_OOM : HB_ERR_CUDA;              \
+    }                                                                                    \
+  } while (0)
+
+#define HB_REQUIRE(cond, ...)                                                            \
+  do {                                                                                   \
+    if (!(cond)) {                                                                       \
+      hb::set_error(__VA_ARGS__);                                                        \
+      return HB_ERR_INVALID;                                                             \
+    }                                                                                    \
+  } while (0)
+
+// One shard of the memory bank, resident in HBM.
+struct Bank {
+  int device = 0;
+  int num_sms = 0;
+  int d = 0;          // feature dim
+  int dpad = 0;       // bf16 row pitch in elements (multiple of 64)
+  int C = 0;          // classes
+  int pp = 0;         // pixels per patch (ps*ps)
+  unsigned flags = 0;
+  int64_t capacity = 0;
+  int64_t rows = 0;
+  bool finalized = false;
+  __nv_bfloat16* feat_bf16 = nullptr;  // (capacity, dpad)
+  float* feat_f32 = nullptr;           // (capacity, d) if HB_BANK_KEEP_F32
+  uint16_t* label_hist = nullptr;      // (capacity, C)
+  CUtensorMap tmap_bank_cg1;           // box (64, 256)
+  CUtensorMap tmap_bank_cg2;           // box (64, 128)
+  // search scratch (grown on demand, owned by the bank)
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  int cfg_cta_group = 0;
+  int cfg_max_chunks = 0;
+  int last_launches = 0;
+};
+
+int ensure_workspace(Bank* b, size_t bytes);
+// Encode a 2-D bf16 row-major (rows, cols_pad) tensor map with a (64 x box_rows) box and
+// 128-byte swizzle.  Resolved through cudaGetDriverEntryPoint: no link-time libcuda.
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, int64_t rows, int cols_pad,
+                      int box_rows);
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- device: small utilities --------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// Order-preserving map float -> uint32 (larger float <=> larger uint); NaN never passes the
+// `>` filters upstream so it is not special-cased here.
+__host__ __device__ __forceinline__ uint32_t f32_to_ordered(float f) {
+  uint32_t b;
+#ifdef __CUDA_ARCH__
+  b = __float_as_uint(f);
+#else
+  __builtin_memcpy(&b, &f, 4);
+#endif
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ordered_to_f32(uint32_t u) {
+  uint32_t b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(b);
+#else
+  float f;
+  __builtin_memcpy(&f, &b, 4);
+  return f;
+#endif
+}
+// Candidate key: high word = ordered score, low word = ~row so that among equal scores the
+// smaller row index is the larger key (faiss keeps the smaller id first on ties).
+__host__ __device__ __forceinline__ uint64_t make_key(float score, uint32_t row) {
+  return (static_cast<uint64_t>(f32_to_ordered(score)) << 32) | static_cast<uint32_t>(~row);
+}
+__host__ __device__ __forceinline__ float key_score(uint64_t k) {
+  return ordered_to_f32(static_cast<uint32_t>(k >> 32));
+}
+__host__ __device__ __forceinline__ uint32_t key_row(uint64_t k) {
+  return ~static_cast<uint32_t>(k);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace hb

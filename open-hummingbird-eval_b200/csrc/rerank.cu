@@ -1,0 +1,232 @@
+// K2b — exact fp32 re-rank, and K3 — cross-shard merge.
+// K2b restores the reference metric: the k' candidates per query that survive the bf16 tensor-core
+// pass are re-scored as fp32 dot products of the ORIGINAL fp32 query with the fp32 copy of the
+// unit-norm bank row — the arithmetic GpuIndexFlatIP performs (search_faiss.py:39-41,89) — and the
+// top-k of those, sorted by descending score (ties: smaller row first), is what hb_search returns.
+// HBM-bound gather: k' * d * 4 bytes per query.
+#include "common.cuh"
+
+namespace hb {
+
+// Sort 32*R keys held R per lane (element e = r*32 + lane) across one warp, bitonic network.
+template <int R, bool DESC>
+__device__ __forceinline__ void warp_bitonic_sort(uint64_t (&a)[R], int lane) {
+  constexpr int n = 32 * R;
+#pragma unroll
+  for (int k = 2; k <= n; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j < 32) {
+        // partner lives in lane ^ j, same register slot
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int e = r * 32 + lane;
+          const uint64_t other = __shfl_xor_sync(0xffffffffu, a[r], j);
+          const bool lower = (e & j) == 0;
+          const bool asc = ((e & k) == 0) != DESC;
+          const uint64_t lo = a[r] < other ? a[r] : other;
+          const uint64_t hi = a[r] < other ? other : a[r];
+          a[r] = (lower == asc) ? lo : hi;
+        }
+      } else {
+        // partner lives in this lane, register slot r ^ (j/32)
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int jr = j >> 5;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if ((r & jr) == 0) {
+            const int r2 = r | jr;
+            const int e = r * 32 + lane;
+            const bool asc = ((e & k) == 0) != DESC;
+            const uint64_t lo = a[r] < a[r2] ? a[r] : a[r2];
+            const uint64_t hi = a[r] < a[r2] ? a[r2] : a[r];
+            a[r] = asc ? lo : hi;
+            a[r2] = asc ? hi : lo;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int R>
+__global__ void __launch_bounds__(128)
+rerank_kernel(const float* __restrict__ q, const float* __restrict__ bank_f32,
+              const __nv_bfloat16* __restrict__ bank_bf16, const uint64_t* __restrict__ cand,
+              int n_chunks, int64_t q_pad, int64_t Q, int d, int dpad, int k, int64_t idx_offset,
+              float* __restrict__ out_scores, int64_t* __restrict__ out_idx) {
+  constexpr int KP = 32 * R;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t qi = static_cast<int64_t>(blockIdx.x) * 4 + warp;
+  if (qi >= Q) return;
+
+  // ---- union of the per-chunk candidate lists -> best k' by the bf16-pass score ----
+  uint64_t top[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) top[r] = cand[qi * KP + r * 32 + lane];
+  warp_bitonic_sort<R, true>(top, lane);
+  for (int c = 1; c < n_chunks; ++c) {
+    uint64_t nxt[R];
+    const uint64_t* src = cand + (static_cast<int64_t>(c) * q_pad + qi) * KP;
+#pragma unroll
+    for (int r = 0; r < R; ++r) nxt[r] = src[r * 32 + lane];
+    warp_bitonic_sort<R, false>(nxt, lane);
+    // top descending, nxt ascending: the element-wise max holds the k' largest of the union
+#pragma unroll
+    for (int r = 0; r < R; ++r) top[r] = top[r] > nxt[r] ? top[r] : nxt[r];
+    warp_bitonic_sort<R, true>(top, lane);
+  }
+
+  // ---- exact fp32 scores of the k' candidates ----
+  const float4* q4 = reinterpret_cast<const float4*>(q + qi * d);
+  const int d4 = d >> 2;
+  uint64_t exact[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    exact[r] = 0ull;
+    for (int c0 = 0; c0 < 32; c0 += 4) {
+      uint32_t rows[4];
+      bool valid[4];
+      float acc[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint64_t key = __shfl_sync(0xffffffffu, top[r], c0 + u);
+        valid[u] = key != 0ull;
+        rows[u] = valid[u] ? key_row(key) : 0u;
+        acc[u] = 0.f;
+      }
+      if (bank_f32 != nullptr) {
+        for (int i = lane; i < d4; i += 32) {
+          const float4 qv = __ldg(q4 + i);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float4 m = __ldg(reinterpret_cast<const float4*>(bank_f32 + static_cast<int64_t>(rows[u]) * d) + i);
+            acc[u] += qv.x * m.x + qv.y * m.y + qv.z * m.z + qv.w * m.w;
+          }
+        }
+      } else {
+        for (int i = lane; i < d4; i += 32) {
+          const float4 qv = __ldg(q4 + i);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint2 pk = __ldg(reinterpret_cast<const uint2*>(bank_bf16 + static_cast<int64_t>(rows[u]) * dpad) + i);
+            const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&pk.x);
+            const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&pk.y);
+            acc[u] += qv.x * __low2float(lo) + qv.y * __high2float(lo) + qv.z * __low2float(hi) + qv.w * __high2float(hi);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float s = warp_sum(acc[u]);
+        if (lane == c0 + u && valid[u]) exact[r] = make_key(s, rows[u]);
+      }
+    }
+  }
+  warp_bitonic_sort<R, true>(exact, lane);
+
+  // ---- emit the top-k ----
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int e = r * 32 + lane;
+    if (e < k) {
+      const bool ok = exact[r] != 0ull;
+      out_scores[qi * k + e] = ok ? key_score(exact[r]) : -INFINITY;
+      out_idx[qi * k + e] = ok ? static_cast<int64_t>(key_row(exact[r])) + idx_offset : -1;
+    }
+  }
+}
+
+int rerank_launch(const Bank* b, const float* q, const float* qnorm_ws, int64_t Q, int k, int kp,
+                  int n_chunks, int64_t q_pad, const uint64_t* cand, int64_t idx_offset,
+                  float* out_scores, int64_t* out_idx, cudaStream_t st) {
+  (void)qnorm_ws;
+  const unsigned blocks = static_cast<unsigned>(ceil_div64(Q, 4));
+#define HB_RERANK(R)                                                                              \
+  rerank_kernel<R><<<blocks, 128, 0, st>>>(q, b->feat_f32, b->feat_bf16, cand, n_chunks, q_pad, Q, \
+                                           b->d, b->dpad, k, idx_offset, out_scores, out_idx)
+  if (kp == 32) HB_RERANK(1);
+  else if (kp == 64) HB_RERANK(2);
+  else if (kp == 128) HB_RERANK(4);
+  else {
+    set_error("rerank: k_prime=%d not in {32, 64, 128}", kp);
+    return HB_ERR_INVALID;
+  }
+#undef HB_RERANK
+  HB_CHECK_CUDA(cudaGetLastError());
+  return HB_OK;
+}
+
+// K3: merge G per-shard sorted top-k lists per query.  One warp per query; k <= 128.
+template <int R>
+__global__ void __launch_bounds__(128)
+merge_topk_kernel(const float* __restrict__ ss, const int64_t* __restrict__ si, int G, int64_t Q,
+                  int k, float* __restrict__ out_scores, int64_t* __restrict__ out_idx) {
+  // keys here carry a 64-bit index, so sort (ordered score, then index) pairs held as two words
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t qi = static_cast<int64_t>(blockIdx.x) * 4 + warp;
+  if (qi >= Q) return;
+  // candidate slots: position in the gathered (G, k) list, encoded as g*k + j in the low word
+  uint64_t top[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) top[r] = 0ull;
+  const int total = G * k;
+  for (int base = 0; base < total; base += 32 * R) {
+    uint64_t nxt[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int e = base + r * 32 + lane;
+      nxt[r] = 0ull;
+      if (e < total) {
+        const int g = e / k, j = e % k;
+        const int64_t off = (static_cast<int64_t>(g) * Q + qi) * k + j;
+        const int64_t id = si[off];
+        // position e doubles as the tie-break: shards hold ascending global rows, and within a
+        // shard ties are already ordered by row, so smaller e <=> smaller global index
+        if (id >= 0) nxt[r] = make_key(ss[off], static_cast<uint32_t>(e));
+      }
+    }
+    warp_bitonic_sort<R, false>(nxt, lane);
+#pragma unroll
+    for (int r = 0; r < R; ++r) top[r] = top[r] > nxt[r] ? top[r] : nxt[r];
+    warp_bitonic_sort<R, true>(top, lane);
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int e = r * 32 + lane;
+    if (e < k) {
+      const bool ok = top[r] != 0ull;
+      int64_t id = -1;
+      float s = -INFINITY;
+      if (ok) {
+        const uint32_t pos = key_row(top[r]);
+        const int g = pos / k, j = pos % k;
+        const int64_t off = (static_cast<int64_t>(g) * Q + qi) * k + j;
+        id = si[off];
+        s = ss[off];
+      }
+      out_scores[qi * k + e] = s;
+      out_idx[qi * k + e] = id;
+    }
+  }
+}
+
+}  // namespace hb
+
+extern "C" int hb_merge_topk(const float* shard_scores_dev, const int64_t* shard_idx_dev, int G,
+                             int64_t Q, int k, float* out_scores_dev, int64_t* out_idx_dev,
+                             void* stream) {
+  HB_REQUIRE(G >= 1 && G <= 1024, "hb_merge_topk: G=%d not in [1, 1024]", G);
+  HB_REQUIRE(k >= 1 && k <= 128, "hb_merge_topk: k=%d not in [1, 128]", k);
+  HB_REQUIRE(Q >= 0, "hb_merge_topk: Q < 0");
+  if (Q == 0) return HB_OK;
+  HB_REQUIRE(shard_scores_dev && shard_idx_dev && out_scores_dev && out_idx_dev, "hb_merge_topk: NULL pointer");
+  const unsigned blocks = static_cast<unsigned>(hb::ceil_div64(Q, 4));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (k <= 32) hb::merge_topk_kernel<1><<<blocks, 128, 0, st>>>(shard_scores_dev, shard_idx_dev, G, Q, k, out_scores_dev, out_idx_dev);
+  else if (k <= 64) hb::merge_topk_kernel<2><<<blocks, 128, 0, st>>>(shard_scores_dev, shard_idx_dev, G, Q, k, out_scores_dev, out_idx_dev);
+  else hb::merge_topk_kernel<4><<<blocks, 128, 0, st>>>(shard_scores_dev, shard_idx_dev, G, Q, k, out_scores_dev, out_idx_dev);
+  HB_CHECK_CUDA(cudaGetLastError());
+  return HB_OK;
+}

@@ -1,0 +1,471 @@
+// K2 — the search: S = Q . Bank^T on the 5th-gen tensor cores with the top-k' selection fused
+// into the epilogue, so the (Q x N) score matrix never leaves the SM.
+// Replaces GpuIndexFlatIP.search as called from search_faiss.py:83-90 (first, bf16 pass; the
+// exact fp32 re-rank that restores the reference's metric is K2b in rerank.cu).
+//
+// Structure (one persistent CTA, or CTA pair with cta_group::2, per SM):
+//   warp 0      TMA producer: streams 128x64 query tiles and (256/CG)x64 bank tiles (bf16,
+//               128B-swizzled) through a STAGES-deep shared-memory ring.
+//   warp 1      tcgen05.mma issuer (one lane; pair leader only): 128*CG x 256 x 16 UMMAs into one
+//               of two 256-column TMEM accumulators; tcgen05.commit frees ring slots and
+//               publishes finished accumulators.  Also owns TMEM alloc/dealloc.
+//   warps 2..5  epilogue: each thread owns ONE query row (TMEM lane).  It scans the 256 scores of
+//               a tile with a running threshold tau = its current k'-th best; survivors are pushed
+//               into a per-thread min-heap of k' (score,row) keys in shared memory.  Accumulator
+//               double-buffering overlaps this scan with the MMAs of the next tile.
+// Work item = (query block of 128*CG rows) x (bank chunk of consecutive 256-row tiles); items are
+// dealt round-robin to the persistent CTAs so that concurrently running CTAs walk the same bank
+// tiles (L2 reuse) with different queries.  Each item emits k' unsorted candidate keys per query.
+#include <algorithm>
+
+#include "common.cuh"
+#include "ptx.cuh"
+#include "search_plan.h"
+
+namespace hb {
+
+constexpr int BM = 128;   // query rows per CTA (TMEM lanes)
+constexpr int BN = 256;   // bank rows per tile (UMMA N)
+constexpr int BK = 64;    // bf16 per k-block: one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kEpiWarps = 4;
+constexpr int kSearchThreads = 32 * (2 + kEpiWarps);
+constexpr int kTmemCols = 512;
+
+struct SearchParams {
+  int64_t n_rows;      // valid bank rows
+  int64_t n_queries;   // valid query rows
+  int num_kblocks;     // dpad / 64
+  int n_qblocks;       // query blocks of 128*CG rows
+  int n_chunks;        // bank chunks per query block
+  int n_tiles;         // ceil(n_rows / 256)
+  uint64_t* cand;      // (n_chunks, n_qblocks*128*CG, KP) candidate keys
+  float* dump;         // optional (n_queries, n_rows) raw scores (validation only)
+};
+
+template <int CG, int STAGES, int KP>
+struct SearchSmem {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = (BN / CG) * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kRingBytes = STAGES * kStageBytes;
+  static constexpr int kHeapBytes = KP * BM * 8;
+  static constexpr int kBarOffset = kRingBytes + kHeapBytes;
+  static constexpr int kNumBars = 2 * STAGES + 4;
+  static constexpr int kTotal = kBarOffset + kNumBars * 8 + 16;
+  static constexpr int kDynamic = kTotal + 1024;  // slack to align the ring to 1024 B
+};
+
+// Replace the heap root (current k'-th best) with `key` and restore the min-heap property.
+// Entry j of epilogue thread t lives at heap[j*BM + t]: conflict-free for any per-lane j.
+template <int KP>
+__device__ __forceinline__ void heap_replace_root(uint64_t* heap, uint64_t key) {
+  int i = 0;
+  while (true) {
+    const int l = 2 * i + 1;
+    if (l >= KP) break;
+    const int r = l + 1;
+    const uint64_t kl = heap[l * BM];
+    const uint64_t kr = (r < KP) ? heap[r * BM] : ~0ull;
+    const bool right = kr < kl;
+    const uint64_t kc = right ? kr : kl;
+    if (kc >= key) break;
+    heap[i * BM] = kc;
+    i = right ? r : l;
+  }
+  heap[i * BM] = key;
+}
+
+template <int CG, int STAGES, int KP>
+__global__ void __launch_bounds__(kSearchThreads, 1)
+search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
+                   const __grid_constant__ CUtensorMap tmap_bank, const SearchParams p) {
+  using L = SearchSmem<CG, STAGES, KP>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
+  const uint32_t smem_base = raw_addr + pad;
+
+  uint64_t* heap_base = reinterpret_cast<uint64_t*>(smem + L::kRingBytes);
+  const uint32_t bar_base = smem_base + L::kBarOffset;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kBarOffset + L::kNumBars * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;
+  const bool is_leader = cta_rank == 0;
+  const int cluster_id = (CG == 2) ? static_cast<int>(ptx::cluster_id_x()) : static_cast<int>(blockIdx.x);
+  const int n_clusters = (CG == 2) ? static_cast<int>(ptx::num_clusters_x()) : static_cast<int>(gridDim.x);
+
+  // ---- one-time setup ----
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_q);
+    ptx::prefetch_tmap(&tmap_bank);
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(tfull_bar(b), 1);
+      ptx::mbar_init(tempty_bar(b), kEpiWarps * CG);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc<CG>(smem_u32(tmem_slot), kTmemCols);
+    ptx::tmem_relinquish<CG>();
+  }
+  ptx::tc_fence_before();
+  if (CG == 2) ptx::cluster_sync_all(); else __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_items = p.n_qblocks * p.n_chunks;
+  const int nkb = p.num_kblocks;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t full_target_rank0 = (CG == 2) ? 0u : 0u;
+    (void)full_target_rank0;
+    for (int item = cluster_id; item < total_items; item += n_clusters) {
+      const int qb = item % p.n_qblocks, chunk = item / p.n_qblocks;
+      const int t0 = chunk_tile_begin(p.n_tiles, p.n_chunks, chunk);
+      const int t1 = chunk_tile_begin(p.n_tiles, p.n_chunks, chunk + 1);
+      const int32_t q_row = (qb * CG + static_cast<int>(cta_rank)) * BM;
+      for (int tile = t0; tile < t1; ++tile) {
+        const int32_t b_row = tile * BN + static_cast<int>(cta_rank) * (BN / CG);
+        for (int kb = 0; kb < nkb; ++kb) {
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u, 1);
+          if (lane == 0) {
+            const uint32_t a_dst = smem_base + stage * L::kStageBytes;
+            const uint32_t b_dst = a_dst + L::kABytes;
+            uint32_t bar = full_bar(stage);
+            if (CG == 2) bar = ptx::mapa(bar, 0);  // completion bytes go to the pair leader
+            if (is_leader) ptx::mbar_arrive_expect_tx(full_bar(stage), L::kStageBytes * CG);
+            ptx::tma_load_2d<CG>(a_dst, &tmap_q, bar, kb * BK, q_row);
+            ptx::tma_load_2d<CG>(b_dst, &tmap_bank, bar, kb * BK, b_row);
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (is_leader) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(BM * CG, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int abuf = 0;
+      uint32_t aphase = 0;
+      for (int item = cluster_id; item < total_items; item += n_clusters) {
+        const int chunk = item / p.n_qblocks;
+        const int t0 = chunk_tile_begin(p.n_tiles, p.n_chunks, chunk);
+        const int t1 = chunk_tile_begin(p.n_tiles, p.n_chunks, chunk + 1);
+        for (int tile = t0; tile < t1; ++tile) {
+          ptx::mbar_wait(tempty_bar(abuf), aphase ^ 1u, 2);  // epilogue drained this accumulator
+          ptx::tc_fence_after();
+          const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(abuf * BN);
+          for (int kb = 0; kb < nkb; ++kb) {
+            ptx::mbar_wait(full_bar(stage), phase, 3);  // TMA bytes have landed
+            ptx::tc_fence_after();
+            if (lane == 0) {
+              const uint32_t a_addr = smem_base + stage * L::kStageBytes;
+              const uint64_t adesc = ptx::make_smem_desc_sw128(a_addr);
+              const uint64_t bdesc = ptx::make_smem_desc_sw128(a_addr + L::kABytes);
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                // advance 16 bf16 = 32 B inside the swizzle atom: +2 in the (addr >> 4) field
+                ptx::umma_bf16<CG>(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc,
+                                   static_cast<uint32_t>((kb | k) != 0));
+              }
+              ptx::umma_commit<CG>(empty_bar(stage));  // frees the ring slot when the MMAs retire
+              if (kb == nkb - 1) ptx::umma_commit<CG>(tfull_bar(abuf));  // accumulator complete
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+          abuf ^= 1;
+          if (abuf == 0) aphase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // =========================== epilogue: fused top-k' ===========================
+    const int quarter = warp & 3;               // TMEM lane quarter this warp may read
+    const int row_in_tile = quarter * 32 + lane;  // query row owned by this thread
+    uint64_t* heap = heap_base + row_in_tile;
+    const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t tempty_leader0 = (CG == 2) ? ptx::mapa(tempty_bar(0), 0) : tempty_bar(0);
+    const uint32_t tempty_leader1 = (CG == 2) ? ptx::mapa(tempty_bar(1), 0) : tempty_bar(1);
+    int abuf = 0;
+    uint32_t aphase = 0;
+    for (int item = cluster_id; item < total_items; item += n_clusters) {
+      const int qb = item % p.n_qblocks, chunk = item / p.n_qblocks;
+      const int t0 = chunk_tile_begin(p.n_tiles, p.n_chunks, chunk);
+      const int t1 = chunk_tile_begin(p.n_tiles, p.n_chunks, chunk + 1);
+      const int64_t q_row = static_cast<int64_t>(qb * CG + static_cast<int>(cta_rank)) * BM + row_in_tile;
+#pragma unroll 4
+      for (int j = 0; j < KP; ++j) heap[j * BM] = 0ull;  // key 0 sorts below every real score
+      float tau = -INFINITY;
+      for (int tile = t0; tile < t1; ++tile) {
+        ptx::mbar_wait(tfull_bar(abuf), aphase, 4);
+        ptx::tc_fence_after();
+        const int64_t col_base = static_cast<int64_t>(tile) * BN;
+        const int64_t rem = p.n_rows - col_base;
+        const int nvalid = rem >= BN ? BN : static_cast<int>(rem);
+        const uint32_t tacc = tmem_lane + static_cast<uint32_t>(abuf * BN);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          if (c0 >= nvalid) break;  // warp-uniform
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(tacc + c0, v);
+          ptx::tmem_ld_wait();
+          if (p.dump != nullptr && q_row < p.n_queries) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c0 + j < nvalid) p.dump[q_row * p.n_rows + col_base + c0 + j] = __uint_as_float(v[j]);
+          }
+          const uint32_t vmask = (nvalid - c0 >= 32) ? 0xffffffffu : ((1u << (nvalid - c0)) - 1u);
+          // fast reject: one max-tree over the 32 columns, one compare, one vote
+          float m = -INFINITY;
+          if (vmask == 0xffffffffu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if ((vmask >> j) & 1u) m = fmaxf(m, __uint_as_float(v[j]));
+          }
+          if (__any_sync(0xffffffffu, m > tau)) {
+            uint32_t mine = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mine |= (__uint_as_float(v[j]) > tau ? 1u : 0u) << j;
+            mine &= vmask;
+            uint32_t todo = __reduce_or_sync(0xffffffffu, mine);
+            while (todo) {
+              const int j = __ffs(todo) - 1;
+              todo &= todo - 1;
+              // registers cannot be indexed by a run-time j: re-read the column from TMEM
+              const float x = __uint_as_float(ptx::tmem_ld_32x32b_x1(tacc + c0 + j));
+              ptx::tmem_ld_wait();
+              if (((mine >> j) & 1u) && x > tau) {
+                heap_replace_root<KP>(heap, make_key(x, static_cast<uint32_t>(col_base + c0 + j)));
+                tau = key_score(heap[0]);
+              }
+            }
+          }
+        }
+        // release the accumulator to the MMA issuer (pair leader's barrier)
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          const uint32_t bar = abuf ? tempty_leader1 : tempty_leader0;
+          if (CG == 2) ptx::mbar_arrive_cluster(bar); else ptx::mbar_arrive_local(bar);
+        }
+        abuf ^= 1;
+        if (abuf == 0) aphase ^= 1u;
+      }
+      // emit this item's k' candidates (unsorted; the re-rank kernel orders them)
+      const int64_t q_pad = static_cast<int64_t>(p.n_qblocks) * BM * CG;
+      uint64_t* out = p.cand + (static_cast<int64_t>(chunk) * q_pad + q_row) * KP;
+#pragma unroll 4
+      for (int j = 0; j < KP; ++j) out[j] = heap[j * BM];
+    }
+  }
+
+  // ---- teardown ----
+  ptx::tc_fence_before();
+  if (CG == 2) ptx::cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<CG>(tmem_base, kTmemCols);
+  }
+}
+
+// Query preparation: fp32 (Q, d) -> bf16 (Q, dpad) zero padded, plus ||q||_2.
+// (hbird_eval.py:624-625 hands the raw, un-normalised query rows to the backend.)
+__global__ void __launch_bounds__(256)
+prep_queries_kernel(const float* __restrict__ q, int64_t Q, int d, int dpad,
+                    __nv_bfloat16* __restrict__ qb, float* __restrict__ qnorm) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d4 = d >> 2;
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp; row < Q;
+       row += static_cast<int64_t>(gridDim.x) * 8) {
+    const float4* in4 = reinterpret_cast<const float4*>(q + row * d);
+    __nv_bfloat16* ob = qb + row * dpad;
+    float ss = 0.f;
+    for (int i = lane; i < d4; i += 32) {
+      const float4 v = __ldg(in4 + i);
+      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
+      __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(ob + 4 * i) = pk;
+    }
+    for (int i = d + lane; i < dpad; i += 32) ob[i] = __float2bfloat16(0.f);
+    ss = warp_sum(ss);
+    if (lane == 0 && qnorm) qnorm[row] = sqrtf(ss);
+  }
+}
+
+template <int CG, int STAGES, int KP>
+static int launch_search(const Bank* b, const CUtensorMap& tmap_q, const SearchParams& p,
+                         cudaStream_t st) {
+  using L = SearchSmem<CG, STAGES, KP>;
+  auto kern = search_topk_kernel<CG, STAGES, KP>;
+  HB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic));
+  const int n_clusters = std::max(1, std::min(b->num_sms / CG, p.n_qblocks * p.n_chunks));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(n_clusters * CG));
+  cfg.blockDim = dim3(kSearchThreads);
+  cfg.dynamicSmemBytes = L::kDynamic;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const CUtensorMap& tmap_b = (CG == 2) ? b->tmap_bank_cg2 : b->tmap_bank_cg1;
+  HB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmap_q, tmap_b, p));
+  return HB_OK;
+}
+
+// Dispatch over (cta_group, k').  Ring depth is what fits beside the k' heap in 227 KB.
+static int dispatch_search(const Bank* b, int cg, int kp, const CUtensorMap& tmap_q,
+                           const SearchParams& p, cudaStream_t st) {
+  if (cg == 2) {
+    if (kp == 32) return launch_search<2, 5, 32>(b, tmap_q, p, st);
+    if (kp == 64) return launch_search<2, 4, 64>(b, tmap_q, p, st);
+    if (kp == 128) return launch_search<2, 3, 128>(b, tmap_q, p, st);
+  } else {
+    if (kp == 32) return launch_search<1, 3, 32>(b, tmap_q, p, st);
+    if (kp == 64) return launch_search<1, 3, 64>(b, tmap_q, p, st);
+    if (kp == 128) return launch_search<1, 2, 128>(b, tmap_q, p, st);
+  }
+  set_error("hb_search: k_prime=%d not in {32, 64, 128}", kp);
+  return HB_ERR_INVALID;
+}
+
+int rerank_launch(const Bank* b, const float* q, const float* qnorm_ws, int64_t Q, int k, int kp,
+                  int n_chunks, int64_t q_pad, const uint64_t* cand, int64_t idx_offset,
+                  float* out_scores, int64_t* out_idx, cudaStream_t st);  // rerank.cu
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_t idx_offset,
+                       float* out_scores, int64_t* out_idx, float* out_qnorm, float* dump, int cg_override,
+                       cudaStream_t st) {
+  int cg = cg_override ? cg_override : (b->cfg_cta_group ? b->cfg_cta_group : 2);
+  if (b->num_sms < 2) cg = 1;
+  const SearchPlan plan = plan_search(b->rows, Q, cg, b->num_sms, b->cfg_max_chunks);
+  const int64_t q_pad = static_cast<int64_t>(plan.n_qblocks) * BM * cg;
+
+  // scratch: bf16 queries | norms | candidate keys
+  const size_t off_q = 0;
+  const size_t off_norm = align_up(off_q + sizeof(__nv_bfloat16) * static_cast<size_t>(Q) * b->dpad, 256);
+  const size_t off_cand = align_up(off_norm + sizeof(float) * static_cast<size_t>(Q), 256);
+  const size_t total = off_cand + sizeof(uint64_t) * static_cast<size_t>(plan.n_chunks) * q_pad * kp;
+  int rc = ensure_workspace(b, total);
+  if (rc != HB_OK) return rc;
+  uint8_t* ws = static_cast<uint8_t*>(b->ws);
+  __nv_bfloat16* q_bf16 = reinterpret_cast<__nv_bfloat16*>(ws + off_q);
+  float* qnorm = out_qnorm ? out_qnorm : reinterpret_cast<float*>(ws + off_norm);
+  uint64_t* cand = reinterpret_cast<uint64_t*>(ws + off_cand);
+
+  b->last_launches = 0;
+  int64_t blocks = std::min<int64_t>(ceil_div64(Q, 8), static_cast<int64_t>(b->num_sms) * 8);
+  prep_queries_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(q, Q, b->d, b->dpad, q_bf16, qnorm);
+  HB_CHECK_CUDA(cudaGetLastError());
+  b->last_launches++;
+
+  CUtensorMap tmap_q;
+  rc = make_tmap_2d_bf16(&tmap_q, q_bf16, Q, b->dpad, BM);
+  if (rc != HB_OK) return rc;
+
+  SearchParams p;
+  p.n_rows = b->rows;
+  p.n_queries = Q;
+  p.num_kblocks = b->dpad / BK;
+  p.n_qblocks = plan.n_qblocks;
+  p.n_chunks = plan.n_chunks;
+  p.n_tiles = plan.n_tiles;
+  p.cand = cand;
+  p.dump = dump;
+  rc = dispatch_search(b, cg, kp, tmap_q, p, st);
+  if (rc != HB_OK) return rc;
+  b->last_launches++;
+  if (out_scores == nullptr) return HB_OK;  // dump-only call
+
+  rc = rerank_launch(b, q, qnorm, Q, k, kp, plan.n_chunks, q_pad, cand, idx_offset, out_scores, out_idx, st);
+  if (rc != HB_OK) return rc;
+  b->last_launches++;
+  return HB_OK;
+}
+
+}  // namespace hb
+
+using hb::Bank;
+
+extern "C" {
+
+int hb_search(hb_bank_t* bank, const float* q_dev, int64_t Q, int k, int k_prime, int64_t idx_offset,
+              float* out_scores_dev, int64_t* out_idx_dev, float* out_qnorm_dev, void* stream) {
+  HB_REQUIRE(bank != nullptr, "hb_search: bank is NULL");
+  Bank* b = reinterpret_cast<Bank*>(bank);
+  if (!b->finalized) {
+    hb::set_error("hb_search: bank not finalized (call hb_bank_finalize first)");
+    return HB_ERR_STATE;
+  }
+  HB_REQUIRE(Q >= 0 && Q < (int64_t(1) << 31), "hb_search: Q=%lld out of range", (long long)Q);
+  HB_REQUIRE(k >= 1 && k <= k_prime, "hb_search: need 1 <= k (%d) <= k_prime (%d)", k, k_prime);
+  HB_REQUIRE(k_prime == 32 || k_prime == 64 || k_prime == 128, "hb_search: k_prime=%d not in {32, 64, 128}", k_prime);
+  if (Q == 0) return HB_OK;
+  HB_REQUIRE(q_dev && out_scores_dev && out_idx_dev, "hb_search: NULL pointer");
+  HB_REQUIRE(b->rows >= 1, "hb_search: the bank is empty");
+  HB_CHECK_CUDA(cudaSetDevice(b->device));
+  return hb::search_impl(b, q_dev, Q, k, k_prime, idx_offset, out_scores_dev, out_idx_dev, out_qnorm_dev,
+                         nullptr, 0, static_cast<cudaStream_t>(stream));
+}
+
+int hb_search_config(hb_bank_t* bank, int cta_group, int max_chunks) {
+  HB_REQUIRE(bank != nullptr, "hb_search_config: bank is NULL");
+  HB_REQUIRE(cta_group >= 0 && cta_group <= 2, "hb_search_config: cta_group=%d not in {0,1,2}", cta_group);
+  HB_REQUIRE(max_chunks >= 0, "hb_search_config: max_chunks < 0");
+  Bank* b = reinterpret_cast<Bank*>(bank);
+  b->cfg_cta_group = cta_group;
+  b->cfg_max_chunks = max_chunks;
+  return HB_OK;
+}
+
+int hb_search_last_launches(const hb_bank_t* bank) {
+  return bank ? reinterpret_cast<const Bank*>(bank)->last_launches : 0;
+}
+
+int hb_search_dump_scores(hb_bank_t* bank, const float* q_dev, int64_t Q, float* out_dev, int cta_group,
+                          void* stream) {
+  HB_REQUIRE(bank != nullptr, "hb_search_dump_scores: bank is NULL");
+  Bank* b = reinterpret_cast<Bank*>(bank);
+  if (!b->finalized) {
+    hb::set_error("hb_search_dump_scores: bank not finalized");
+    return HB_ERR_STATE;
+  }
+  HB_REQUIRE(Q >= 1 && q_dev && out_dev, "hb_search_dump_scores: bad arguments");
+  HB_REQUIRE(cta_group >= 0 && cta_group <= 2, "hb_search_dump_scores: cta_group=%d", cta_group);
+  HB_REQUIRE(Q * b->rows <= (int64_t(1) << 28), "hb_search_dump_scores: Q*rows too large for a debug dump");
+  HB_CHECK_CUDA(cudaSetDevice(b->device));
+  return hb::search_impl(b, q_dev, Q, 1, 64, 0, nullptr, nullptr, nullptr, out_dev, cta_group,
+                         static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,210 @@
+"""Torch-tensor front end of the C-ABI: device memory and streams come from PyTorch, every
+computation is a call into libhbird_b200.so.  No function here has a PyTorch/CPU fallback."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _capi
+from ._capi import check, lib, ptr, stream_ptr
+
+
+def _require_cuda(t: torch.Tensor, name: str, dtype: torch.dtype) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"hbird_b200: `{name}` must be a CUDA tensor (no CPU fallback)")
+    if t.dtype != dtype:
+        raise ValueError(f"hbird_b200: `{name}` must be {dtype}, got {t.dtype}")
+    return t.contiguous()
+
+
+def device_check(device: int = 0) -> int:
+    """SM count of an sm_100 device; raises RuntimeError otherwise (search_faiss.py:14-16)."""
+    import ctypes
+
+    n = ctypes.c_int(0)
+    check(lib.hb_device_check(int(device), ctypes.byref(n)))
+    return n.value
+
+
+class _CudaArray:
+    """Minimal __cuda_array_interface__ view over library-owned HBM."""
+
+    def __init__(self, address: int, shape, typestr: str, owner):
+        self.__cuda_array_interface__ = {
+            "shape": tuple(shape), "typestr": typestr, "data": (address, False), "version": 3, "strides": None,
+        }
+        self._owner = owner
+
+
+class MemoryBank:
+    """One HBM-resident shard of the memory bank (K1).  Mirrors feature_memory / label_memory of
+    hbird_eval.py:156-161,357-366, packed as bf16 rows (+ fp32 copy) and uint16 class histograms."""
+
+    def __init__(self, d: int, num_classes: int, patch_pixels: int, capacity_rows: int,
+                 device: int = 0, keep_f32: bool = True):
+        import ctypes
+
+        self.d, self.num_classes, self.patch_pixels = int(d), int(num_classes), int(patch_pixels)
+        self.device = int(device)
+        self._h = ctypes.c_void_p(0)
+        flags = _capi.HB_BANK_KEEP_F32 if keep_f32 else 0
+        check(lib.hb_bank_create(self.device, self.d, self.num_classes, self.patch_pixels,
+                                 int(capacity_rows), flags, ctypes.byref(self._h)))
+        self.finalized = False
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib.hb_bank_destroy(self._h)
+            self._h.value = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def rows(self) -> int:
+        return int(lib.hb_bank_rows(self._h))
+
+    @property
+    def capacity(self) -> int:
+        return int(lib.hb_bank_capacity(self._h))
+
+    def append(self, feats: torch.Tensor, mask_u8: torch.Tensor, S: int, ps: int,
+               sel: Optional[torch.Tensor] = None) -> None:
+        """feats fp32 (B, S*S, d) raw features; mask_u8 uint8 (B, S*ps, S*ps) decoded class ids;
+        sel optional int32 (n,) flat source-row picks (bounded sampler)."""
+        feats = _require_cuda(feats, "feats", torch.float32)
+        mask_u8 = _require_cuda(mask_u8, "mask", torch.uint8)
+        B = mask_u8.shape[0]
+        if feats.numel() != B * S * S * self.d:
+            raise ValueError(f"feats has {feats.numel()} elements, expected B*S*S*d = {B * S * S * self.d}")
+        if tuple(mask_u8.shape[-2:]) != (S * ps, S * ps):
+            raise ValueError(f"mask spatial size {tuple(mask_u8.shape[-2:])} != (S*ps, S*ps) = {(S * ps, S * ps)}")
+        if sel is not None:
+            sel = _require_cuda(sel, "sel", torch.int32)
+            n = sel.numel()
+        else:
+            n = B * S * S
+        check(lib.hb_bank_append(self._h, ptr(feats), ptr(mask_u8), B, S, ps, ptr(sel), n,
+                                 stream_ptr(feats.device)))
+
+    def append_soft(self, feats: torch.Tensor, soft: torch.Tensor, normalise: bool = False) -> None:
+        feats = _require_cuda(feats, "feats", torch.float32)
+        soft = _require_cuda(soft, "soft", torch.float32)
+        n = feats.shape[0]
+        if feats.shape != (n, self.d) or soft.shape != (n, self.num_classes):
+            raise ValueError("append_soft expects feats (n, d) and soft (n, C)")
+        check(lib.hb_bank_append_soft(self._h, ptr(feats), ptr(soft), n, int(normalise), stream_ptr(feats.device)))
+
+    def finalize(self) -> None:
+        torch.cuda.current_stream(self.device).synchronize()
+        check(lib.hb_bank_finalize(self._h))
+        self.finalized = True
+
+    def label_table(self) -> torch.Tensor:
+        """(rows, C) view of the bank-owned uint16 label histograms (no copy).  Exposed as int16
+        (counts are <= patch_pixels < 32768) because torch/NCCL support for uint16 is partial."""
+        addr = lib.hb_bank_label_table(self._h)
+        arr = _CudaArray(addr, (self.rows, self.num_classes), "<i2", self)
+        with torch.cuda.device(self.device):
+            return torch.as_tensor(arr, device=f"cuda:{self.device}")
+
+    def export(self, row0: int = 0, n: Optional[int] = None, features: bool = True,
+               labels: bool = True) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+        """The reference's (feature_memory (n,d) fp32, label_memory (n,C) fp32) for rows [row0,row0+n)."""
+        n = self.rows - row0 if n is None else n
+        dev = torch.device("cuda", self.device)
+        f = torch.empty((n, self.d), dtype=torch.float32, device=dev) if features else None
+        l = torch.empty((n, self.num_classes), dtype=torch.float32, device=dev) if labels else None
+        check(lib.hb_bank_export(self._h, row0, n, ptr(f), ptr(l), stream_ptr(dev)))
+        return f, l
+
+    def configure_search(self, cta_group: int = 0, max_chunks: int = 0) -> None:
+        check(lib.hb_search_config(self._h, int(cta_group), int(max_chunks)))
+
+    def search(self, q: torch.Tensor, k: int = 30, k_prime: int = 64, idx_offset: int = 0,
+               return_qnorm: bool = True):
+        """K2 + K2b.  q fp32 (Q, d) on the bank's device, raw (un-normalised).  Returns
+        (scores fp32 (Q,k) descending, idx int64 (Q,k), qnorm fp32 (Q,) or None)."""
+        q = _require_cuda(q, "q", torch.float32)
+        if q.dim() != 2 or q.shape[1] != self.d:
+            raise ValueError(f"queries must be (Q, {self.d}), got {tuple(q.shape)}")
+        Q = q.shape[0]
+        scores = torch.empty((Q, k), dtype=torch.float32, device=q.device)
+        idx = torch.empty((Q, k), dtype=torch.int64, device=q.device)
+        qn = torch.empty((Q,), dtype=torch.float32, device=q.device) if return_qnorm else None
+        check(lib.hb_search(self._h, ptr(q), Q, int(k), int(k_prime), int(idx_offset), ptr(scores), ptr(idx),
+                            ptr(qn), stream_ptr(q.device)))
+        return scores, idx, qn
+
+    def last_search_launches(self) -> int:
+        return int(lib.hb_search_last_launches(self._h))
+
+    def dump_scores(self, q: torch.Tensor, cta_group: int = 0) -> torch.Tensor:
+        """Validation only: the full (Q, rows) bf16-input score matrix of the tcgen05 pass."""
+        q = _require_cuda(q, "q", torch.float32)
+        out = torch.full((q.shape[0], self.rows), float("nan"), dtype=torch.float32, device=q.device)
+        check(lib.hb_search_dump_scores(self._h, ptr(q), q.shape[0], ptr(out), int(cta_group), stream_ptr(q.device)))
+        return out
+
+
+def merge_topk(shard_scores: torch.Tensor, shard_idx: torch.Tensor):
+    """K3: (G, Q, k) gathered per-shard results -> (Q, k) global top-k."""
+    shard_scores = _require_cuda(shard_scores, "shard_scores", torch.float32)
+    shard_idx = _require_cuda(shard_idx, "shard_idx", torch.int64)
+    G, Q, k = shard_scores.shape
+    out_s = torch.empty((Q, k), dtype=torch.float32, device=shard_scores.device)
+    out_i = torch.empty((Q, k), dtype=torch.int64, device=shard_scores.device)
+    check(lib.hb_merge_topk(ptr(shard_scores), ptr(shard_idx), G, Q, k, ptr(out_s), ptr(out_i),
+                            stream_ptr(shard_scores.device)))
+    return out_s, out_i
+
+
+def label_transfer(label_table: torch.Tensor, patch_pixels: int, scores: torch.Tensor, idx: torch.Tensor,
+                   qnorm: torch.Tensor, beta: float = 0.02) -> torch.Tensor:
+    """K4a: (Q, C) label_hat from neighbour scores/indices (hbird_eval.py:575-609,611-637)."""
+    label_table = _require_cuda(label_table, "label_table", torch.int16)
+    scores = _require_cuda(scores, "scores", torch.float32)
+    idx = _require_cuda(idx, "idx", torch.int64)
+    qnorm = _require_cuda(qnorm, "qnorm", torch.float32)
+    Q, k = scores.shape
+    rows, C = label_table.shape
+    out = torch.empty((Q, C), dtype=torch.float32, device=scores.device)
+    check(lib.hb_label_transfer(ptr(label_table), rows, C, int(patch_pixels), ptr(scores), ptr(idx), ptr(qnorm),
+                                Q, k, float(beta), ptr(out), stream_ptr(scores.device)))
+    return out
+
+
+def upsample_argmax(label_hat: torch.Tensor, B: int, S: int, H: int, W: int) -> torch.Tensor:
+    """K4b: label_hat fp32 (B*S*S, C) -> uint8 (B, H, W) prediction (hbird_eval.py:235-243)."""
+    label_hat = _require_cuda(label_hat, "label_hat", torch.float32)
+    C = label_hat.shape[-1]
+    if label_hat.numel() != B * S * S * C:
+        raise ValueError("label_hat must hold B*S*S rows")
+    out = torch.empty((B, H, W), dtype=torch.uint8, device=label_hat.device)
+    check(lib.hb_upsample_argmax(ptr(label_hat), B, S, C, H, W, ptr(out), stream_ptr(label_hat.device)))
+    return out
+
+
+def decode_mask(y: torch.Tensor, remap_255_to_0: bool) -> torch.Tensor:
+    """(y*255).long() as uint8, optional 255->0 (hbird_eval.py:219,309-310)."""
+    y = _require_cuda(y, "y", torch.float32)
+    out = torch.empty(y.shape, dtype=torch.uint8, device=y.device)
+    check(lib.hb_decode_mask(ptr(y), y.numel(), int(remap_255_to_0), ptr(out), stream_ptr(y.device)))
+    return out
+
+
+def confusion_accumulate(conf: torch.Tensor, gt_u8: torch.Tensor, pred_u8: torch.Tensor,
+                         ignore_index: Optional[int]) -> None:
+    """K5: conf int64 (C_gt, C_pred) += histogram of (gt, pred) pairs (eval_metrics.py:73-109)."""
+    conf = _require_cuda(conf, "conf", torch.int64)
+    gt_u8 = _require_cuda(gt_u8, "gt", torch.uint8)
+    pred_u8 = _require_cuda(pred_u8, "pred", torch.uint8)
+    if gt_u8.numel() != pred_u8.numel():
+        raise ValueError(f"Shapes must match. Got gt={tuple(gt_u8.shape)}, pred={tuple(pred_u8.shape)}")
+    ig = -1 if ignore_index is None else int(ignore_index)
+    check(lib.hb_confusion_accumulate(ptr(gt_u8), ptr(pred_u8), gt_u8.numel(), conf.shape[0], conf.shape[1], ig,
+                                      ptr(conf), stream_ptr(conf.device)))

@@ -1,0 +1,212 @@
+"""Staged on-GPU validation of the C-ABI kernels (run under gpurun, one stage per process so a
+trap in one stage cannot poison the next).  Writes gpurun_out/probe_<stage>.json.
+
+    python tools/gpu_probe.py <stage>      stages: simple gemm1 gemm2 search1 search2 perf
+"""
+import json
+import os
+import sys
+import time
+
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "open-hummingbird-eval_b200"))
+from hbird_b200 import ops  # noqa: E402
+
+OUT = os.path.join(ROOT, "gpurun_out")
+os.makedirs(OUT, exist_ok=True)
+DEV = torch.device("cuda", 0)
+torch.backends.cuda.matmul.allow_tf32 = False
+torch.backends.cudnn.allow_tf32 = False
+
+
+def synth_bank(N, d, seed=1):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.randn((N, d), generator=g, device=DEV, dtype=torch.float32)
+
+
+def make_bank(feats, C=21, ps=4, keep_f32=True):
+    """Bank from (N, d) raw features via the soft-label entry (labels irrelevant here)."""
+    N, d = feats.shape
+    bank = ops.MemoryBank(d, C, ps * ps, N, 0, keep_f32)
+    soft = torch.zeros((N, C), device=DEV)
+    soft[:, 0] = 1.0
+    step = 1 << 20
+    for i in range(0, N, step):
+        bank.append_soft(feats[i:i + step], soft[i:i + step], normalise=True)
+    bank.finalize()
+    return bank
+
+
+def stage_simple(res):
+    g = torch.Generator(device="cuda").manual_seed(0)
+    # decode
+    ids = torch.randint(0, 256, (3, 1, 64, 64), generator=g, device=DEV)
+    y = ids.float() / 255.0
+    dec = ops.decode_mask(y, False)
+    res["decode_exact"] = bool((dec.long() == (y * 255).long()).all())
+    dec0 = ops.decode_mask(y, True)
+    ref0 = (y * 255).long()
+    ref0[ref0 == 255] = 0
+    res["decode_remap_exact"] = bool((dec0.long() == ref0).all())
+    # confusion
+    for C, n in [(21, 1_000_003), (151, 3_000_017), (3, 7)]:
+        gt = torch.randint(0, C + 3, (n,), generator=g, device=DEV).to(torch.uint8)
+        gt[::17] = 255
+        pr = torch.randint(0, C, (n,), generator=g, device=DEV).to(torch.uint8)
+        conf = torch.zeros((C, C), dtype=torch.int64, device=DEV)
+        ops.confusion_accumulate(conf, gt, pr, 255)
+        ops.confusion_accumulate(conf, gt, pr, 255)
+        m = (gt != 255) & (gt < C)
+        ref = torch.bincount(gt[m].long() * C + pr[m].long(), minlength=C * C).view(C, C) * 2
+        res[f"confusion_exact_C{C}"] = bool((conf == ref).all())
+    # bank pack vs torch
+    B, S, ps, d, C = 4, 7, 4, 72, 21
+    feats = torch.randn((B, S * S, d), generator=g, device=DEV) * 3.7
+    mask = torch.randint(0, C, (B, S * ps, S * ps), generator=g, device=DEV).to(torch.uint8)
+    bank = ops.MemoryBank(d, C, ps * ps, B * S * S + 10, 0, True)
+    bank.append(feats, mask, S, ps)
+    sel = torch.tensor([5, 0, 77, 195], device=DEV, dtype=torch.int32)
+    bank.append(feats, mask, S, ps, sel)
+    bank.finalize()
+    f, l = bank.export()
+    nf = (feats / torch.norm(feats, dim=2, keepdim=True)).flatten(0, 1)
+    y = mask.long().unsqueeze(1)
+    gt = y.reshape(B, 1, S, ps, S, ps).permute(0, 2, 4, 1, 3, 5).reshape(B, S, S, ps * ps)
+    lab = F.one_hot(gt, C).float().mean(3).flatten(0, 2)
+    nf = torch.cat([nf, nf[sel.long()]])
+    lab = torch.cat([lab, lab[sel.long()]])
+    res["pack_feat_maxabs"] = float((f - nf).abs().max())
+    res["pack_label_maxabs"] = float((l - lab).abs().max())
+    res["pack_rows"] = bank.rows
+    # label transfer vs torch
+    N = bank.rows
+    Q, k = 50, 30
+    idx = torch.randint(0, N, (Q, k), generator=g, device=DEV)
+    scores = torch.rand((Q, k), generator=g, device=DEV) * 3
+    qn = torch.rand((Q,), generator=g, device=DEV) * 4 + 1
+    lh = ops.label_transfer(bank.label_table(), ps * ps, scores, idx, qn, 0.02)
+    attn = torch.softmax((scores / qn[:, None]) / 0.02, dim=-1)
+    ref = torch.bmm(attn.unsqueeze(1), l[idx.flatten()].view(Q, k, C)).squeeze(1)
+    res["label_transfer_maxabs"] = float((lh - ref).abs().max())
+    # upsample + argmax vs torch
+    for (B2, S2, C2, H2) in [(2, 14, 21, 224), (1, 37, 151, 518)]:
+        lh2 = torch.rand((B2 * S2 * S2, C2), generator=g, device=DEV)
+        pred = ops.upsample_argmax(lh2, B2, S2, H2, H2)
+        t = lh2.view(B2, S2, S2, C2).permute(0, 3, 1, 2)
+        refp = F.interpolate(t, size=(H2, H2), mode="bilinear").argmax(1)
+        refc = F.interpolate(t.cpu(), size=(H2, H2), mode="bilinear").argmax(1)
+        res[f"upsample_agree_cuda_S{S2}"] = float((pred.long() == refp).float().mean())
+        res[f"upsample_agree_cpu_S{S2}"] = float((pred.long().cpu() == refc).float().mean())
+    # merge
+    G, Q, k = 4, 33, 30
+    ss = torch.randn((G, Q, k), generator=g, device=DEV).sort(dim=-1, descending=True).values
+    si = torch.stack([torch.randint(0, 1000, (Q, k), generator=g, device=DEV) + 1000 * gg for gg in range(G)])
+    ms, mi = ops.merge_topk(ss, si)
+    alls = ss.permute(1, 0, 2).reshape(Q, G * k)
+    alli = si.permute(1, 0, 2).reshape(Q, G * k)
+    top = alls.topk(k, dim=-1)
+    res["merge_scores_exact"] = bool((ms == top.values).all())
+    res["merge_idx_exact"] = bool((mi == alli.gather(1, top.indices)).all())
+
+
+def gemm_check(res, cg):
+    for (Q, N, d) in [(128, 256, 64), (128, 512, 128), (300, 1000, 384), (257, 2049, 768), (1, 100, 1024)]:
+        feats = synth_bank(N, d, seed=N + d)
+        bank = make_bank(feats)
+        q = synth_bank(Q, d, seed=7) * 3.0
+        S = bank.dump_scores(q, cta_group=cg)
+        torch.cuda.synchronize()
+        fb, _ = bank.export()
+        ref = q.to(torch.bfloat16).float() @ fb.to(torch.bfloat16).float().T
+        err = (S - ref).abs().max().item()
+        nan = int(torch.isnan(S).sum())
+        res[f"gemm_cg{cg}_Q{Q}_N{N}_d{d}"] = {"maxabs": err, "nan": nan, "ref_absmax": float(ref.abs().max())}
+        bank.close()
+
+
+def search_check(res, cg):
+    for (Q, N, d, kp) in [(1000, 5000, 384, 64), (12544, 102400, 384, 64), (2000, 300000, 768, 64), (777, 40000, 384, 32), (300, 20000, 1024, 128)]:
+        feats = synth_bank(N, d, seed=3)
+        bank = make_bank(feats)
+        bank.configure_search(cta_group=cg)
+        g = torch.Generator(device="cuda").manual_seed(11)
+        # planted neighbours: queries near bank rows so the top of the list is non-trivial
+        pick = torch.randint(0, N, (Q,), generator=g, device=DEV)
+        q = (feats[pick] / feats[pick].norm(dim=1, keepdim=True) + 0.05 * torch.randn((Q, d), generator=g, device=DEV)) * 3.7
+        s, i, qn = bank.search(q, 30, kp)
+        torch.cuda.synchronize()
+        fb, _ = bank.export()
+        rs, ri = [], []
+        for a in range(0, Q, 2048):
+            t = (q[a:a + 2048] @ fb.T).topk(30, dim=-1)
+            rs.append(t.values)
+            ri.append(t.indices)
+        rs, ri = torch.cat(rs), torch.cat(ri)
+        hit = (i.unsqueeze(2) == ri.unsqueeze(1)).any(2).float().mean().item()
+        rel = ((s - rs).abs() / rs.abs().clamp_min(1e-6)).max().item()
+        res[f"search_cg{cg}_Q{Q}_N{N}_d{d}_kp{kp}"] = {
+            "recall": hit, "score_rel": rel, "qnorm_err": float((qn - q.norm(dim=1)).abs().max()),
+            "sorted": bool((s[:, :-1] >= s[:, 1:]).all()), "launches": bank.last_search_launches()}
+        bank.close()
+
+
+def perf(res):
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("bf16_tflops_sustained", 1425.8)
+    for (name, Q, N, d) in [("cfg1", 12544, 102400, 384), ("cfg2", 12544, 1024000, 384),
+                            ("cfg3_shard8", 21904, 1280000, 768), ("d768_1M", 21904, 1024000, 768)]:
+        feats = synth_bank(N, d, seed=5)
+        bank = make_bank(feats)
+        del feats
+        q = synth_bank(Q, d, seed=9) * 3.0
+        for cg in (1, 2):
+            bank.configure_search(cta_group=cg)
+            for _ in range(2):
+                bank.search(q, 30, 64)
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            iters = 5
+            for _ in range(iters):
+                bank.search(q, 30, 64)
+            ev1.record()
+            torch.cuda.synchronize()
+            ms = ev0.elapsed_time(ev1) / iters
+            tf = 2.0 * Q * N * d / (ms * 1e-3) / 1e12
+            res[f"perf_{name}_cg{cg}"] = {"ms": ms, "qps": Q / (ms * 1e-3), "tflops": tf, "frac_sustained": tf / peak}
+        bank.close()
+
+
+if __name__ == "__main__":
+    stage = sys.argv[1]
+    res = {"stage": stage, "gpu": torch.cuda.get_device_name(0), "sms": ops.device_check(0)}
+    t0 = time.time()
+    try:
+        if stage == "simple":
+            stage_simple(res)
+        elif stage == "gemm1":
+            gemm_check(res, 1)
+        elif stage == "gemm2":
+            gemm_check(res, 2)
+        elif stage == "search1":
+            search_check(res, 1)
+        elif stage == "search2":
+            search_check(res, 2)
+        elif stage == "perf":
+            perf(res)
+        torch.cuda.synchronize()
+        res["ok"] = True
+    except Exception as e:  # noqa: BLE001
+        res["ok"] = False
+        res["error"] = f"{type(e).__name__}: {e}"
+    res["seconds"] = time.time() - t0
+    with open(os.path.join(OUT, f"probe_{stage}.json"), "w") as f:
+        json.dump(res, f, indent=1)
+    print(json.dumps(res, indent=1))
