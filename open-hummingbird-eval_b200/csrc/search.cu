@@ -257,7 +257,8 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
               ptx::tmem_ld_wait();
               if (((mine >> j) & 1u) && x > tau) {
                 heap_replace_root<KP>(heap, make_key(x, static_cast<uint32_t>(col_base + c0 + j)));
-                tau = key_score(heap[0]);
+                const uint64_t root = heap[0];  // still the 0 sentinel until k' real entries exist
+                tau = root ? key_score(root) : -INFINITY;
               }
             }
           }
