@@ -9,10 +9,13 @@
 //   warp 1      tcgen05.mma issuer (one lane; pair leader only): 128*CG x 256 x 16 UMMAs into one
 //               of two 256-column TMEM accumulators; tcgen05.commit frees ring slots and
 //               publishes finished accumulators.  Also owns TMEM alloc/dealloc.
-//   warps 2..5  epilogue: each thread owns ONE query row (TMEM lane).  It scans the 256 scores of
-//               a tile with a running threshold tau = its current k'-th best; survivors are pushed
-//               into a per-thread min-heap of k' (score,row) keys in shared memory.  Accumulator
-//               double-buffering overlaps this scan with the MMAs of the next tile.
+//   warps 2..9  epilogue: each thread owns ONE query row (TMEM lane) and one 128-column half of the
+//               tile.  It scans its scores against a running threshold tau (a lower bound of its
+//               current k'/2-th best): a max-tree + one vote rejects 32 columns at a time; the rare
+//               survivors are appended to a small per-thread queue in shared memory, and when any
+//               lane's queue fills, the whole warp merges queues into per-thread sorted lists with
+//               fully unrolled bitonic networks (lock-step, no divergence) and tightens tau.
+//               Accumulator double-buffering overlaps this scan with the MMAs of the next tile.
 // Work item = (query block of 128*CG rows) x (bank chunk of consecutive 256-row tiles); items are
 // dealt round-robin to the persistent CTAs so that concurrently running CTAs walk the same bank
 // tiles (L2 reuse) with different queries.  Each item emits k' unsorted candidate keys per query.
@@ -28,7 +31,8 @@ constexpr int BM = 128;   // query rows per CTA (TMEM lanes)
 constexpr int BN = 256;   // bank rows per tile (UMMA N)
 constexpr int BK = 64;    // bf16 per k-block: one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kEpiWarps = 4;
+constexpr int kEpiWarps = 8;   // 4 TMEM lane quarters x 2 column halves
+constexpr int kQueueCap = 16;  // per-thread pending-candidate queue
 constexpr int kSearchThreads = 32 * (2 + kEpiWarps);
 constexpr int kTmemCols = 512;
 
@@ -49,31 +53,71 @@ struct SearchSmem {
   static constexpr int kBBytes = (BN / CG) * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kRingBytes = STAGES * kStageBytes;
-  static constexpr int kHeapBytes = KP * BM * 8;
+  static constexpr int kHeapBytes = (KP + 2 * kQueueCap) * BM * 8;  // 2 x (list k'/2 + queue) per row
   static constexpr int kBarOffset = kRingBytes + kHeapBytes;
   static constexpr int kNumBars = 2 * STAGES + 4;
   static constexpr int kTotal = kBarOffset + kNumBars * 8 + 16;
   static constexpr int kDynamic = kTotal + 1024;  // slack to align the ring to 1024 B
+  static_assert(kDynamic <= 227 * 1024, "search kernel shared memory exceeds 227 KB");
 };
 
-// Replace the heap root (current k'-th best) with `key` and restore the min-heap property.
-// Entry j of epilogue thread t lives at heap[j*BM + t]: conflict-free for any per-lane j.
-template <int KP>
-__device__ __forceinline__ void heap_replace_root(uint64_t* heap, uint64_t key) {
-  int i = 0;
-  while (true) {
-    const int l = 2 * i + 1;
-    if (l >= KP) break;
-    const int r = l + 1;
-    const uint64_t kl = heap[l * BM];
-    const uint64_t kr = (r < KP) ? heap[r * BM] : ~0ull;
-    const bool right = kr < kl;
-    const uint64_t kc = right ? kr : kl;
-    if (kc >= key) break;
-    heap[i * BM] = kc;
-    i = right ? r : l;
+// ---- per-thread candidate selection state in shared memory -------------------------------
+// Entry j of the thread owning tile row t lives at base[j*BM + t]: every lane of a warp touches a
+// different bank for any j, so the lock-step networks below are conflict-free.
+
+// One compare-exchange stage (K, J) of a bitonic network over N keys.
+template <int N, int K, int J, bool DESC>
+__device__ __forceinline__ void bitonic_stage(uint64_t* a) {
+#pragma unroll
+  for (int i = 0; i < N / 2; ++i) {
+    const int e = ((i & ~(J - 1)) << 1) | (i & (J - 1));
+    const int p = e | J;
+    const bool asc = ((e & K) == 0) != DESC;
+    const uint64_t x = a[e * BM], y = a[p * BM];
+    const bool sw = asc ? (x > y) : (x < y);
+    a[e * BM] = sw ? y : x;
+    a[p * BM] = sw ? x : y;
   }
-  heap[i * BM] = key;
+}
+template <int N, int K, int J, bool DESC>
+struct BitonicJ {
+  static __device__ __forceinline__ void run(uint64_t* a) {
+    bitonic_stage<N, K, J, DESC>(a);
+    if constexpr (J > 1) BitonicJ<N, K, J / 2, DESC>::run(a);
+  }
+};
+template <int N, int K, bool DESC>
+struct BitonicK {  // full sort: stages K = 2, 4, ..., N
+  static __device__ __forceinline__ void run(uint64_t* a) {
+    if constexpr (K > 2) BitonicK<N, K / 2, DESC>::run(a);
+    BitonicJ<N, K, K / 2, DESC>::run(a);
+  }
+};
+// Sort N keys / merge a bitonic sequence of N keys (DESC: largest first).
+template <int N, bool DESC>
+__device__ __forceinline__ void smem_sort(uint64_t* a) { BitonicK<N, N, DESC>::run(a); }
+template <int N, bool DESC>
+__device__ __forceinline__ void smem_bitonic_merge(uint64_t* a) { BitonicJ<N, N, N / 2, DESC>::run(a); }
+
+// Fold the `cnt` queued keys into the sorted (descending) list of KL keys; returns the new tau.
+template <int KL, int QC>
+__device__ __noinline__ float merge_queue(uint64_t* list, uint64_t* queue, int cnt) {
+  for (int j = cnt; j < QC; ++j) queue[j * BM] = 0ull;  // key 0 sorts below every real score
+  smem_sort<QC, false>(queue);                          // ascending
+  uint64_t* tail = list + (KL - QC) * BM;               // the QC smallest kept keys, descending
+#pragma unroll
+  for (int i = 0; i < QC; ++i) {
+    const uint64_t t = tail[i * BM], q = queue[i * BM];
+    tail[i * BM] = t > q ? t : q;                       // QC largest of (tail U queue), bitonic
+  }
+  if constexpr (KL > QC) {
+    smem_bitonic_merge<QC, false>(tail);                // ... ascending
+    smem_bitonic_merge<KL, true>(list);                 // [descending head | ascending tail] -> sorted
+  } else {
+    smem_bitonic_merge<QC, true>(tail);
+  }
+  const uint64_t worst = list[(KL - 1) * BM];
+  return worst ? key_score(worst) : -INFINITY;
 }
 
 template <int CG, int STAGES, int KP>
@@ -198,10 +242,14 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
     }
   } else {
     // =========================== epilogue: fused top-k' ===========================
-    const int quarter = warp & 3;               // TMEM lane quarter this warp may read
+    constexpr int KL = KP / 2;                    // list length per (row, column half)
+    constexpr int QC = kQueueCap < KL ? kQueueCap : KL;
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;             // which 128 columns of the tile
     const int row_in_tile = quarter * 32 + lane;  // query row owned by this thread
-    uint64_t* heap = heap_base + row_in_tile;
-    const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    uint64_t* list = heap_base + (half * KL) * BM + row_in_tile;
+    uint64_t* queue = heap_base + (KP + half * kQueueCap) * BM + row_in_tile;
+    const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + half * (BN / 2);
     const uint32_t tempty_leader0 = (CG == 2) ? ptx::mapa(tempty_bar(0), 0) : tempty_bar(0);
     const uint32_t tempty_leader1 = (CG == 2) ? ptx::mapa(tempty_bar(1), 0) : tempty_bar(1);
     int abuf = 0;
@@ -212,17 +260,18 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       const int t1 = chunk_tile_begin(p.n_tiles, p.n_chunks, chunk + 1);
       const int64_t q_row = static_cast<int64_t>(qb * CG + static_cast<int>(cta_rank)) * BM + row_in_tile;
 #pragma unroll 4
-      for (int j = 0; j < KP; ++j) heap[j * BM] = 0ull;  // key 0 sorts below every real score
+      for (int j = 0; j < KL; ++j) list[j * BM] = 0ull;
       float tau = -INFINITY;
+      int cnt = 0;
       for (int tile = t0; tile < t1; ++tile) {
         ptx::mbar_wait(tfull_bar(abuf), aphase, 4);
         ptx::tc_fence_after();
-        const int64_t col_base = static_cast<int64_t>(tile) * BN;
+        const int64_t col_base = static_cast<int64_t>(tile) * BN + half * (BN / 2);
         const int64_t rem = p.n_rows - col_base;
-        const int nvalid = rem >= BN ? BN : static_cast<int>(rem);
+        const int nvalid = rem >= BN / 2 ? BN / 2 : (rem > 0 ? static_cast<int>(rem) : 0);
         const uint32_t tacc = tmem_lane + static_cast<uint32_t>(abuf * BN);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = 0; c0 < BN / 2; c0 += 32) {
           if (c0 >= nvalid) break;  // warp-uniform
           uint32_t v[32];
           ptx::tmem_ld_32x32b_x32(tacc + c0, v);
@@ -232,33 +281,38 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             for (int j = 0; j < 32; ++j)
               if (c0 + j < nvalid) p.dump[q_row * p.n_rows + col_base + c0 + j] = __uint_as_float(v[j]);
           }
-          const uint32_t vmask = (nvalid - c0 >= 32) ? 0xffffffffu : ((1u << (nvalid - c0)) - 1u);
-          // fast reject: one max-tree over the 32 columns, one compare, one vote
-          float m = -INFINITY;
-          if (vmask == 0xffffffffu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
-          } else {
+          if (c0 + 32 > nvalid) {  // last, partial tile of the bank: padded rows never win
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if ((vmask >> j) & 1u) m = fmaxf(m, __uint_as_float(v[j]));
+              if (c0 + j >= nvalid) v[j] = 0xff800000u;  // -inf
           }
-          if (__any_sync(0xffffffffu, m > tau)) {
-            uint32_t mine = 0;
+          // fast reject: max-tree over 4 groups of 8 columns, one compare, one vote
+          float mg[4];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) mine |= (__uint_as_float(v[j]) > tau ? 1u : 0u) << j;
-            mine &= vmask;
-            uint32_t todo = __reduce_or_sync(0xffffffffu, mine);
-            while (todo) {
-              const int j = __ffs(todo) - 1;
-              todo &= todo - 1;
-              // registers cannot be indexed by a run-time j: re-read the column from TMEM
-              const float x = __uint_as_float(ptx::tmem_ld_32x32b_x1(tacc + c0 + j));
-              ptx::tmem_ld_wait();
-              if (((mine >> j) & 1u) && x > tau) {
-                heap_replace_root<KP>(heap, make_key(x, static_cast<uint32_t>(col_base + c0 + j)));
-                const uint64_t root = heap[0];  // still the 0 sentinel until k' real entries exist
-                tau = root ? key_score(root) : -INFINITY;
+          for (int g = 0; g < 4; ++g) {
+            float m = __uint_as_float(v[8 * g]);
+#pragma unroll
+            for (int j = 1; j < 8; ++j) m = fmaxf(m, __uint_as_float(v[8 * g + j]));
+            mg[g] = m;
+          }
+          const float m = fmaxf(fmaxf(mg[0], mg[1]), fmaxf(mg[2], mg[3]));
+          if (__any_sync(0xffffffffu, m > tau)) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (__any_sync(0xffffffffu, mg[g] > tau)) {
+                if (__any_sync(0xffffffffu, cnt > QC - 8)) {  // room for 8 more in every lane?
+                  tau = merge_queue<KL, QC>(list, queue, cnt);
+                  cnt = 0;
+                }
+                const uint32_t col = static_cast<uint32_t>(col_base + c0 + 8 * g);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float x = __uint_as_float(v[8 * g + j]);
+                  if (x > tau) {
+                    queue[cnt * BM] = make_key(x, col + j);
+                    ++cnt;
+                  }
+                }
               }
             }
           }
@@ -273,11 +327,12 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         abuf ^= 1;
         if (abuf == 0) aphase ^= 1u;
       }
-      // emit this item's k' candidates (unsorted; the re-rank kernel orders them)
+      if (__any_sync(0xffffffffu, cnt > 0)) tau = merge_queue<KL, QC>(list, queue, cnt);
+      // emit this item's candidates (k'/2 per column half, sorted; the re-rank kernel merges them)
       const int64_t q_pad = static_cast<int64_t>(p.n_qblocks) * BM * CG;
-      uint64_t* out = p.cand + (static_cast<int64_t>(chunk) * q_pad + q_row) * KP;
+      uint64_t* out = p.cand + (static_cast<int64_t>(chunk) * q_pad + q_row) * KP + half * KL;
 #pragma unroll 4
-      for (int j = 0; j < KP; ++j) out[j] = heap[j * BM];
+      for (int j = 0; j < KL; ++j) out[j] = list[j * BM];
     }
   }
 
@@ -348,11 +403,11 @@ static int dispatch_search(const Bank* b, int cg, int kp, const CUtensorMap& tma
   if (cg == 2) {
     if (kp == 32) return launch_search<2, 5, 32>(b, tmap_q, p, st);
     if (kp == 64) return launch_search<2, 4, 64>(b, tmap_q, p, st);
-    if (kp == 128) return launch_search<2, 3, 128>(b, tmap_q, p, st);
+    if (kp == 128) return launch_search<2, 2, 128>(b, tmap_q, p, st);
   } else {
     if (kp == 32) return launch_search<1, 3, 32>(b, tmap_q, p, st);
-    if (kp == 64) return launch_search<1, 3, 64>(b, tmap_q, p, st);
-    if (kp == 128) return launch_search<1, 2, 128>(b, tmap_q, p, st);
+    if (kp == 64) return launch_search<1, 2, 64>(b, tmap_q, p, st);
+    if (kp == 128) return launch_search<1, 1, 128>(b, tmap_q, p, st);
   }
   set_error("hb_search: k_prime=%d not in {32, 64, 128}", kp);
   return HB_ERR_INVALID;
