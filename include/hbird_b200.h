@@ -114,6 +114,11 @@ int hb_search_config(hb_bank_t* bank, int cta_group, int max_chunks);
 /* Number of kernel launches the last hb_search on this bank issued. */
 int hb_search_last_launches(const hb_bank_t* bank);
 
+/* Host-only (no GPU needed): the work decomposition hb_search would use for a bank of `rows`
+ * rows and Q queries on `num_sms` SMs.  out4 = {n_tiles, n_qblocks, n_chunks, n_units}; chunk c
+ * covers tiles [n_tiles*c/n_chunks, n_tiles*(c+1)/n_chunks) of 256 bank rows. */
+int hb_plan_search(int64_t rows, int64_t Q, int cta_group, int num_sms, int max_chunks, int* out4);
+
 /* Debug/validation: full bf16-input fp32-accumulate score matrix of the tcgen05 pass,
  * out_dev fp32 (Q, rows).  Small problems only (Q*rows*4 bytes are written). */
 int hb_search_dump_scores(hb_bank_t* bank, const float* q_dev, int64_t Q, float* out_dev,

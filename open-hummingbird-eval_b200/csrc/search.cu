@@ -504,6 +504,19 @@ int hb_search_config(hb_bank_t* bank, int cta_group, int max_chunks) {
   return HB_OK;
 }
 
+int hb_plan_search(int64_t rows, int64_t Q, int cta_group, int num_sms, int max_chunks, int* out4) {
+  HB_REQUIRE(out4 != nullptr, "hb_plan_search: out4 is NULL");
+  HB_REQUIRE(rows >= 1 && Q >= 1, "hb_plan_search: rows and Q must be positive");
+  HB_REQUIRE(cta_group == 1 || cta_group == 2, "hb_plan_search: cta_group=%d not in {1,2}", cta_group);
+  HB_REQUIRE(num_sms >= 1 && max_chunks >= 0, "hb_plan_search: bad num_sms/max_chunks");
+  const hb::SearchPlan p = hb::plan_search(rows, Q, cta_group, num_sms, max_chunks);
+  out4[0] = p.n_tiles;
+  out4[1] = p.n_qblocks;
+  out4[2] = p.n_chunks;
+  out4[3] = p.n_units;
+  return HB_OK;
+}
+
 int hb_search_last_launches(const hb_bank_t* bank) {
   return bank ? reinterpret_cast<const Bank*>(bank)->last_launches : 0;
 }

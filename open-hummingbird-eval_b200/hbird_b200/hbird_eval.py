@@ -1,0 +1,307 @@
+"""HbirdEvaluation / hbird_evaluation — host-side mirror of the reference's evaluation engine
+(hbird/hbird_eval.py:54-722) for the dense nearest-neighbour hot path, device resident end to end.
+
+Same constructor, `evaluate(...)` and `hbird_evaluation(...)` signatures and return types as the
+reference.  What differs is where the work happens:
+
+  reference (hbird_eval.py)                         here
+  ------------------------------------------------  ---------------------------------------------
+  :309-329 decode, patchify, one_hot.mean, norm,    K1  hb_decode_mask + hb_bank_append (fused
+           D2H append, torch.cat                        normalise/cast/pack + class histogram)
+  :182     faiss index build + index.add (H2D)      -   the bank already lives in HBM
+  :628     features.cpu() -> faiss search -> host   K2  tcgen05 GEMM + fused top-k', K2b fp32
+                                                        re-rank (+ NCCL all-gather, K3 merge)
+  :632-636 index_select of neighbour features       -   not needed: cos = score/||q||
+           and labels on the CPU                    K4a hb_label_transfer (gathers uint16 hists)
+  :594-609 normalise, bmm, softmax, bmm
+  :235-243 permute, F.interpolate, argmax           K4b hb_upsample_argmax
+  :245-252 cat all pixels, one giant bincount       K5  hb_confusion_accumulate per batch
+  :253     Hungarian mIoU on the C x C matrix       host (scipy), unchanged
+
+ViT feature extraction and data loading stay in PyTorch.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import logging
+from typing import Any, Dict, Optional
+
+import torch
+
+from . import distributed as hdist
+from . import ops
+from .models import FeatureExtractorSimple
+from .registry import NN_BACKENDS, create_nn_backend
+from .utils.eval_metrics import PredsmIoU
+
+logger = logging.getLogger(__name__)
+
+BETA = 0.02  # cross-attention temperature, hbird_eval.py:576
+
+
+class HbirdEvaluation:
+    """Build the patch memory bank from `train_loader`, then evaluate `val_loader` by kNN label
+    transfer.  Loaders are any iterable of (x fp32 (B,3,H,W), y fp32 = class_id/255 (B,1,H,W))."""
+
+    def __init__(self, feature_extractor: torch.nn.Module, train_loader, num_classes: int,
+                 n_neighbours: int = 30, augmentation_epoch: int = 1, device: torch.device | str = "cpu",
+                 nn_method: str = "b200", nn_params: Optional[Dict[str, Any]] = None,
+                 memory_size: Optional[int] = None, dataset_size: Optional[int] = None,
+                 f_mem_p: Optional[str] = None, l_mem_p: Optional[str] = None) -> None:
+        self.nn_params = dict(nn_params or {})
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("hbird_b200 runs on a CUDA device (sm_100); there is no CPU fallback. "
+                               f"Got device={device!r}.")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        ops.device_check(self.device.index)
+        if nn_method not in NN_BACKENDS:
+            raise ValueError(f"Unsupported NN method. Choose from {set(NN_BACKENDS)}.")
+        self.nn_method = nn_method
+        self.feature_extractor = feature_extractor.to(self.device)
+        self.feature_extractor.eval()
+        self.augmentation_epoch = augmentation_epoch
+        self.memory_size = memory_size
+        self.n_neighbours = n_neighbours
+        self.num_classes = num_classes
+        self.f_mem_p, self.l_mem_p = f_mem_p, l_mem_p
+        self.num_sampled_features: Optional[int] = None
+        self.rank, self.world = hdist.dist_info()
+        self.k_prime = int(self.nn_params.get("k_prime", 64))
+        self.keep_f32 = bool(self.nn_params.get("keep_f32", True))
+
+        S = self.feature_extractor.eval_spatial_resolution
+        if self.memory_size is not None:
+            if dataset_size is None:
+                raise ValueError("dataset_size must be provided when memory_size is set.")
+            denom = dataset_size * self.augmentation_epoch
+            self.num_sampled_features = max(1, self.memory_size // max(1, denom))
+            logger.info("Bounded memory: memory_size=%d => %d sampled patches per image",
+                        self.memory_size, self.num_sampled_features)
+
+        self.bank: Optional[ops.MemoryBank] = None
+        self._create_memory(train_loader, num_classes, S)
+        self._save_memory()
+        self._create_nn(self.n_neighbours, nn_method=self.nn_method, **self.nn_params)
+
+    # ------------------------------------------------------------------ bank construction
+    def _capacity_rows(self, loader_len: Optional[int], first_batch: int, S: int) -> int:
+        if self.memory_size is not None:
+            return int(self.memory_size)
+        if loader_len is None:
+            raise ValueError("train_loader must define __len__ when memory_size is None")
+        my_batches = (loader_len - self.rank + self.world - 1) // self.world
+        return max(1, my_batches * first_batch * S * S * self.augmentation_epoch)
+
+    @torch.no_grad()
+    def _create_memory(self, train_loader, num_classes: int, eval_spatial_resolution: int) -> int:
+        """hbird_eval.py:283-369.  With world_size > 1 rank r takes batches r, r+W, ... and owns
+        the rows it produces (row-sharded bank)."""
+        S = eval_spatial_resolution
+        d = self.feature_extractor.d_model
+        loader_len = len(train_loader) if hasattr(train_loader, "__len__") else None
+        step = 0
+        for _ in range(self.augmentation_epoch):
+            for x, y in train_loader:
+                mine = (step % self.world) == self.rank
+                step += 1
+                if not mine:
+                    continue
+                x = x.to(self.device)
+                y = y.to(self.device, dtype=torch.float32)
+                B, _, H, W = x.shape
+                ps = x.shape[-1] // S
+                if H != S * ps or W != S * ps:
+                    raise ValueError(f"input {H}x{W} is not eval_spatial_resolution*patch = {S}*{ps}")
+                feats, _ = self.feature_extractor.forward_features(x)
+                feats = feats.to(torch.float32).contiguous()
+                mask = ops.decode_mask(y.contiguous(), True).view(B, H, W)
+                if self.bank is None:
+                    cap = self._capacity_rows(loader_len, B, S)
+                    self.bank = ops.MemoryBank(d, num_classes, ps * ps, cap, self.device.index, self.keep_f32)
+                    self._ps = ps
+                if self.memory_size is None:
+                    self.bank.append(feats, mask, S, ps)
+                else:
+                    sel = self._sample_patches(mask, S, ps, num_classes)
+                    room = self.bank.capacity - self.bank.rows
+                    if sel.numel() > room:  # the reference's slice assignment would raise here too
+                        raise ValueError("memory_size exhausted before the training set was consumed")
+                    self.bank.append(feats, mask, S, ps, sel)
+        if self.bank is None:
+            raise ValueError("train_loader yielded no batches for this rank")
+        self.bank.finalize()
+        # replicate the label table and fix the global row offset of this shard
+        counts = hdist.gather_counts(self.bank.rows, self.device)
+        self.shard_counts = counts
+        self.idx_offset = hdist.offsets_from_counts(counts)[self.rank]
+        self.total_rows = sum(counts)
+        self.label_table = hdist.all_gather_rows(self.bank.label_table(), counts)
+        logger.info("Memory bank: %d rows on this rank, %d total, d=%d", self.bank.rows, self.total_rows, d)
+        return self.bank.rows
+
+    def _sample_patches(self, mask: torch.Tensor, S: int, ps: int, num_classes: int) -> torch.Tensor:
+        """Bounded-memory sampler, hbird_eval.py:447-517: per image keep the K patches with the
+        smallest score*U(0,1), score = sum over the classes present in the patch of the number of
+        patches of the image containing that class.  U is drawn with the CPU generator in image
+        order exactly as the reference does, so a seeded run picks the same patches.
+        Returns int32 flat source rows (b*S*S + patch) on the device."""
+        B = mask.shape[0]
+        K = int(self.num_sampled_features)
+        patches = mask.view(B, S, ps, S, ps).permute(0, 1, 3, 2, 4).reshape(B, S * S, ps * ps).long()
+        presence = torch.zeros((B, S * S, num_classes), dtype=torch.bool, device=mask.device)
+        presence.scatter_(2, patches.clamp_max(num_classes - 1), True)
+        class_freq = presence.sum(dim=1).float()
+        scores = torch.einsum("bpc,bc->bp", presence.float(), class_freq).cpu()
+        nonzero = presence.any(dim=2).cpu()
+        scores.masked_fill_(~nonzero, 1e6)
+        total = int(nonzero.sum())
+        if total > 0:
+            noise = torch.ones_like(scores)
+            noise[nonzero] = torch.rand(total)  # row-major fill == per-image order of the reference
+            scores.mul_(noise)
+        _, picks = torch.topk(scores, K, largest=False)
+        flat = picks + torch.arange(B).unsqueeze(1) * (S * S)
+        return flat.reshape(-1).to(device=mask.device, dtype=torch.int32)
+
+    def _save_memory(self) -> None:
+        """hbird_eval.py:371-378 — same on-disk format: fp32 (N,d) and (N,C) tensors."""
+        if self.f_mem_p is None and self.l_mem_p is None:
+            return
+        f, l = self.bank.export(features=self.f_mem_p is not None, labels=self.l_mem_p is not None)
+        if self.f_mem_p is not None:
+            torch.save(f.cpu(), self.f_mem_p)
+        if self.l_mem_p is not None:
+            torch.save(l.cpu(), self.l_mem_p)
+
+    @property
+    def feature_memory(self) -> torch.Tensor:
+        """The reference's feature_memory (N, d) fp32 CPU tensor, materialised on demand."""
+        return self.bank.export(labels=False)[0].cpu()
+
+    @property
+    def label_memory(self) -> torch.Tensor:
+        return self.bank.export(features=False)[1].cpu()
+
+    def _create_nn(self, n_neighbours: int = 30, nn_method: str = "b200", **kwargs) -> None:
+        """hbird_eval.py:267-281, through the registry."""
+        if nn_method == "b200":
+            kw = {k: v for k, v in kwargs.items() if k not in ("k_prime", "keep_f32", "gpu_ids")}
+            self.NN_algorithm = create_nn_backend(
+                "b200", None, n_neighbors=n_neighbours, bank=self.bank, k_prime=self.k_prime,
+                idx_offset=self.idx_offset, gpu_ids=[self.device.index], **kw)
+        else:
+            # legacy / third-party plugins take the reference's CPU feature tensor
+            self.NN_algorithm = create_nn_backend(nn_method, self.feature_memory, n_neighbors=n_neighbours, **kwargs)
+
+    # ------------------------------------------------------------------ evaluation
+    def _search(self, q: torch.Tensor):
+        """(scores, global idx, qnorm) for all queries; merges shards when world_size > 1."""
+        if self.nn_method == "b200":
+            scores, idx, qn = self.NN_algorithm.search_device(q, self.n_neighbours)
+        else:
+            idx_np, dist_np = self.NN_algorithm.find_nearest_neighbors(q.cpu())
+            idx = torch.as_tensor(idx_np.astype("int64"), device=self.device)
+            scores = torch.as_tensor(dist_np, dtype=torch.float32, device=self.device)
+            qn = torch.linalg.vector_norm(q, dim=1)
+        if self.world > 1:
+            gs, gi = hdist.all_gather_topk(scores, idx)
+            scores, idx = ops.merge_topk(gs, gi)
+        return scores, idx, qn
+
+    @torch.no_grad()
+    def evaluate(self, val_loader, eval_spatial_resolution: int, return_knn_details: bool = False,
+                 ignore_index: int = 255):
+        """hbird_eval.py:184-265.  Returns the mIoU (Python float in [0, 1]) or (mIoU, details)."""
+        S = eval_spatial_resolution
+        C = self.num_classes
+        metric = PredsmIoU(C, C, device=self.device, ignore_index=ignore_index)
+        knns, knns_labels, knns_ca = [], [], []
+        for x, y in val_loader:
+            x = x.to(self.device)
+            B, _, h, w = x.shape
+            feats, _ = self.feature_extractor.forward_features(x)
+            feats = feats.to(torch.float32).contiguous()
+            N, d = feats.shape[1], feats.shape[2]
+            gt = ops.decode_mask(y.to(self.device, dtype=torch.float32).contiguous(), False).view(B, h, w)
+            scores, idx, qn = self._search(feats.view(B * N, d))
+            # after the merge every rank holds all results; each post-processes its image slice
+            b0, b1 = hdist.split_range(B, self.world, self.rank)
+            if b1 > b0:
+                sl = slice(b0 * N, b1 * N)
+                label_hat = ops.label_transfer(self.label_table, self.bank.patch_pixels, scores[sl], idx[sl],
+                                               qn[sl], BETA)
+                pred = ops.upsample_argmax(label_hat, b1 - b0, S, h, w)
+                metric.update(gt[b0:b1], pred)
+                if return_knn_details:
+                    kf, kl = self._gather_details(idx[sl])
+                    k = self.n_neighbours
+                    knns.append(kf.view(b1 - b0, N, k, -1).cpu())
+                    knns_labels.append(kl.view(b1 - b0, N, k, -1).cpu())
+                    knns_ca.append(label_hat.view(b1 - b0, N, -1).cpu())
+        jac, tp, fp, fn, _, _ = metric.compute(is_global_zero=True, sync_distributed=self.world > 1,
+                                               return_reordered=False)
+        self.last_confusion = metric.confusion_matrix()
+        if return_knn_details:
+            return jac, {"knns": torch.cat(knns), "knns_labels": torch.cat(knns_labels),
+                         "knns_ca_labels": torch.cat(knns_ca)}
+        return jac
+
+    def _gather_details(self, idx: torch.Tensor):
+        """return_knn_details support (hbird_eval.py:229-232,255-262): neighbour features / soft
+        labels gathered from the exported fp32 bank (single-GPU banks only)."""
+        if self.world > 1:
+            raise NotImplementedError("return_knn_details is supported for an unsharded bank")
+        if not hasattr(self, "_export_cache"):
+            self._export_cache = self.bank.export()
+        f, l = self._export_cache
+        flat = idx.reshape(-1).clamp_min(0)
+        return f.index_select(0, flat), l.index_select(0, flat)
+
+
+def hbird_evaluation(model, d_model: int, patch_size: int, dataset_name, data_dir: str, batch_size: int = 64,
+                     input_size: int = 224, augmentation_epoch: int = 1, device: str | torch.device = "cpu",
+                     return_knn_details: bool = False, n_neighbours: int = 30, nn_method: str = "b200",
+                     nn_params: Optional[Dict[str, Any]] = None, ftr_extr_fn=None,
+                     memory_size: Optional[int] = None, num_workers: int = 8, ignore_index: int = 255,
+                     train_fs_path: Optional[str] = None, val_fs_path: Optional[str] = None):
+    """Same entry point as hbird_eval.py:640-722.  `dataset_name` is either a registered dataset
+    name — resolved by the REFERENCE package's data layer (hbird.data / hbird.utils.transforms),
+    which is out of scope here and must be installed for real datasets — or a datamodule-like
+    object exposing get_train_dataset_size(), get_num_classes(), train_dataloader(),
+    val_dataloader() and optionally `ignore_index` (e.g. hbird_b200.data.SyntheticSegmentationData)."""
+    nn_params = dict(nn_params or {})
+    S = input_size // patch_size
+    if ftr_extr_fn is None:
+        try:
+            from hbird.models import FeatureExtractor  # reference's auto-detecting wrapper
+        except ImportError as e:
+            raise ImportError("ftr_extr_fn=None needs the reference package's hbird.models.FeatureExtractor; "
+                              "pass ftr_extr_fn=(model, imgs) -> (features, None) instead") from e
+        feature_extractor = FeatureExtractor(model, eval_spatial_resolution=S, d_model=d_model)
+    else:
+        feature_extractor = FeatureExtractorSimple(model, ftr_extr_fn=ftr_extr_fn, eval_spatial_resolution=S,
+                                                   d_model=d_model)
+    if isinstance(dataset_name, str):
+        try:
+            from hbird.data import get_dataset
+            from hbird.utils.image_transformations import CombTransforms
+            from hbird.utils.transforms import get_hbird_train_transforms, get_hbird_val_transforms
+        except ImportError as e:
+            raise ImportError("named datasets are loaded by the reference package's data layer "
+                              f"(hbird.data), which is not importable here: {e}") from e
+        tt, vt = get_hbird_train_transforms(input_size), get_hbird_val_transforms(input_size)
+        train_tf = CombTransforms(img_transform=tt["img"], tgt_transform=None, img_tgt_transform=tt["shared"])
+        val_tf = CombTransforms(img_transform=vt["img"], tgt_transform=None, img_tgt_transform=vt["shared"])
+        dataset, ignore_index_local = get_dataset(dataset_name, data_dir, batch_size, num_workers, train_tf,
+                                                  val_tf, train_fs_path, val_fs_path)
+    else:
+        dataset = dataset_name
+        ignore_index_local = getattr(dataset, "ignore_index", 255)
+    evaluator = HbirdEvaluation(
+        feature_extractor, dataset.train_dataloader(), num_classes=dataset.get_num_classes(),
+        n_neighbours=n_neighbours, augmentation_epoch=augmentation_epoch, device=device, nn_method=nn_method,
+        nn_params=nn_params, memory_size=memory_size, dataset_size=dataset.get_train_dataset_size())
+    effective_ignore = ignore_index if ignore_index != 255 else ignore_index_local  # hbird_eval.py:715
+    return evaluator.evaluate(dataset.val_dataloader(), eval_spatial_resolution=S,
+                              return_knn_details=return_knn_details, ignore_index=effective_ignore)

@@ -1,0 +1,73 @@
+"""world_size-2 gloo run of the one-process-per-GPU host logic (hbird_b200.distributed): shard
+bounds, ragged label-table replication, the all-gather layout hb_merge_topk consumes (checked with
+the oracle's shard merge), and the confusion-matrix all-reduce.  CPU only."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from hbird_b200 import distributed as hdist
+from oracle import hbird_oracle as O
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        assert hdist.dist_info() == (rank, world)
+        rng = np.random.default_rng(0)  # same data on every rank
+        N, d, Q, k, C = 301, 16, 23, 30, 5
+        bank = O.normalise_rows(rng.standard_normal((N, d)).astype(np.float32))
+        q = rng.standard_normal((Q, d)).astype(np.float32) * 3
+        labels = rng.integers(0, 50, size=(N, C)).astype(np.int16)
+        a, b = hdist.shard_bounds(N, world, rank)
+        # ragged shards: counts gathered, offsets derived
+        counts = hdist.gather_counts(b - a, torch.device("cpu"))
+        assert counts == [hdist.shard_bounds(N, world, r)[1] - hdist.shard_bounds(N, world, r)[0] for r in range(world)]
+        off = hdist.offsets_from_counts(counts)
+        assert off[rank] == a
+        # label table replication (int16 rows moved as bytes)
+        table = hdist.all_gather_rows(torch.from_numpy(labels[a:b]), counts)
+        assert table.dtype == torch.int16 and np.array_equal(table.numpy(), labels)
+        # per-shard search (oracle stands in for the kernel), gather, merge
+        li, ld = O.search_exact_ip(q, bank[a:b], k)
+        gs, gi = hdist.all_gather_topk(torch.from_numpy(ld), torch.from_numpy(li + a))
+        assert gs.shape == (world, Q, k) and gi.shape == (world, Q, k)
+        mi, md = O.merge_shards(gi.numpy(), gs.numpy(), k)
+        ri, rd = O.search_exact_ip(q, bank, k)
+        assert np.array_equal(mi, ri) and np.array_equal(md, rd)
+        # confusion matrices add up (eval_metrics.py:251-252)
+        conf = torch.full((C, C), rank + 1, dtype=torch.int64)
+        dist.all_reduce(conf, op=dist.ReduceOp.SUM)
+        assert int(conf[0, 0]) == sum(range(1, world + 1))
+        b0, b1 = hdist.split_range(7, world, rank)
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write(f"{b0},{b1}")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_gloo(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    spans = [tuple(map(int, open(tmp_path / f"ok{r}").read().split(","))) for r in range(world)]
+    assert spans[0][0] == 0 and spans[-1][1] == 7 and spans[0][1] == spans[1][0]
+
+
+def test_single_process_helpers():
+    assert hdist.dist_info() == (0, 1)
+    assert hdist.shard_bounds(10, 3, 0) == (0, 3) and hdist.shard_bounds(10, 3, 2) == (6, 10)
+    s, i = torch.zeros(4, 3), torch.zeros(4, 3, dtype=torch.int64)
+    gs, gi = hdist.all_gather_topk(s, i)
+    assert gs.shape == (1, 4, 3) and gi.shape == (1, 4, 3)

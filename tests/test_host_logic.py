@@ -1,0 +1,115 @@
+"""Host-side logic that needs no GPU: metric math vs the reference's known answers, the registry,
+the bounded sampler's RNG parity with the reference, the search work decomposition, the synthetic
+data contract."""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, load_golden
+from hbird_b200 import _capi
+from hbird_b200.data import SyntheticSegmentationData
+from hbird_b200.hbird_eval import HbirdEvaluation
+from hbird_b200.registry import NN_BACKENDS, create_nn_backend, register_nn_backend
+from hbird_b200.utils.eval_metrics import miou_from_confusion
+from oracle import hbird_oracle as O
+
+
+def test_metric_math_reproduces_reference_known_answers():
+    for k in json.load(open(os.path.join(GOLDEN, "ref_kats.json"))):
+        conf = np.array(k["conf"], dtype=np.int64)
+        miou, tp, fp, fn, mapping, bg = miou_from_confusion(
+            conf, many_to_one=k["mode"] == "many_to_one", linear_probe=k["mode"] == "linear_probe")
+        assert miou == pytest.approx(k["miou"], abs=1e-12), k
+        assert (tp, fp, fn) == (k["tp"], k["fp"], k["fn"]), k
+        assert bg == pytest.approx(k["bg"])
+
+
+def test_metric_math_matches_oracle_on_random_matrices():
+    rng = np.random.default_rng(1)
+    for C in (3, 21, 151):
+        conf = rng.integers(0, 1000, size=(C, C)).astype(np.int64)
+        conf[rng.integers(0, C)] = 0  # an absent class still counts in the mean
+        a = miou_from_confusion(conf)
+        b = O.miou_from_confusion(conf)
+        assert a[0] == pytest.approx(b[0], abs=1e-12) and a[1:4] == b[1:4]
+
+
+def test_registry_dispatch_and_errors():
+    assert {"b200", "faiss", "scann"} <= set(NN_BACKENDS)
+    with pytest.raises(ValueError, match="Unsupported NN method"):
+        create_nn_backend("annoy", torch.zeros(2, 8))
+    with pytest.raises(ValueError, match="reference package"):
+        create_nn_backend("faiss", torch.zeros(2, 8))  # legacy names defer to the reference classes
+    register_nn_backend("dummy", lambda fm, n_neighbors=30, **kw: ("dummy", n_neighbors, kw))
+    assert create_nn_backend("dummy", None, n_neighbors=7, a=1) == ("dummy", 7, {"a": 1})
+    NN_BACKENDS.pop("dummy")
+
+
+@pytest.mark.parametrize("name", ["voc_tiny", "ade_tiny"])
+def test_bounded_sampler_host_logic_picks_the_reference_rows(name):
+    """HbirdEvaluation._sample_patches (torch host code + CPU RNG) selects, per image, exactly the
+    patches whose features the reference's bounded bank holds."""
+    cfg, g = load_golden(name + "_bounded")
+    data = SyntheticSegmentationData(**cfg)
+    ms = int(np.load(os.path.join(GOLDEN, f"ref_{name}_bounded.npz"))["memory_size"])
+    K = max(1, ms // data.get_train_dataset_size())
+    stub = HbirdEvaluation.__new__(HbirdEvaluation)
+    stub.num_sampled_features = K
+    torch.manual_seed(123)
+    row = 0
+    for (x, y) in data.train_dataloader():
+        ids = torch.from_numpy(O.decode_mask(y.numpy(), True)).to(torch.uint8)[:, 0]
+        sel = stub._sample_patches(ids, data.S, data.ps, data.C).long()
+        feats = data.ftr_extr_fn(data.model, x)[0].flatten(0, 1)[sel].numpy()
+        mine = O.normalise_rows(feats)
+        ref = g["feature_memory"][row:row + mine.shape[0]]
+        row += mine.shape[0]
+        B = x.shape[0]
+        for b in range(B):
+            dist = np.abs(mine[b * K:(b + 1) * K, None] - ref[None, b * K:(b + 1) * K]).max(axis=2)
+            assert (dist.min(axis=1) <= 1e-6).all()
+    assert row == g["feature_memory"].shape[0]
+
+
+def _plan(rows, Q, cg, sms=148, max_chunks=0):
+    out = (ctypes.c_int * 4)()
+    assert _capi.lib.hb_plan_search(rows, Q, cg, sms, max_chunks, out) == 0
+    return list(out)
+
+
+@pytest.mark.parametrize("rows,Q", [(1, 1), (255, 128), (257, 129), (102400, 12544), (1024000, 12544),
+                                    (10240000, 21904), (12500000, 65536), (1000003, 7)])
+@pytest.mark.parametrize("cg", [1, 2])
+def test_search_plan_covers_every_tile_once(rows, Q, cg):
+    n_tiles, n_qblocks, n_chunks, n_units = _plan(rows, Q, cg)
+    assert n_tiles == (rows + 255) // 256 and n_qblocks == -(-Q // (128 * cg)) and n_units == 148 // cg
+    assert 1 <= n_chunks <= min(64, n_tiles)
+    bounds = [n_tiles * c // n_chunks for c in range(n_chunks + 1)]
+    assert bounds[0] == 0 and bounds[-1] == n_tiles
+    sizes = np.diff(bounds)
+    assert (sizes >= 1).all() and sizes.max() - sizes.min() <= 1  # balanced, no empty chunk
+
+
+def test_search_plan_fills_waves_for_headline_configs():
+    for rows, Q in [(1024000, 12544), (10240000, 21904), (1280000, 21904)]:
+        n_tiles, n_qblocks, n_chunks, n_units = _plan(rows, Q, 2)
+        items = n_qblocks * n_chunks
+        waves = -(-items // n_units)
+        assert items / (waves * n_units) >= 0.95
+    assert _plan(1024000, 12544, 2, max_chunks=1)[2] == 1
+
+
+def test_synthetic_data_contract():
+    d = SyntheticSegmentationData(num_train=3, num_val=2, input_size=32, patch_size=8, d_model=16, num_classes=4,
+                                  batch_size=2, ignore_index=255, cells=2)
+    (x, y), = d.val_dataloader()
+    assert x.shape == (2, 3, 32, 32) and y.shape == (2, 1, 32, 32) and y.dtype == torch.float32
+    ids = (y * 255).long()
+    assert set(ids.unique().tolist()) <= {0, 1, 2, 3, 255}
+    f, aux = d.ftr_extr_fn(d.model, x)
+    assert f.shape == (2, 16, 16) and aux is None
+    assert (f.norm(dim=-1) > 1.5).all()  # queries are NOT unit norm (hbird_eval.py:222-224)
