@@ -114,6 +114,13 @@ int hb_search_config(hb_bank_t* bank, int cta_group, int max_chunks);
 /* Number of kernel launches the last hb_search on this bank issued. */
 int hb_search_last_launches(const hb_bank_t* bank);
 
+/* Kernel timing for roofline reports: when enabled, every hb_search brackets its tcgen05
+ * GEMM+top-k kernel with CUDA events on the launching stream (a ring of 64 pairs).
+ * hb_search_kernel_time synchronises those events and returns the mean duration in ms of the
+ * kernels recorded since timing was (re-)enabled, and how many there were. */
+int hb_search_timing(hb_bank_t* bank, int enable);
+int hb_search_kernel_time(hb_bank_t* bank, float* mean_ms_out, int* count_out);
+
 /* Host-only (no GPU needed): the work decomposition hb_search would use for a bank of `rows`
  * rows and Q queries on `num_sms` SMs.  out4 = {n_tiles, n_qblocks, n_chunks, n_units}; chunk c
  * covers tiles [n_tiles*c/n_chunks, n_tiles*(c+1)/n_chunks) of 256 bank rows. */

@@ -176,6 +176,10 @@ int hb_bank_destroy(hb_bank_t* bank) {
   if (b->feat_f32) cudaFree(b->feat_f32);
   if (b->label_hist) cudaFree(b->label_hist);
   if (b->ws) cudaFree(b->ws);
+  for (int i = 0; i < 64; ++i) {
+    if (b->ev_begin[i]) cudaEventDestroy(b->ev_begin[i]);
+    if (b->ev_end[i]) cudaEventDestroy(b->ev_end[i]);
+  }
   (void)cudaGetLastError();
   delete b;
   return HB_OK;

@@ -55,6 +55,11 @@ struct Bank {
   int cfg_cta_group = 0;
   int cfg_max_chunks = 0;
   int last_launches = 0;
+  // optional kernel timing (hb_search_timing)
+  bool timing = false;
+  int timing_count = 0;
+  cudaEvent_t ev_begin[64] = {};
+  cudaEvent_t ev_end[64] = {};
 };
 
 int ensure_workspace(Bank* b, size_t bytes);

@@ -458,8 +458,14 @@ static int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_
   p.n_tiles = plan.n_tiles;
   p.cand = cand;
   p.dump = dump;
+  const int slot = b->timing_count & 63;
+  if (b->timing) HB_CHECK_CUDA(cudaEventRecord(b->ev_begin[slot], st));
   rc = dispatch_search(b, cg, kp, tmap_q, p, st);
   if (rc != HB_OK) return rc;
+  if (b->timing) {
+    HB_CHECK_CUDA(cudaEventRecord(b->ev_end[slot], st));
+    b->timing_count++;
+  }
   b->last_launches++;
   if (out_scores == nullptr) return HB_OK;  // dump-only call
 
@@ -501,6 +507,38 @@ int hb_search_config(hb_bank_t* bank, int cta_group, int max_chunks) {
   Bank* b = reinterpret_cast<Bank*>(bank);
   b->cfg_cta_group = cta_group;
   b->cfg_max_chunks = max_chunks;
+  return HB_OK;
+}
+
+int hb_search_timing(hb_bank_t* bank, int enable) {
+  HB_REQUIRE(bank != nullptr, "hb_search_timing: bank is NULL");
+  Bank* b = reinterpret_cast<Bank*>(bank);
+  HB_CHECK_CUDA(cudaSetDevice(b->device));
+  if (enable && b->ev_begin[0] == nullptr) {
+    for (int i = 0; i < 64; ++i) {
+      HB_CHECK_CUDA(cudaEventCreate(&b->ev_begin[i]));
+      HB_CHECK_CUDA(cudaEventCreate(&b->ev_end[i]));
+    }
+  }
+  b->timing = enable != 0;
+  b->timing_count = 0;
+  return HB_OK;
+}
+
+int hb_search_kernel_time(hb_bank_t* bank, float* mean_ms_out, int* count_out) {
+  HB_REQUIRE(bank != nullptr && mean_ms_out != nullptr && count_out != nullptr, "hb_search_kernel_time: NULL argument");
+  Bank* b = reinterpret_cast<Bank*>(bank);
+  HB_CHECK_CUDA(cudaSetDevice(b->device));
+  const int n = b->timing_count < 64 ? b->timing_count : 64;
+  double sum = 0.0;
+  for (int i = 0; i < n; ++i) {
+    float ms = 0.f;
+    HB_CHECK_CUDA(cudaEventSynchronize(b->ev_end[i]));
+    HB_CHECK_CUDA(cudaEventElapsedTime(&ms, b->ev_begin[i], b->ev_end[i]));
+    sum += ms;
+  }
+  *mean_ms_out = n ? static_cast<float>(sum / n) : 0.f;
+  *count_out = n;
   return HB_OK;
 }
 

@@ -140,6 +140,17 @@ class MemoryBank:
                             ptr(qn), stream_ptr(q.device)))
         return scores, idx, qn
 
+    def enable_kernel_timing(self, enable: bool = True) -> None:
+        check(lib.hb_search_timing(self._h, int(enable)))
+
+    def kernel_time_ms(self):
+        """(mean ms, count) of the tcgen05 search kernel over the searches since timing was enabled."""
+        import ctypes
+
+        ms, n = ctypes.c_float(0), ctypes.c_int(0)
+        check(lib.hb_search_kernel_time(self._h, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
+
     def last_search_launches(self) -> int:
         return int(lib.hb_search_last_launches(self._h))
 

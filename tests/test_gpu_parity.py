@@ -1,0 +1,359 @@
+"""Parity tests proper: every CUDA kernel is called through the C-ABI (hbird_b200.ops ->
+libhbird_b200.so) and compared with the CPU oracle on the same seeded inputs and with the golden
+fixtures produced by the unmodified reference.  Gates (BASELINE.json north_star):
+recall@30 >= 0.999, neighbour scores within 1e-3 relative, confusion matrix bit-exact for
+identical predictions, mIoU within 0.05 points (5e-4 on the [0,1] scale)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import batches_np, load_golden, recall
+from hbird_b200 import HbirdEvaluation, NearestNeighborSearchB200, hbird_evaluation, ops
+from hbird_b200.data import SyntheticSegmentationData
+from hbird_b200.models import FeatureExtractorSimple
+from oracle import hbird_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+CASES = ["voc_tiny", "ade_tiny"]
+
+
+def cuda(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    return t.to(dtype) if dtype is not None else t
+
+
+@pytest.fixture(scope="module", params=CASES)
+def case(request):
+    cfg, g = load_golden(request.param)
+    return cfg, g, SyntheticSegmentationData(**cfg)
+
+
+def build_bank_from_loader(data, keep_f32=True):
+    bank = None
+    for x, y in data.train_dataloader():
+        f, _ = data.ftr_extr_fn(data.model, x)
+        B, _, H, W = x.shape
+        mask = ops.decode_mask(y.to(DEV).contiguous(), True).view(B, H, W)
+        if bank is None:
+            cap = data.get_train_dataset_size() * data.S * data.S
+            bank = ops.MemoryBank(data.d, data.C, data.ps * data.ps, cap, 0, keep_f32)
+        bank.append(f.to(DEV).contiguous(), mask, data.S, data.ps)
+    bank.finalize()
+    return bank
+
+
+def bank_from_rows(rows: torch.Tensor, keep_f32=True, normalise=True):
+    n, d = rows.shape
+    bank = ops.MemoryBank(d, 1, 1, n, 0, keep_f32)
+    one = torch.ones((min(n, 1 << 20), 1), device=DEV)
+    for a in range(0, n, 1 << 20):
+        blk = rows[a:a + (1 << 20)]
+        bank.append_soft(blk.contiguous(), one[:blk.shape[0]], normalise=normalise)
+    bank.finalize()
+    return bank
+
+
+# ------------------------------------------------------------------ K5 / A0: decode + confusion
+def test_decode_mask_all_byte_values_exact():
+    ids = np.arange(256, dtype=np.float32)
+    y = (ids / np.float32(255)).astype(np.float32)
+    for remap in (False, True):
+        got = ops.decode_mask(cuda(y), remap).cpu().numpy()
+        np.testing.assert_array_equal(got, O.decode_mask(y, remap).astype(np.uint8))
+
+
+@pytest.mark.parametrize("C,n,ignore", [(21, 1_000_003, 255), (151, 2_000_017, 0), (3, 7, 255), (6, 12288, None), (200, 65536, 255)])
+def test_confusion_bit_exact_vs_oracle(C, n, ignore):
+    rng = np.random.default_rng(C + n)
+    gt = rng.integers(0, min(C + 4, 256), size=n).astype(np.uint8)
+    # blocky runs like a real mask, plus ignore pixels and out-of-range ids
+    gt = np.repeat(gt[: n // 13 + 1], 13)[:n].copy()
+    gt[::17] = 255
+    pred = np.repeat(rng.integers(0, min(C + 2, 256), size=n // 5 + 1).astype(np.uint8), 5)[:n].copy()
+    conf = torch.zeros((C, C), dtype=torch.int64, device=DEV)
+    tg, tp = cuda(gt), cuda(pred)
+    ops.confusion_accumulate(conf, tg, tp, ignore)
+    ops.confusion_accumulate(conf, tg[1:], tp[1:], ignore)  # unaligned device pointers; accumulates
+    ref = O.confusion_matrix(gt, pred, C, C, ignore) + O.confusion_matrix(gt[1:], pred[1:], C, C, ignore)
+    np.testing.assert_array_equal(conf.cpu().numpy(), ref)
+
+
+def test_confusion_matches_reference_golden(case):
+    cfg, g, data = case
+    conf = torch.zeros((data.C, data.C), dtype=torch.int64, device=DEV)
+    ops.confusion_accumulate(conf, cuda(g["gt"].astype(np.uint8)), cuda(g["pred"]), data.ignore_index)
+    np.testing.assert_array_equal(conf.cpu().numpy(), g["conf"])
+
+
+# ------------------------------------------------------------------ K1: bank construction
+def test_bank_pack_matches_reference_golden(case):
+    cfg, g, data = case
+    bank = build_bank_from_loader(data)
+    f, l = bank.export()
+    assert bank.rows == g["feature_memory"].shape[0]
+    np.testing.assert_allclose(f.cpu().numpy(), g["feature_memory"], rtol=0, atol=2e-7)
+    np.testing.assert_array_equal(l.cpu().numpy(), g["label_memory"])
+    # bf16 copy = round-to-nearest of the same unit rows
+    nb = build_bank_from_loader(data, keep_f32=False)
+    fb16, _ = nb.export()
+    ref16 = torch.from_numpy(g["feature_memory"]).to(torch.bfloat16).float().numpy()
+    assert np.abs(fb16.cpu().numpy() - ref16).max() <= 2 ** -8  # at most one bf16 ulp from rounding order
+    bank.close(), nb.close()
+
+
+def test_bank_append_validation_errors():
+    bank = ops.MemoryBank(64, 3, 16, 32, 0, True)
+    feats = torch.zeros((1, 4, 64), device=DEV)
+    with pytest.raises(ValueError):
+        bank.append(feats, torch.zeros((1, 9, 9), dtype=torch.uint8, device=DEV), 2, 4)  # wrong mask size
+    with pytest.raises(ValueError):
+        bank.append(torch.zeros((9, 4, 64), device=DEV), torch.zeros((9, 8, 8), dtype=torch.uint8, device=DEV), 2, 4)  # capacity
+    with pytest.raises(RuntimeError):
+        bank.search(torch.zeros((1, 64), device=DEV))  # not finalized
+    with pytest.raises(ValueError):
+        ops.MemoryBank(63, 3, 16, 32, 0, True)  # d must be a multiple of 8
+    bank.close()
+
+
+# ------------------------------------------------------------------ K2 + K2b: search
+def check_search(scores, idx, q_np, bank_np, k=30, min_recall=0.999):
+    ri, rd = O.search_exact_ip(q_np, bank_np, k)
+    s, i = scores.cpu().numpy(), idx.cpu().numpy()
+    assert (np.diff(s, axis=1) <= 0).all(), "scores must be sorted descending"
+    assert recall(i, ri) >= min_recall
+    rel = np.abs(s - rd) / np.maximum(np.abs(rd), 1e-6)
+    assert rel.max() <= 1e-3
+    # every returned (score, idx) pair is a true inner product
+    true = np.einsum("qd,qkd->qk", q_np, bank_np[i])
+    assert np.abs(true - s).max() <= 1e-4 * max(1.0, np.abs(s).max())
+
+
+def test_search_matches_reference_golden(case):
+    cfg, g, data = case
+    bank = build_bank_from_loader(data)
+    q = np.concatenate([f.reshape(-1, f.shape[-1]) for f, _ in batches_np(data, data.val_dataloader())])
+    for cg in (1, 2):
+        bank.configure_search(cta_group=cg)
+        s, i, qn = bank.search(cuda(q), 30, 64)
+        check_search(s, i, q, g["feature_memory"])
+        assert recall(i.cpu().numpy(), g["knn_idx"]) >= 0.999
+        rel = np.abs(s.cpu().numpy() - g["knn_dist"]) / np.abs(g["knn_dist"])
+        assert rel.max() <= 1e-3
+        np.testing.assert_allclose(qn.cpu().numpy(), np.linalg.norm(q, axis=1), rtol=1e-6)
+    bank.close()
+
+
+@pytest.mark.parametrize("N,d,Q,kp", [(102400, 384, 1536, 64), (5000, 384, 1000, 64), (40000, 768, 300, 128),
+                                      (257, 64, 129, 64), (2049, 1024, 1, 64), (70000, 200, 333, 64)])
+def test_search_vs_oracle_seeded(N, d, Q, kp):
+    g = torch.Generator().manual_seed(N + d)
+    rows = torch.randn((N, d), generator=g)
+    pick = torch.randint(0, N, (Q,), generator=g)
+    q = (rows[pick] / rows[pick].norm(dim=1, keepdim=True) + 0.05 * torch.randn((Q, d), generator=g)) * 3.7
+    bank = bank_from_rows(rows.to(DEV))
+    s, i, _ = bank.search(q.to(DEV), 30, kp)
+    fb, _ = bank.export()
+    check_search(s, i, q.numpy(), fb.cpu().numpy())
+    bank.close()
+
+
+def test_search_pads_like_faiss_when_bank_smaller_than_k():
+    rows = torch.eye(8, 64)
+    bank = bank_from_rows(rows.to(DEV))
+    s, i, _ = bank.search(torch.ones((3, 64), device=DEV), 30, 64)
+    s, i = s.cpu().numpy(), i.cpu().numpy()
+    assert (i[:, 8:] == -1).all() and np.isneginf(s[:, 8:]).all()
+    assert sorted(i[0, :8].tolist()) == list(range(8)) and np.allclose(s[:, :8], 1.0)
+    # ties: equal scores come back with the smaller index first
+    assert i[0, :8].tolist() == list(range(8))
+    bank.close()
+
+
+def test_search_argument_errors_and_empty_query():
+    bank = bank_from_rows(torch.randn((300, 64), device=DEV))
+    with pytest.raises(ValueError):
+        bank.search(torch.zeros((2, 32), device=DEV))  # wrong d
+    with pytest.raises(ValueError):
+        bank.search(torch.zeros((2, 64), device=DEV), 30, 48)  # k_prime not in {32,64,128}
+    with pytest.raises(ValueError):
+        bank.search(torch.zeros((2, 64), device=DEV), 65, 64)  # k > k_prime
+    with pytest.raises(RuntimeError):
+        bank.search(torch.zeros((2, 64)))  # CPU tensor: no fallback
+    s, i, _ = bank.search(torch.zeros((0, 64), device=DEV))
+    assert s.shape == (0, 30) and i.shape == (0, 30)
+    bank.close()
+
+
+def test_plugin_contract_matches_faiss_backend():
+    """find_nearest_neighbors(q) -> host (indices int64, distances fp32), indices first
+    (search_faiss.py:83-90); the ctor takes the CPU fp32 bank the reference hands over."""
+    rng = np.random.default_rng(3)
+    fm = O.normalise_rows(rng.standard_normal((3000, 128)).astype(np.float32))
+    q = rng.standard_normal((77, 128)).astype(np.float32) * 2
+    nn = NearestNeighborSearchB200(torch.from_numpy(fm), n_neighbors=30)
+    idx, dist = nn.find_nearest_neighbors(torch.from_numpy(q))
+    assert isinstance(idx, np.ndarray) and idx.dtype == np.int64 and dist.dtype == np.float32
+    ri, rd = O.search_exact_ip(q, fm, 30)
+    assert recall(idx, ri) >= 0.999 and np.abs(dist - rd).max() <= 1e-3 * np.abs(rd).max()
+    idx5, _ = nn.find_nearest_neighbors(q, k=5)
+    assert idx5.shape == (77, 5) and recall(idx5, ri[:, :5]) >= 0.995
+    with pytest.raises(ValueError, match="Unsupported distance measure"):
+        NearestNeighborSearchB200(torch.from_numpy(fm), distance_measure="l2")
+    with pytest.raises(ValueError, match="Invalid GPU ID"):
+        NearestNeighborSearchB200(torch.from_numpy(fm), gpu_ids=[99])
+
+
+# ------------------------------------------------------------------ K3: merge
+def test_merge_topk_equals_oracle_and_unsharded_search():
+    g = torch.Generator().manual_seed(5)
+    rows = torch.randn((30011, 128), generator=g)
+    q = torch.randn((257, 128), generator=g) * 2
+    whole = bank_from_rows(rows.to(DEV))
+    s0, i0, _ = whole.search(q.to(DEV), 30, 64)
+    G = 4
+    ss, si = [], []
+    for r in range(G):
+        a, b = 30011 * r // G, 30011 * (r + 1) // G
+        shard = bank_from_rows(rows[a:b].to(DEV))
+        s, i, _ = shard.search(q.to(DEV), 30, 64, idx_offset=a)
+        ss.append(s), si.append(i)
+        shard.close()
+    ms, mi = ops.merge_topk(torch.stack(ss), torch.stack(si))
+    oi, od = O.merge_shards(torch.stack(si).cpu().numpy(), torch.stack(ss).cpu().numpy(), 30)
+    np.testing.assert_array_equal(mi.cpu().numpy(), oi)
+    np.testing.assert_array_equal(ms.cpu().numpy(), od)
+    # sharded == unsharded (same exact fp32 re-rank on both sides)
+    assert recall(mi.cpu().numpy(), i0.cpu().numpy()) >= 0.9999
+    np.testing.assert_allclose(ms.cpu().numpy(), s0.cpu().numpy(), rtol=1e-6, atol=1e-6)
+    whole.close()
+
+
+# ------------------------------------------------------------------ K4: label transfer, upsample + argmax
+def test_label_transfer_matches_reference_golden(case):
+    cfg, g, data = case
+    bank = build_bank_from_loader(data)
+    q = np.concatenate([f.reshape(-1, f.shape[-1]) for f, _ in batches_np(data, data.val_dataloader())])
+    qn = np.linalg.norm(q, axis=1).astype(np.float32)
+    lh = ops.label_transfer(bank.label_table(), data.ps * data.ps, cuda(g["knn_dist"]), cuda(g["knn_idx"]),
+                            cuda(qn), 0.02)
+    ref = g["label_hat"].reshape(-1, data.C)
+    np.testing.assert_allclose(lh.cpu().numpy(), ref, rtol=0, atol=1e-5)
+    assert (lh.cpu().numpy().argmax(1) == ref.argmax(1)).mean() >= 0.999
+    bank.close()
+
+
+def test_upsample_argmax_matches_reference_golden(case):
+    cfg, g, data = case
+    n_img = g["pred"].shape[0]
+    lh = cuda(g["label_hat"].reshape(-1, data.C))
+    pred = ops.upsample_argmax(lh, n_img, data.S, data.H, data.H)
+    assert (pred.cpu().numpy() == g["pred"][:, 0]).mean() >= 0.9999
+
+
+@pytest.mark.parametrize("B,S,C,H", [(2, 14, 21, 224), (1, 37, 151, 518), (3, 5, 2, 33)])
+def test_upsample_argmax_vs_oracle(B, S, C, H):
+    rng = np.random.default_rng(S)
+    lh = rng.random((B, S * S, C)).astype(np.float32)
+    pred = ops.upsample_argmax(cuda(lh.reshape(-1, C)), B, S, H, H).cpu().numpy()
+    ref = O.predict_map(lh, S, H, H)[:, 0]
+    assert (pred == ref).mean() >= 0.9999
+
+
+# ------------------------------------------------------------------ end to end
+def run_engine(data, **kw):
+    fe = FeatureExtractorSimple(data.model, data.ftr_extr_fn, data.S, data.d)
+    ev = HbirdEvaluation(fe, data.train_dataloader(), num_classes=data.C, n_neighbours=30, device=DEV,
+                         nn_method="b200", dataset_size=data.get_train_dataset_size(), **kw)
+    return ev
+
+
+def test_engine_end_to_end_matches_reference(case):
+    cfg, g, data = case
+    ev = run_engine(data)
+    miou, det = ev.evaluate(data.val_dataloader(), data.S, return_knn_details=True, ignore_index=data.ignore_index)
+    assert isinstance(miou, float)
+    assert abs(miou - float(g["miou"])) <= 5e-4  # 0.05 points
+    conf = ev.last_confusion
+    assert conf.sum() == g["conf"].sum()  # same pixels counted: integer bookkeeping is exact
+    assert np.abs(conf - g["conf"]).sum() <= 2e-4 * conf.sum()
+    np.testing.assert_allclose(det["knns_ca_labels"].numpy(), g["label_hat"], rtol=0, atol=2e-5)
+    assert det["knns"].shape == g["label_hat"].shape[:2] + (30, data.d)
+    assert det["knns_labels"].shape == g["label_hat"].shape[:2] + (30, data.C)
+    # exported memory is the reference's feature_memory / label_memory
+    np.testing.assert_allclose(ev.feature_memory.numpy(), g["feature_memory"], atol=2e-7, rtol=0)
+    np.testing.assert_array_equal(ev.label_memory.numpy(), g["label_memory"])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_engine_bounded_memory_matches_reference(name):
+    cfg, g = load_golden(name + "_bounded")
+    data = SyntheticSegmentationData(**cfg)
+    torch.manual_seed(123)  # the sampler draws from the CPU generator, as the reference does
+    ev = run_engine(data, memory_size=int(g["memory_size"]))
+    assert ev.bank.rows == g["feature_memory"].shape[0]
+    miou = ev.evaluate(data.val_dataloader(), data.S, ignore_index=data.ignore_index)
+    assert abs(miou - float(g["miou"])) <= 5e-4
+    assert np.abs(ev.last_confusion - g["conf"]).sum() <= 5e-4 * g["conf"].sum()
+
+
+def test_hbird_evaluation_entry_point():
+    cfg, g = load_golden("voc_tiny")
+    data = SyntheticSegmentationData(**cfg)
+    miou = hbird_evaluation(data.model, d_model=data.d, patch_size=data.ps, dataset_name=data, data_dir="",
+                            batch_size=cfg["batch_size"], input_size=cfg["input_size"], device=DEV,
+                            n_neighbours=30, nn_method="b200", nn_params={"k_prime": 64},
+                            ftr_extr_fn=data.ftr_extr_fn)
+    assert abs(miou - float(g["miou"])) <= 5e-4
+    with pytest.raises(ValueError, match="Unsupported NN method"):
+        hbird_evaluation(data.model, data.d, data.ps, data, "", device=DEV, nn_method="annoy",
+                         input_size=cfg["input_size"], ftr_extr_fn=data.ftr_extr_fn)
+
+
+# ------------------------------------------------------------------ BASELINE-size properties (cfg2 shape)
+@pytest.fixture(scope="module")
+def big_bank():
+    N, d = 1_024_000, 384
+    g = torch.Generator(device=DEV).manual_seed(1)
+    rows = torch.randn((N, d), generator=g, device=DEV)
+    bank = bank_from_rows(rows)
+    del rows
+    yield bank
+    bank.close()
+
+
+def test_full_size_self_retrieval_sorted_idempotent(big_bank):
+    """N = 1,024,000 x 384 (BASELINE configs[1]): a query that is a scaled bank row must retrieve
+    that row first with score == scale; output sorted; the search is deterministic."""
+    g = torch.Generator(device=DEV).manual_seed(2)
+    pick = torch.randint(0, big_bank.rows, (12544,), generator=g, device=DEV)
+    f, _ = big_bank.export(0, big_bank.rows, labels=False)
+    scale = torch.rand((12544, 1), generator=g, device=DEV) * 5 + 0.5
+    q = f[pick] * scale
+    s, i, qn = big_bank.search(q, 30, 64)
+    assert bool((i[:, 0] == pick).all())
+    assert torch.allclose(s[:, 0], scale[:, 0], rtol=1e-5)
+    assert bool((s[:, :-1] >= s[:, 1:]).all())
+    assert bool(((i >= 0) & (i < big_bank.rows)).all())
+    assert int((i.sort(dim=1).values.diff(dim=1) == 0).sum()) == 0  # no duplicate neighbours
+    s2, i2, _ = big_bank.search(q, 30, 64)
+    assert torch.equal(s, s2) and torch.equal(i, i2)
+    # linearity of the metric: scaling a query scales its scores and keeps its neighbours
+    s3, i3, _ = big_bank.search(q[:512] * 2.0, 30, 64)
+    assert torch.equal(i3, i[:512]) and torch.allclose(s3, 2 * s[:512], rtol=1e-5)
+
+
+def test_full_size_recall_vs_exact_fp32(big_bank):
+    g = torch.Generator(device=DEV).manual_seed(4)
+    q = torch.randn((2048, 384), generator=g, device=DEV) * 3
+    f, _ = big_bank.export(0, big_bank.rows, labels=False)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref = (q @ f.T).topk(30, dim=1)
+    for cg in (1, 2):
+        big_bank.configure_search(cta_group=cg)
+        s, i, _ = big_bank.search(q, 30, 64)
+        hit = (i.unsqueeze(2) == ref.indices.unsqueeze(1)).any(2).float().mean().item()
+        assert hit >= 0.999
+        rel = ((s - ref.values).abs() / ref.values.abs()).max().item()
+        assert rel <= 1e-3
+    big_bank.configure_search(cta_group=0)
