@@ -99,7 +99,7 @@ int hb_bank_export(const hb_bank_t* bank, int64_t row0, int64_t n, float* feats_
  * Replaces NearestNeighborSearchFaiss.find_nearest_neighbors (search_faiss.py:83-90),
  * i.e. GpuIndexFlatIP.search: exact top-k by inner product of the raw (un-normalised)
  * queries against the unit-norm bank rows, sorted by descending score.
- * q_dev: fp32 (Q, d).  k <= k_prime, k_prime in {32, 64, 128}: the tcgen05 bf16 pass keeps
+ * q_dev: fp32 (Q, d).  k <= k_prime, k_prime in {32, 64}: the tcgen05 bf16 pass keeps
  * k_prime candidates per query, the fp32 pass re-scores them exactly and keeps k.
  * out_scores_dev fp32 (Q, k); out_idx_dev int64 (Q, k) = row index + idx_offset (the
  * shard's first global row); out_qnorm_dev fp32 (Q,) = ||q||_2 or NULL.  If the bank
@@ -111,6 +111,10 @@ int hb_search(hb_bank_t* bank, const float* q_dev, int64_t Q, int k, int k_prime
 /* Tuning/diagnostics for hb_search: cta_group (1 or 2; 0 = library default),
  * max_chunks (bank split per query block; 0 = auto). */
 int hb_search_config(hb_bank_t* bank, int cta_group, int max_chunks);
+/* L2 prefetch distance (in 256-row bank tiles) of the search kernel's TMA producer; 0 = off.
+ * ablate is a MEASUREMENT-ONLY switch (results are wrong when it is non-zero): 1 = the epilogue
+ * releases accumulators unread (pure GEMM pipeline), 2 = it scans but never inserts. */
+int hb_search_tune(hb_bank_t* bank, int prefetch_tiles, int ablate);
 /* Number of kernel launches the last hb_search on this bank issued. */
 int hb_search_last_launches(const hb_bank_t* bank);
 

@@ -57,9 +57,11 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 __device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Arrive on a barrier that lives in another CTA of the cluster (address from mapa()).
+// Arrive on a barrier that lives in another CTA of the cluster (address from mapa()).  Default
+// semantics (release at CTA scope): the data handed over is TMEM, ordered by tcgen05.fence, so no
+// GPU-scope memory fence is wanted here (an explicit .release.cluster costs a MEMBAR.ALL.GPU).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -109,6 +111,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void* tmap,
         ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
   }
+}
+
+// Pull a 2-D tile into L2 only (no shared-memory destination, no barrier).
+__device__ __forceinline__ void tma_prefetch_2d(const void* tmap, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1)
+               : "memory");
 }
 
 // ---- tcgen05 -------------------------------------------------------------------------

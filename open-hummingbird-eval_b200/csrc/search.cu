@@ -4,18 +4,21 @@
 // exact fp32 re-rank that restores the reference's metric is K2b in rerank.cu).
 //
 // Structure (one persistent CTA, or CTA pair with cta_group::2, per SM):
-//   warp 0      TMA producer: streams 128x64 query tiles and (256/CG)x64 bank tiles (bf16,
+//   warp 8      TMA producer: streams 128x64 query tiles and (256/CG)x64 bank tiles (bf16,
 //               128B-swizzled) through a STAGES-deep shared-memory ring.
-//   warp 1      tcgen05.mma issuer (one lane; pair leader only): 128*CG x 256 x 16 UMMAs into one
+//   warp 9      tcgen05.mma issuer (one lane; pair leader only): 128*CG x 256 x 16 UMMAs into one
 //               of two 256-column TMEM accumulators; tcgen05.commit frees ring slots and
 //               publishes finished accumulators.  Also owns TMEM alloc/dealloc.
-//   warps 2..9  epilogue: each thread owns ONE query row (TMEM lane) and one 128-column half of the
-//               tile.  It scans its scores against a running threshold tau (a lower bound of its
-//               current k'/2-th best): a max-tree + one vote rejects 32 columns at a time; the rare
-//               survivors are appended to a small per-thread queue in shared memory, and when any
-//               lane's queue fills, the whole warp merges queues into per-thread sorted lists with
-//               fully unrolled bitonic networks (lock-step, no divergence) and tightens tau.
-//               Accumulator double-buffering overlaps this scan with the MMAs of the next tile.
+//   warps 0..7  epilogue: each thread owns ONE query row (TMEM lane) and one 128-column half of the
+//               tile, and keeps its k'/2 best (score, row) pairs as a SORTED LIST IN REGISTERS.
+//               A max-tree + one vote rejects 32 columns at a time against tau = the list's last
+//               score; a survivor is bubbled into the list by a fully unrolled compare/select
+//               chain executed in lock-step by the warp (no shared memory, no divergence).
+//               Shared memory is left entirely to the TMA ring.  Accumulator double-buffering
+//               overlaps this scan with the MMAs of the next tile.
+// The two single-thread roles sit in the HIGHEST warp ids on purpose: the SM's warp arbiter
+// favours higher warp ids, so the TMA/MMA issue slots are never starved by the ALU-heavy
+// selection warps that share their scheduler.
 // Work item = (query block of 128*CG rows) x (bank chunk of consecutive 256-row tiles); items are
 // dealt round-robin to the persistent CTAs so that concurrently running CTAs walk the same bank
 // tiles (L2 reuse) with different queries.  Each item emits k' unsorted candidate keys per query.
@@ -32,8 +35,9 @@ constexpr int BN = 256;   // bank rows per tile (UMMA N)
 constexpr int BK = 64;    // bf16 per k-block: one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int kEpiWarps = 8;   // 4 TMEM lane quarters x 2 column halves
-constexpr int kQueueCap = 16;  // per-thread pending-candidate queue
 constexpr int kSearchThreads = 32 * (2 + kEpiWarps);
+constexpr int kProducerWarp = kEpiWarps;      // warp 8
+constexpr int kMmaWarp = kEpiWarps + 1;       // warp 9
 constexpr int kTmemCols = 512;
 
 struct SearchParams {
@@ -44,7 +48,10 @@ struct SearchParams {
   int n_chunks;        // bank chunks per query block
   int n_tiles;         // ceil(n_rows / 256)
   uint64_t* cand;      // (n_chunks, n_qblocks*128*CG, KP) candidate keys
+  uint32_t* tau_seed;  // (n_qblocks*128*CG) per-query shared threshold, ordered-float bits (0 = none yet)
   float* dump;         // optional (n_queries, n_rows) raw scores (validation only)
+  int prefetch_tiles;  // > 0: L2-prefetch bank tiles this many tiles ahead (split over the CTAs)
+  int ablate;          // measurement only: 1 = release accumulators unread, 2 = scan but never insert
 };
 
 template <int CG, int STAGES, int KP>
@@ -53,71 +60,29 @@ struct SearchSmem {
   static constexpr int kBBytes = (BN / CG) * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kRingBytes = STAGES * kStageBytes;
-  static constexpr int kHeapBytes = (KP + 2 * kQueueCap) * BM * 8;  // 2 x (list k'/2 + queue) per row
-  static constexpr int kBarOffset = kRingBytes + kHeapBytes;
+  static constexpr int kBarOffset = kRingBytes;
   static constexpr int kNumBars = 2 * STAGES + 4;
   static constexpr int kTotal = kBarOffset + kNumBars * 8 + 16;
   static constexpr int kDynamic = kTotal + 1024;  // slack to align the ring to 1024 B
   static_assert(kDynamic <= 227 * 1024, "search kernel shared memory exceeds 227 KB");
 };
 
-// ---- per-thread candidate selection state in shared memory -------------------------------
-// Entry j of the thread owning tile row t lives at base[j*BM + t]: every lane of a warp touches a
-// different bank for any j, so the lock-step networks below are conflict-free.
-
-// One compare-exchange stage (K, J) of a bitonic network over N keys.
-template <int N, int K, int J, bool DESC>
-__device__ __forceinline__ void bitonic_stage(uint64_t* a) {
+// ---- per-thread candidate list in registers ---------------------------------------------------
+// ls[] descending scores, li[] their bank rows.  Inserting x bubbles it down the list; a lane that
+// has nothing to insert passes x = -inf, which leaves its list untouched.  Fully unrolled: every
+// index is a compile-time constant, so the list never leaves the register file.
+template <int KL>
+__device__ __forceinline__ void list_insert(float (&ls)[KL], uint32_t (&li)[KL], float x, uint32_t row) {
 #pragma unroll
-  for (int i = 0; i < N / 2; ++i) {
-    const int e = ((i & ~(J - 1)) << 1) | (i & (J - 1));
-    const int p = e | J;
-    const bool asc = ((e & K) == 0) != DESC;
-    const uint64_t x = a[e * BM], y = a[p * BM];
-    const bool sw = asc ? (x > y) : (x < y);
-    a[e * BM] = sw ? y : x;
-    a[p * BM] = sw ? x : y;
+  for (int i = 0; i < KL; ++i) {
+    const bool gt = x > ls[i];
+    const float hs = gt ? x : ls[i];
+    const uint32_t hi = gt ? row : li[i];
+    x = gt ? ls[i] : x;
+    row = gt ? li[i] : row;
+    ls[i] = hs;
+    li[i] = hi;
   }
-}
-template <int N, int K, int J, bool DESC>
-struct BitonicJ {
-  static __device__ __forceinline__ void run(uint64_t* a) {
-    bitonic_stage<N, K, J, DESC>(a);
-    if constexpr (J > 1) BitonicJ<N, K, J / 2, DESC>::run(a);
-  }
-};
-template <int N, int K, bool DESC>
-struct BitonicK {  // full sort: stages K = 2, 4, ..., N
-  static __device__ __forceinline__ void run(uint64_t* a) {
-    if constexpr (K > 2) BitonicK<N, K / 2, DESC>::run(a);
-    BitonicJ<N, K, K / 2, DESC>::run(a);
-  }
-};
-// Sort N keys / merge a bitonic sequence of N keys (DESC: largest first).
-template <int N, bool DESC>
-__device__ __forceinline__ void smem_sort(uint64_t* a) { BitonicK<N, N, DESC>::run(a); }
-template <int N, bool DESC>
-__device__ __forceinline__ void smem_bitonic_merge(uint64_t* a) { BitonicJ<N, N, N / 2, DESC>::run(a); }
-
-// Fold the `cnt` queued keys into the sorted (descending) list of KL keys; returns the new tau.
-template <int KL, int QC>
-__device__ __noinline__ float merge_queue(uint64_t* list, uint64_t* queue, int cnt) {
-  for (int j = cnt; j < QC; ++j) queue[j * BM] = 0ull;  // key 0 sorts below every real score
-  smem_sort<QC, false>(queue);                          // ascending
-  uint64_t* tail = list + (KL - QC) * BM;               // the QC smallest kept keys, descending
-#pragma unroll
-  for (int i = 0; i < QC; ++i) {
-    const uint64_t t = tail[i * BM], q = queue[i * BM];
-    tail[i * BM] = t > q ? t : q;                       // QC largest of (tail U queue), bitonic
-  }
-  if constexpr (KL > QC) {
-    smem_bitonic_merge<QC, false>(tail);                // ... ascending
-    smem_bitonic_merge<KL, true>(list);                 // [descending head | ascending tail] -> sorted
-  } else {
-    smem_bitonic_merge<QC, true>(tail);
-  }
-  const uint64_t worst = list[(KL - 1) * BM];
-  return worst ? key_score(worst) : -INFINITY;
 }
 
 template <int CG, int STAGES, int KP>
@@ -131,7 +96,6 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   uint8_t* smem = smem_raw + pad;
   const uint32_t smem_base = raw_addr + pad;
 
-  uint64_t* heap_base = reinterpret_cast<uint64_t*>(smem + L::kRingBytes);
   const uint32_t bar_base = smem_base + L::kBarOffset;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -146,7 +110,7 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const int n_clusters = (CG == 2) ? static_cast<int>(ptx::num_clusters_x()) : static_cast<int>(gridDim.x);
 
   // ---- one-time setup ----
-  if (warp == 0 && lane == 0) {
+  if (warp == kProducerWarp && lane == 0) {
     ptx::prefetch_tmap(&tmap_q);
     ptx::prefetch_tmap(&tmap_bank);
     for (int s = 0; s < STAGES; ++s) {
@@ -159,7 +123,7 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
     }
     ptx::fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     ptx::tmem_alloc<CG>(smem_u32(tmem_slot), kTmemCols);
     ptx::tmem_relinquish<CG>();
   }
@@ -171,7 +135,7 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const int total_items = p.n_qblocks * p.n_chunks;
   const int nkb = p.num_kblocks;
 
-  if (warp == 0) {
+  if (warp == kProducerWarp) {
     // =========================== TMA producer ===========================
     int stage = 0;
     uint32_t phase = 0;
@@ -194,13 +158,18 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             if (is_leader) ptx::mbar_arrive_expect_tx(full_bar(stage), L::kStageBytes * CG);
             ptx::tma_load_2d<CG>(a_dst, &tmap_q, bar, kb * BK, q_row);
             ptx::tma_load_2d<CG>(b_dst, &tmap_bank, bar, kb * BK, b_row);
+            // bank tiles are shared by all CTAs walking this chunk: each (tile, k-block) box is
+            // pulled into L2 ahead of time by exactly one of them
+            if (p.prefetch_tiles > 0 && tile + p.prefetch_tiles < t1 &&
+                (tile * nkb + kb) % n_clusters == cluster_id)
+              ptx::tma_prefetch_2d(&tmap_bank, kb * BK, b_row + p.prefetch_tiles * BN);
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // =========================== MMA issuer ===========================
     if (is_leader) {
       constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(BM * CG, BN);
@@ -243,12 +212,9 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   } else {
     // =========================== epilogue: fused top-k' ===========================
     constexpr int KL = KP / 2;                    // list length per (row, column half)
-    constexpr int QC = kQueueCap < KL ? kQueueCap : KL;
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
-    const int half = (warp - 2) >> 2;             // which 128 columns of the tile
+    const int half = warp >> 2;                   // which 128 columns of the tile
     const int row_in_tile = quarter * 32 + lane;  // query row owned by this thread
-    uint64_t* list = heap_base + (half * KL) * BM + row_in_tile;
-    uint64_t* queue = heap_base + (KP + half * kQueueCap) * BM + row_in_tile;
     const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + half * (BN / 2);
     const uint32_t tempty_leader0 = (CG == 2) ? ptx::mapa(tempty_bar(0), 0) : tempty_bar(0);
     const uint32_t tempty_leader1 = (CG == 2) ? ptx::mapa(tempty_bar(1), 0) : tempty_bar(1);
@@ -259,20 +225,37 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       const int t0 = chunk_tile_begin(p.n_tiles, p.n_chunks, chunk);
       const int t1 = chunk_tile_begin(p.n_tiles, p.n_chunks, chunk + 1);
       const int64_t q_row = static_cast<int64_t>(qb * CG + static_cast<int>(cta_rank)) * BM + row_in_tile;
-#pragma unroll 4
-      for (int j = 0; j < KL; ++j) list[j * BM] = 0ull;
+      float ls[KL];
+      uint32_t li[KL];
+#pragma unroll
+      for (int j = 0; j < KL; ++j) {
+        ls[j] = -INFINITY;
+        li[j] = 0xffffffffu;  // "no candidate"
+      }
+      // Live threshold sharing: every list that scans bank rows for this query (2 column halves x
+      // n_chunks chunks, on different CTAs, possibly at the same time) publishes its current
+      // k'/2-th best score with a global atomicMax and re-reads the maximum once per tile.  A
+      // published value has k'/2 better candidates behind it, so nothing below it can be among the
+      // query's best k'/2: lists stay exact for those, and the start-up transient of each list
+      // (thousands of insertions while its own threshold is still loose) is paid once, jointly.
+      uint32_t* seed_ptr = p.tau_seed + q_row;
+      float seed = -INFINITY;
       float tau = -INFINITY;
-      int cnt = 0;
       for (int tile = t0; tile < t1; ++tile) {
         ptx::mbar_wait(tfull_bar(abuf), aphase, 4);
         ptx::tc_fence_after();
+        {
+          const uint32_t sb = __ldcg(seed_ptr);
+          if (sb) seed = fmaxf(seed, ordered_to_f32(sb));
+          tau = fmaxf(tau, seed);
+        }
         const int64_t col_base = static_cast<int64_t>(tile) * BN + half * (BN / 2);
         const int64_t rem = p.n_rows - col_base;
         const int nvalid = rem >= BN / 2 ? BN / 2 : (rem > 0 ? static_cast<int>(rem) : 0);
         const uint32_t tacc = tmem_lane + static_cast<uint32_t>(abuf * BN);
 #pragma unroll 1
         for (int c0 = 0; c0 < BN / 2; c0 += 32) {
-          if (c0 >= nvalid) break;  // warp-uniform
+          if (c0 >= nvalid || p.ablate == 1) break;  // warp-uniform
           uint32_t v[32];
           ptx::tmem_ld_32x32b_x32(tacc + c0, v);
           ptx::tmem_ld_wait();
@@ -296,23 +279,29 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             mg[g] = m;
           }
           const float m = fmaxf(fmaxf(mg[0], mg[1]), fmaxf(mg[2], mg[3]));
-          if (__any_sync(0xffffffffu, m > tau)) {
+          if (__any_sync(0xffffffffu, m > tau) && p.ablate != 2) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              if (__any_sync(0xffffffffu, mg[g] > tau)) {
-                if (__any_sync(0xffffffffu, cnt > QC - 8)) {  // room for 8 more in every lane?
-                  tau = merge_queue<KL, QC>(list, queue, cnt);
-                  cnt = 0;
-                }
-                const uint32_t col = static_cast<uint32_t>(col_base + c0 + 8 * g);
+              // each pass inserts, per lane, the best remaining column of this group of 8
+              while (__any_sync(0xffffffffu, mg[g] > tau)) {
+                const bool hit = mg[g] > tau;
+                int jbest = 0;
+#pragma unroll
+                for (int j = 1; j < 8; ++j)
+                  if (__uint_as_float(v[8 * g + j]) == mg[g]) jbest = j;
+                if (__uint_as_float(v[8 * g]) == mg[g]) jbest = 0;
+                list_insert<KL>(ls, li, hit ? mg[g] : -INFINITY,
+                                static_cast<uint32_t>(col_base + c0 + 8 * g) + jbest);
+                tau = fmaxf(seed, ls[KL - 1]);
+                if (hit && ls[KL - 1] > seed) atomicMax(seed_ptr, f32_to_ordered(ls[KL - 1]));
+                // retire the inserted column and recompute the group maximum
+                float m2 = -INFINITY;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                  const float x = __uint_as_float(v[8 * g + j]);
-                  if (x > tau) {
-                    queue[cnt * BM] = make_key(x, col + j);
-                    ++cnt;
-                  }
+                  if (hit && j == jbest) v[8 * g + j] = 0xff800000u;
+                  m2 = fmaxf(m2, __uint_as_float(v[8 * g + j]));
                 }
+                mg[g] = m2;
               }
             }
           }
@@ -327,19 +316,19 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         abuf ^= 1;
         if (abuf == 0) aphase ^= 1u;
       }
-      if (__any_sync(0xffffffffu, cnt > 0)) tau = merge_queue<KL, QC>(list, queue, cnt);
-      // emit this item's candidates (k'/2 per column half, sorted; the re-rank kernel merges them)
+      // emit this item's candidates (k'/2 per column half; the re-rank kernel merges them)
       const int64_t q_pad = static_cast<int64_t>(p.n_qblocks) * BM * CG;
       uint64_t* out = p.cand + (static_cast<int64_t>(chunk) * q_pad + q_row) * KP + half * KL;
-#pragma unroll 4
-      for (int j = 0; j < KL; ++j) out[j] = list[j * BM];
+#pragma unroll
+      for (int j = 0; j < KL; ++j)
+        out[j] = (li[j] == 0xffffffffu) ? 0ull : make_key(ls[j], li[j]);
     }
   }
 
   // ---- teardown ----
   ptx::tc_fence_before();
   if (CG == 2) ptx::cluster_sync_all(); else __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<CG>(tmem_base, kTmemCols);
   }
@@ -401,15 +390,13 @@ static int launch_search(const Bank* b, const CUtensorMap& tmap_q, const SearchP
 static int dispatch_search(const Bank* b, int cg, int kp, const CUtensorMap& tmap_q,
                            const SearchParams& p, cudaStream_t st) {
   if (cg == 2) {
-    if (kp == 32) return launch_search<2, 5, 32>(b, tmap_q, p, st);
-    if (kp == 64) return launch_search<2, 4, 64>(b, tmap_q, p, st);
-    if (kp == 128) return launch_search<2, 2, 128>(b, tmap_q, p, st);
+    if (kp == 32) return launch_search<2, 7, 32>(b, tmap_q, p, st);
+    if (kp == 64) return launch_search<2, 7, 64>(b, tmap_q, p, st);
   } else {
-    if (kp == 32) return launch_search<1, 3, 32>(b, tmap_q, p, st);
-    if (kp == 64) return launch_search<1, 2, 64>(b, tmap_q, p, st);
-    if (kp == 128) return launch_search<1, 1, 128>(b, tmap_q, p, st);
+    if (kp == 32) return launch_search<1, 4, 32>(b, tmap_q, p, st);
+    if (kp == 64) return launch_search<1, 4, 64>(b, tmap_q, p, st);
   }
-  set_error("hb_search: k_prime=%d not in {32, 64, 128}", kp);
+  set_error("hb_search: k_prime=%d not in {32, 64}", kp);
   return HB_ERR_INVALID;
 }
 
@@ -431,13 +418,16 @@ static int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_
   const size_t off_q = 0;
   const size_t off_norm = align_up(off_q + sizeof(__nv_bfloat16) * static_cast<size_t>(Q) * b->dpad, 256);
   const size_t off_cand = align_up(off_norm + sizeof(float) * static_cast<size_t>(Q), 256);
-  const size_t total = off_cand + sizeof(uint64_t) * static_cast<size_t>(plan.n_chunks) * q_pad * kp;
+  const size_t off_seed = align_up(off_cand + sizeof(uint64_t) * static_cast<size_t>(plan.n_chunks) * q_pad * kp, 256);
+  const size_t total = off_seed + sizeof(uint32_t) * static_cast<size_t>(q_pad);
   int rc = ensure_workspace(b, total);
   if (rc != HB_OK) return rc;
   uint8_t* ws = static_cast<uint8_t*>(b->ws);
   __nv_bfloat16* q_bf16 = reinterpret_cast<__nv_bfloat16*>(ws + off_q);
   float* qnorm = out_qnorm ? out_qnorm : reinterpret_cast<float*>(ws + off_norm);
   uint64_t* cand = reinterpret_cast<uint64_t*>(ws + off_cand);
+  uint32_t* tau_seed = reinterpret_cast<uint32_t*>(ws + off_seed);
+  HB_CHECK_CUDA(cudaMemsetAsync(tau_seed, 0, sizeof(uint32_t) * static_cast<size_t>(q_pad), st));
 
   b->last_launches = 0;
   int64_t blocks = std::min<int64_t>(ceil_div64(Q, 8), static_cast<int64_t>(b->num_sms) * 8);
@@ -457,7 +447,10 @@ static int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_
   p.n_chunks = plan.n_chunks;
   p.n_tiles = plan.n_tiles;
   p.cand = cand;
+  p.tau_seed = tau_seed;
   p.dump = dump;
+  p.prefetch_tiles = b->cfg_prefetch_tiles;
+  p.ablate = b->cfg_ablate;
   const int slot = b->timing_count & 63;
   if (b->timing) HB_CHECK_CUDA(cudaEventRecord(b->ev_begin[slot], st));
   rc = dispatch_search(b, cg, kp, tmap_q, p, st);
@@ -491,13 +484,22 @@ int hb_search(hb_bank_t* bank, const float* q_dev, int64_t Q, int k, int k_prime
   }
   HB_REQUIRE(Q >= 0 && Q < (int64_t(1) << 31), "hb_search: Q=%lld out of range", (long long)Q);
   HB_REQUIRE(k >= 1 && k <= k_prime, "hb_search: need 1 <= k (%d) <= k_prime (%d)", k, k_prime);
-  HB_REQUIRE(k_prime == 32 || k_prime == 64 || k_prime == 128, "hb_search: k_prime=%d not in {32, 64, 128}", k_prime);
+  HB_REQUIRE(k_prime == 32 || k_prime == 64, "hb_search: k_prime=%d not in {32, 64}", k_prime);
   if (Q == 0) return HB_OK;
   HB_REQUIRE(q_dev && out_scores_dev && out_idx_dev, "hb_search: NULL pointer");
   HB_REQUIRE(b->rows >= 1, "hb_search: the bank is empty");
   HB_CHECK_CUDA(cudaSetDevice(b->device));
   return hb::search_impl(b, q_dev, Q, k, k_prime, idx_offset, out_scores_dev, out_idx_dev, out_qnorm_dev,
                          nullptr, 0, static_cast<cudaStream_t>(stream));
+}
+
+int hb_search_tune(hb_bank_t* bank, int prefetch_tiles, int ablate) {
+  HB_REQUIRE(bank != nullptr, "hb_search_tune: bank is NULL");
+  HB_REQUIRE(prefetch_tiles >= 0 && prefetch_tiles <= 64, "hb_search_tune: prefetch_tiles=%d not in [0, 64]", prefetch_tiles);
+  HB_REQUIRE(ablate >= 0 && ablate <= 2, "hb_search_tune: ablate=%d not in {0,1,2}", ablate);
+  reinterpret_cast<Bank*>(bank)->cfg_prefetch_tiles = prefetch_tiles;
+  reinterpret_cast<Bank*>(bank)->cfg_ablate = ablate;
+  return HB_OK;
 }
 
 int hb_search_config(hb_bank_t* bank, int cta_group, int max_chunks) {

@@ -128,7 +128,7 @@ def gemm_check(res, cg):
 
 
 def search_check(res, cg):
-    for (Q, N, d, kp) in [(1000, 5000, 384, 64), (12544, 102400, 384, 64), (2000, 300000, 768, 64), (777, 40000, 384, 32), (300, 20000, 1024, 128)]:
+    for (Q, N, d, kp) in [(1000, 5000, 384, 64), (12544, 102400, 384, 64), (2000, 300000, 768, 64), (777, 40000, 384, 32), (300, 20000, 1024, 64)]:
         feats = synth_bank(N, d, seed=3)
         bank = make_bank(feats)
         bank.configure_search(cta_group=cg)
@@ -166,8 +166,9 @@ def perf(res):
         bank = make_bank(feats)
         del feats
         q = synth_bank(Q, d, seed=9) * 3.0
-        for cg in (1, 2):
+        for cg, pf, ab in ((1, 0, 0), (2, 4, 0), (1, 0, 1), (2, 4, 1), (1, 0, 2), (2, 4, 2)):
             bank.configure_search(cta_group=cg)
+            bank.tune_search(prefetch_tiles=pf, ablate=ab)
             for _ in range(2):
                 bank.search(q, 30, 64)
             torch.cuda.synchronize()
@@ -180,7 +181,7 @@ def perf(res):
             torch.cuda.synchronize()
             ms = ev0.elapsed_time(ev1) / iters
             tf = 2.0 * Q * N * d / (ms * 1e-3) / 1e12
-            res[f"perf_{name}_cg{cg}"] = {"ms": ms, "qps": Q / (ms * 1e-3), "tflops": tf, "frac_sustained": tf / peak}
+            res[f"perf_{name}_cg{cg}_pf{pf}_ab{ab}"] = {"ms": ms, "qps": Q / (ms * 1e-3), "tflops": tf, "frac_sustained": tf / peak}
         bank.close()
 
 
