@@ -111,7 +111,8 @@ int hb_search(hb_bank_t* bank, const float* q_dev, int64_t Q, int k, int k_prime
 /* Tuning/diagnostics for hb_search: cta_group (1 or 2; 0 = library default),
  * max_chunks (bank split per query block; 0 = auto). */
 int hb_search_config(hb_bank_t* bank, int cta_group, int max_chunks);
-/* L2 prefetch distance (in 256-row bank tiles) of the search kernel's TMA producer; 0 = off.
+/* L2 prefetch distance (in 256-row bank tiles) of the search kernel's TMA producer; 0 = off,
+ * -1 = library default.
  * ablate is a MEASUREMENT-ONLY switch (results are wrong when it is non-zero): 1 = the epilogue
  * releases accumulators unread (pure GEMM pipeline), 2 = it scans but never inserts. */
 int hb_search_tune(hb_bank_t* bank, int prefetch_tiles, int ablate);

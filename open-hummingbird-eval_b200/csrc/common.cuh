@@ -54,7 +54,7 @@ struct Bank {
   size_t ws_bytes = 0;
   int cfg_cta_group = 0;
   int cfg_max_chunks = 0;
-  int cfg_prefetch_tiles = 0;
+  int cfg_prefetch_tiles = -1;  // -1 = auto
   int cfg_ablate = 0;
   int last_launches = 0;
   // optional kernel timing (hb_search_timing)

@@ -63,14 +63,17 @@ __device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
+// try_wait parks the warp in hardware until the phase flips or the hint expires; a generous hint
+// keeps waiting warps from burning issue slots (and power) in a software spin loop.
+constexpr uint32_t kSuspendHintNs = 20000;
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(kSuspendHintNs)
       : "memory");
   return ok != 0;
 }

@@ -12,10 +12,11 @@
 //   warps 0..7  epilogue: each thread owns ONE query row (TMEM lane) and one 128-column half of the
 //               tile, and keeps its k'/2 best (score, row) pairs as a SORTED LIST IN REGISTERS.
 //               A max-tree + one vote rejects 32 columns at a time against tau = the list's last
-//               score; a survivor is bubbled into the list by a fully unrolled compare/select
-//               chain executed in lock-step by the warp (no shared memory, no divergence).
-//               Shared memory is left entirely to the TMA ring.  Accumulator double-buffering
-//               overlaps this scan with the MMAs of the next tile.
+//               score.  A survivor costs one predicated 8-byte store into a 16-entry per-thread
+//               queue in shared memory; when any lane's queue is nearly full the whole warp folds
+//               queues into lists with a fully unrolled bitonic network ON REGISTERS, in lock-step
+//               (no divergence), so the merge is amortised over all 32 queries of the warp.
+//               Accumulator double-buffering overlaps this scan with the MMAs of the next tile.
 // The two single-thread roles sit in the HIGHEST warp ids on purpose: the SM's warp arbiter
 // favours higher warp ids, so the TMA/MMA issue slots are never starved by the ALU-heavy
 // selection warps that share their scheduler.
@@ -35,6 +36,8 @@ constexpr int BN = 256;   // bank rows per tile (UMMA N)
 constexpr int BK = 64;    // bf16 per k-block: one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int kEpiWarps = 8;   // 4 TMEM lane quarters x 2 column halves
+constexpr int kQueueCap = 16;  // pending-candidate queue entries per epilogue thread
+constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kSearchThreads = 32 * (2 + kEpiWarps);
 constexpr int kProducerWarp = kEpiWarps;      // warp 8
 constexpr int kMmaWarp = kEpiWarps + 1;       // warp 9
@@ -60,7 +63,8 @@ struct SearchSmem {
   static constexpr int kBBytes = (BN / CG) * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kRingBytes = STAGES * kStageBytes;
-  static constexpr int kBarOffset = kRingBytes;
+  static constexpr int kQueueBytes = kQueueCap * kEpiThreads * 8;
+  static constexpr int kBarOffset = kRingBytes + kQueueBytes;
   static constexpr int kNumBars = 2 * STAGES + 4;
   static constexpr int kTotal = kBarOffset + kNumBars * 8 + 16;
   static constexpr int kDynamic = kTotal + 1024;  // slack to align the ring to 1024 B
@@ -68,24 +72,82 @@ struct SearchSmem {
 };
 
 // ---- per-thread candidate list in registers ---------------------------------------------------
-// ls[] descending scores, li[] their bank rows.  Inserting x bubbles it down the list; a lane that
-// has nothing to insert passes x = -inf, which leaves its list untouched.  Fully unrolled: every
-// index is a compile-time constant, so the list never leaves the register file.
-template <int KL>
-__device__ __forceinline__ void list_insert(float (&ls)[KL], uint32_t (&li)[KL], float x, uint32_t row) {
+// s[] scores / r[] bank rows, every index a compile-time constant so the arrays never leave the
+// register file.  All lanes of a warp run these networks in lock-step on their own lists.
+template <bool DESC>
+__device__ __forceinline__ void cmpx(float& sa, uint32_t& ra, float& sb, uint32_t& rb) {
+  // after the call (a, b) is ordered: descending if DESC else ascending
+  const bool sw = DESC ? (sa < sb) : (sa > sb);
+  const float ts = sw ? sb : sa;
+  const uint32_t tr = sw ? rb : ra;
+  sb = sw ? sa : sb;
+  rb = sw ? ra : rb;
+  sa = ts;
+  ra = tr;
+}
+// Bitonic merge of s[LO .. LO+N): input bitonic, output sorted (DESC or ascending).
+template <int N, int LO, bool DESC, int M>
+__device__ __forceinline__ void reg_bitonic_merge(float (&s)[M], uint32_t (&r)[M]) {
 #pragma unroll
-  for (int i = 0; i < KL; ++i) {
-    const bool gt = x > ls[i];
-    const float hs = gt ? x : ls[i];
-    const uint32_t hi = gt ? row : li[i];
-    x = gt ? ls[i] : x;
-    row = gt ? li[i] : row;
-    ls[i] = hs;
-    li[i] = hi;
+  for (int j = N / 2; j > 0; j >>= 1) {
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      if ((i & j) == 0) cmpx<DESC>(s[LO + i], r[LO + i], s[LO + i + j], r[LO + i + j]);
+  }
+}
+// Full bitonic sort of s[0 .. N).
+template <int N, bool DESC, int M>
+__device__ __forceinline__ void reg_bitonic_sort(float (&s)[M], uint32_t (&r)[M]) {
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        if ((i & j) == 0) {
+          const bool up = ((i & k) == 0) == DESC;  // direction of this sub-sequence
+          if (up) cmpx<true>(s[i], r[i], s[i + j], r[i + j]);
+          else cmpx<false>(s[i], r[i], s[i + j], r[i + j]);
+        }
+      }
+    }
+  }
+}
+// Fold `cnt` queued (score,row) pairs (shared memory, entry j at queue[j*kEpiThreads]) into the
+// sorted-descending register list of KL entries.  QC <= KL / 2 ... KL.
+template <int KL, int QC>
+__device__ __forceinline__ void fold_queue(float (&ls)[KL], uint32_t (&lr)[KL], const uint2* queue, int cnt) {
+  float qs[QC];
+  uint32_t qr[QC];
+#pragma unroll
+  for (int j = 0; j < QC; ++j) {
+    const uint2 e = queue[j * kEpiThreads];
+    const bool ok = j < cnt;
+    qs[j] = ok ? __uint_as_float(e.x) : -INFINITY;
+    qr[j] = ok ? e.y : 0xffffffffu;
+  }
+  reg_bitonic_sort<QC, false>(qs, qr);  // ascending
+  // the QC smallest list entries (descending) against the ascending queue: element-wise max
+  // keeps the QC largest of their union, as a bitonic sequence
+#pragma unroll
+  for (int j = 0; j < QC; ++j) {
+    const bool take = qs[j] > ls[KL - QC + j];
+    ls[KL - QC + j] = take ? qs[j] : ls[KL - QC + j];
+    lr[KL - QC + j] = take ? qr[j] : lr[KL - QC + j];
+  }
+  reg_bitonic_merge<QC, KL - QC, true>(ls, lr);  // tail sorted descending
+  if constexpr (KL > QC) {
+    static_assert(KL == 2 * QC, "fold_queue expects KL == QC or KL == 2*QC");
+    // two descending runs of QC: compare i <-> KL-1-i makes both halves bitonic with every head
+    // element >= every tail element, then merge each half
+#pragma unroll
+    for (int i = 0; i < QC; ++i) cmpx<true>(ls[i], lr[i], ls[KL - 1 - i], lr[KL - 1 - i]);
+    reg_bitonic_merge<QC, 0, true>(ls, lr);
+    reg_bitonic_merge<QC, QC, true>(ls, lr);
   }
 }
 
-template <int CG, int STAGES, int KP>
+template <int CG, int STAGES, int KP, bool DUMP>
 __global__ void __launch_bounds__(kSearchThreads, 1)
 search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
                    const __grid_constant__ CUtensorMap tmap_bank, const SearchParams p) {
@@ -212,9 +274,11 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   } else {
     // =========================== epilogue: fused top-k' ===========================
     constexpr int KL = KP / 2;                    // list length per (row, column half)
+    constexpr int QC = kQueueCap;
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
     const int half = warp >> 2;                   // which 128 columns of the tile
     const int row_in_tile = quarter * 32 + lane;  // query row owned by this thread
+    uint2* queue = reinterpret_cast<uint2*>(smem + L::kRingBytes) + threadIdx.x;  // entry j at [j*kEpiThreads]
     const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + half * (BN / 2);
     const uint32_t tempty_leader0 = (CG == 2) ? ptx::mapa(tempty_bar(0), 0) : tempty_bar(0);
     const uint32_t tempty_leader1 = (CG == 2) ? ptx::mapa(tempty_bar(1), 0) : tempty_bar(1);
@@ -226,29 +290,31 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       const int t1 = chunk_tile_begin(p.n_tiles, p.n_chunks, chunk + 1);
       const int64_t q_row = static_cast<int64_t>(qb * CG + static_cast<int>(cta_rank)) * BM + row_in_tile;
       float ls[KL];
-      uint32_t li[KL];
+      uint32_t lr[KL];
 #pragma unroll
       for (int j = 0; j < KL; ++j) {
         ls[j] = -INFINITY;
-        li[j] = 0xffffffffu;  // "no candidate"
+        lr[j] = 0xffffffffu;  // "no candidate"
       }
+      int cnt = 0;  // queued, not yet folded
       // Live threshold sharing: every list that scans bank rows for this query (2 column halves x
       // n_chunks chunks, on different CTAs, possibly at the same time) publishes its current
       // k'/2-th best score with a global atomicMax and re-reads the maximum once per tile.  A
       // published value has k'/2 better candidates behind it, so nothing below it can be among the
       // query's best k'/2: lists stay exact for those, and the start-up transient of each list
-      // (thousands of insertions while its own threshold is still loose) is paid once, jointly.
+      // is paid once, jointly.
       uint32_t* seed_ptr = p.tau_seed + q_row;
       float seed = -INFINITY;
       float tau = -INFINITY;
+      uint32_t seed_bits = __ldcg(seed_ptr);
       for (int tile = t0; tile < t1; ++tile) {
         ptx::mbar_wait(tfull_bar(abuf), aphase, 4);
         ptx::tc_fence_after();
-        {
-          const uint32_t sb = __ldcg(seed_ptr);
-          if (sb) seed = fmaxf(seed, ordered_to_f32(sb));
-          tau = fmaxf(tau, seed);
-        }
+        // software-pipelined refresh of the shared threshold: the value loaded during the previous
+        // tile is applied now and the next load is issued, so its L2 latency is never waited on
+        if (seed_bits) seed = fmaxf(seed, ordered_to_f32(seed_bits));
+        tau = fmaxf(tau, seed);
+        seed_bits = __ldcg(seed_ptr);
         const int64_t col_base = static_cast<int64_t>(tile) * BN + half * (BN / 2);
         const int64_t rem = p.n_rows - col_base;
         const int nvalid = rem >= BN / 2 ? BN / 2 : (rem > 0 ? static_cast<int>(rem) : 0);
@@ -259,7 +325,7 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
           uint32_t v[32];
           ptx::tmem_ld_32x32b_x32(tacc + c0, v);
           ptx::tmem_ld_wait();
-          if (p.dump != nullptr && q_row < p.n_queries) {
+          if (DUMP && q_row < p.n_queries) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (c0 + j < nvalid) p.dump[q_row * p.n_rows + col_base + c0 + j] = __uint_as_float(v[j]);
@@ -280,30 +346,40 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
           }
           const float m = fmaxf(fmaxf(mg[0], mg[1]), fmaxf(mg[2], mg[3]));
           if (__any_sync(0xffffffffu, m > tau) && p.ablate != 2) {
+            uint32_t done = 0;  // groups already queued (bit g)
+            bool fold;
+            do {
+              fold = false;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              // each pass inserts, per lane, the best remaining column of this group of 8
-              while (__any_sync(0xffffffffu, mg[g] > tau)) {
-                const bool hit = mg[g] > tau;
-                int jbest = 0;
+              for (int g = 0; g < 4; ++g) {
+                if (!fold && !((done >> g) & 1u)) {
+                  if (__any_sync(0xffffffffu, mg[g] > tau)) {
+                    if (__any_sync(0xffffffffu, cnt > QC - 8)) {
+                      fold = true;  // some lane lacks room for 8 more: fold first, then resume at g
+                    } else {
+                      const uint32_t col = static_cast<uint32_t>(col_base + c0 + 8 * g);
 #pragma unroll
-                for (int j = 1; j < 8; ++j)
-                  if (__uint_as_float(v[8 * g + j]) == mg[g]) jbest = j;
-                if (__uint_as_float(v[8 * g]) == mg[g]) jbest = 0;
-                list_insert<KL>(ls, li, hit ? mg[g] : -INFINITY,
-                                static_cast<uint32_t>(col_base + c0 + 8 * g) + jbest);
-                tau = fmaxf(seed, ls[KL - 1]);
-                if (hit && ls[KL - 1] > seed) atomicMax(seed_ptr, f32_to_ordered(ls[KL - 1]));
-                // retire the inserted column and recompute the group maximum
-                float m2 = -INFINITY;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  if (hit && j == jbest) v[8 * g + j] = 0xff800000u;
-                  m2 = fmaxf(m2, __uint_as_float(v[8 * g + j]));
+                      for (int j = 0; j < 8; ++j) {
+                        if (__uint_as_float(v[8 * g + j]) > tau) {
+                          queue[cnt * kEpiThreads] = make_uint2(v[8 * g + j], col + j);
+                          ++cnt;
+                        }
+                      }
+                      done |= 1u << g;
+                    }
+                  } else {
+                    done |= 1u << g;
+                  }
                 }
-                mg[g] = m2;
               }
-            }
+              if (fold) {  // the single fold site of the tile loop
+                fold_queue<KL, QC>(ls, lr, queue, cnt);
+                cnt = 0;
+                const float worst = ls[KL - 1];
+                if (worst > seed) atomicMax(seed_ptr, f32_to_ordered(worst));
+                tau = fmaxf(seed, worst);
+              }
+            } while (fold);
           }
         }
         // release the accumulator to the MMA issuer (pair leader's barrier)
@@ -316,12 +392,13 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         abuf ^= 1;
         if (abuf == 0) aphase ^= 1u;
       }
+      if (__any_sync(0xffffffffu, cnt > 0)) fold_queue<KL, QC>(ls, lr, queue, cnt);
       // emit this item's candidates (k'/2 per column half; the re-rank kernel merges them)
       const int64_t q_pad = static_cast<int64_t>(p.n_qblocks) * BM * CG;
       uint64_t* out = p.cand + (static_cast<int64_t>(chunk) * q_pad + q_row) * KP + half * KL;
 #pragma unroll
       for (int j = 0; j < KL; ++j)
-        out[j] = (li[j] == 0xffffffffu) ? 0ull : make_key(ls[j], li[j]);
+        out[j] = (lr[j] == 0xffffffffu) ? 0ull : make_key(ls[j], lr[j]);
     }
   }
 
@@ -362,11 +439,11 @@ prep_queries_kernel(const float* __restrict__ q, int64_t Q, int d, int dpad,
   }
 }
 
-template <int CG, int STAGES, int KP>
+template <int CG, int STAGES, int KP, bool DUMP = false>
 static int launch_search(const Bank* b, const CUtensorMap& tmap_q, const SearchParams& p,
                          cudaStream_t st) {
   using L = SearchSmem<CG, STAGES, KP>;
-  auto kern = search_topk_kernel<CG, STAGES, KP>;
+  auto kern = search_topk_kernel<CG, STAGES, KP, DUMP>;
   HB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic));
   const int n_clusters = std::max(1, std::min(b->num_sms / CG, p.n_qblocks * p.n_chunks));
   cudaLaunchConfig_t cfg{};
@@ -389,9 +466,13 @@ static int launch_search(const Bank* b, const CUtensorMap& tmap_q, const SearchP
 // Dispatch over (cta_group, k').  Ring depth is what fits beside the k' heap in 227 KB.
 static int dispatch_search(const Bank* b, int cg, int kp, const CUtensorMap& tmap_q,
                            const SearchParams& p, cudaStream_t st) {
+  if (p.dump != nullptr) {  // validation build of the same kernel that also writes the raw scores
+    if (cg == 2) return launch_search<2, 6, 64, true>(b, tmap_q, p, st);
+    return launch_search<1, 4, 64, true>(b, tmap_q, p, st);
+  }
   if (cg == 2) {
-    if (kp == 32) return launch_search<2, 7, 32>(b, tmap_q, p, st);
-    if (kp == 64) return launch_search<2, 7, 64>(b, tmap_q, p, st);
+    if (kp == 32) return launch_search<2, 6, 32>(b, tmap_q, p, st);
+    if (kp == 64) return launch_search<2, 6, 64>(b, tmap_q, p, st);
   } else {
     if (kp == 32) return launch_search<1, 4, 32>(b, tmap_q, p, st);
     if (kp == 64) return launch_search<1, 4, 64>(b, tmap_q, p, st);
@@ -409,7 +490,9 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_t idx_offset,
                        float* out_scores, int64_t* out_idx, float* out_qnorm, float* dump, int cg_override,
                        cudaStream_t st) {
-  int cg = cg_override ? cg_override : (b->cfg_cta_group ? b->cfg_cta_group : 2);
+  // measured on B200 (profiles/): independent CTAs win for d <= 512, CTA pairs (half the B-operand
+  // traffic per SM) from d = 768 up
+  int cg = cg_override ? cg_override : (b->cfg_cta_group ? b->cfg_cta_group : (b->dpad <= 512 ? 1 : 2));
   if (b->num_sms < 2) cg = 1;
   const SearchPlan plan = plan_search(b->rows, Q, cg, b->num_sms, b->cfg_max_chunks);
   const int64_t q_pad = static_cast<int64_t>(plan.n_qblocks) * BM * cg;
@@ -449,7 +532,7 @@ static int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_
   p.cand = cand;
   p.tau_seed = tau_seed;
   p.dump = dump;
-  p.prefetch_tiles = b->cfg_prefetch_tiles;
+  p.prefetch_tiles = b->cfg_prefetch_tiles >= 0 ? b->cfg_prefetch_tiles : (cg == 2 ? 4 : 0);
   p.ablate = b->cfg_ablate;
   const int slot = b->timing_count & 63;
   if (b->timing) HB_CHECK_CUDA(cudaEventRecord(b->ev_begin[slot], st));
@@ -495,7 +578,7 @@ int hb_search(hb_bank_t* bank, const float* q_dev, int64_t Q, int k, int k_prime
 
 int hb_search_tune(hb_bank_t* bank, int prefetch_tiles, int ablate) {
   HB_REQUIRE(bank != nullptr, "hb_search_tune: bank is NULL");
-  HB_REQUIRE(prefetch_tiles >= 0 && prefetch_tiles <= 64, "hb_search_tune: prefetch_tiles=%d not in [0, 64]", prefetch_tiles);
+  HB_REQUIRE(prefetch_tiles >= -1 && prefetch_tiles <= 64, "hb_search_tune: prefetch_tiles=%d not in [-1, 64]", prefetch_tiles);
   HB_REQUIRE(ablate >= 0 && ablate <= 2, "hb_search_tune: ablate=%d not in {0,1,2}", ablate);
   reinterpret_cast<Bank*>(bank)->cfg_prefetch_tiles = prefetch_tiles;
   reinterpret_cast<Bank*>(bank)->cfg_ablate = ablate;

@@ -140,7 +140,7 @@ class MemoryBank:
                             ptr(qn), stream_ptr(q.device)))
         return scores, idx, qn
 
-    def tune_search(self, prefetch_tiles: int = 0, ablate: int = 0) -> None:
+    def tune_search(self, prefetch_tiles: int = -1, ablate: int = 0) -> None:
         """ablate != 0 is for measurement only (wrong results): 1 = GEMM pipeline alone, 2 = scan only."""
         check(lib.hb_search_tune(self._h, int(prefetch_tiles), int(ablate)))
 
