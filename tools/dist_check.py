@@ -1,0 +1,43 @@
+"""Run under torchrun (one rank per GPU): the row-sharded engine must reproduce the reference's
+golden result (tests/golden) — per-shard search, NCCL all-gather, K3 merge, replicated label table,
+all-reduced confusion matrix."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "open-hummingbird-eval_b200"), os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+from helpers import load_golden  # noqa: E402
+from hbird_b200 import HbirdEvaluation  # noqa: E402
+from hbird_b200.data import SyntheticSegmentationData  # noqa: E402
+from hbird_b200.models import FeatureExtractorSimple  # noqa: E402
+
+rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+ok = True
+report = {}
+for name in ("voc_tiny", "ade_tiny"):
+    cfg, g = load_golden(name)
+    data = SyntheticSegmentationData(**cfg)
+    fe = FeatureExtractorSimple(data.model, data.ftr_extr_fn, data.S, data.d)
+    ev = HbirdEvaluation(fe, data.train_dataloader(), num_classes=data.C, n_neighbours=30, device=f"cuda:{local}",
+                         nn_method="b200", dataset_size=data.get_train_dataset_size())
+    miou = ev.evaluate(data.val_dataloader(), data.S, ignore_index=data.ignore_index)
+    conf = ev.last_confusion
+    rows = ev.shard_counts
+    good = abs(miou - float(g["miou"])) <= 5e-4 and conf.sum() == g["conf"].sum() and \
+        np.abs(conf - g["conf"]).sum() <= 2e-4 * conf.sum() and sum(rows) == g["feature_memory"].shape[0] and len(rows) == world
+    report[name] = {"miou": miou, "ref": float(g["miou"]), "shard_rows": rows, "ok": bool(good)}
+    ok = ok and good
+flag = torch.tensor([1 if ok else 0], device="cuda")
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print(json.dumps({"world": world, "ok": bool(flag.item()), **report}))
+dist.destroy_process_group()
+sys.exit(0 if flag.item() else 1)
