@@ -44,6 +44,18 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
   return r;
 }
 
+// One lane of a fully converged warp (the predicate form keeps surrounding values in the uniform
+// datapath, so descriptors need no per-instruction register -> uniform-register moves).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- mbarrier --------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");

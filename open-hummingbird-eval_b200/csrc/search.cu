@@ -142,8 +142,8 @@ __device__ __forceinline__ void fold_queue(float (&ls)[KL], uint32_t (&lr)[KL], 
     // element >= every tail element, then merge each half
 #pragma unroll
     for (int i = 0; i < QC; ++i) cmpx<true>(ls[i], lr[i], ls[KL - 1 - i], lr[KL - 1 - i]);
-    reg_bitonic_merge<QC, 0, true>(ls, lr);
-    reg_bitonic_merge<QC, QC, true>(ls, lr);
+      reg_bitonic_merge<QC, 0, true>(ls, lr);
+      reg_bitonic_merge<QC, QC, true>(ls, lr);
   }
 }
 
@@ -198,43 +198,49 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const int nkb = p.num_kblocks;
 
   if (warp == kProducerWarp) {
-    // =========================== TMA producer ===========================
-    int stage = 0;
-    uint32_t phase = 0;
-    const uint32_t full_target_rank0 = (CG == 2) ? 0u : 0u;
-    (void)full_target_rank0;
-    for (int item = cluster_id; item < total_items; item += n_clusters) {
-      const int qb = item % p.n_qblocks, chunk = item / p.n_qblocks;
-      const int t0 = chunk_tile_begin(p.n_tiles, p.n_chunks, chunk);
-      const int t1 = chunk_tile_begin(p.n_tiles, p.n_chunks, chunk + 1);
-      const int32_t q_row = (qb * CG + static_cast<int>(cta_rank)) * BM;
-      for (int tile = t0; tile < t1; ++tile) {
-        const int32_t b_row = tile * BN + static_cast<int>(cta_rank) * (BN / CG);
-        for (int kb = 0; kb < nkb; ++kb) {
-          ptx::mbar_wait(empty_bar(stage), phase ^ 1u, 1);
-          if (lane == 0) {
-            const uint32_t a_dst = smem_base + stage * L::kStageBytes;
-            const uint32_t b_dst = a_dst + L::kABytes;
-            uint32_t bar = full_bar(stage);
-            if (CG == 2) bar = ptx::mapa(bar, 0);  // completion bytes go to the pair leader
-            if (is_leader) ptx::mbar_arrive_expect_tx(full_bar(stage), L::kStageBytes * CG);
-            ptx::tma_load_2d<CG>(a_dst, &tmap_q, bar, kb * BK, q_row);
-            ptx::tma_load_2d<CG>(b_dst, &tmap_bank, bar, kb * BK, b_row);
-            // bank tiles are shared by all CTAs walking this chunk: each (tile, k-block) box is
-            // pulled into L2 ahead of time by exactly one of them
-            if (p.prefetch_tiles > 0 && tile + p.prefetch_tiles < t1 &&
-                (tile * nkb + kb) % n_clusters == cluster_id)
-              ptx::tma_prefetch_2d(&tmap_bank, kb * BK, b_row + p.prefetch_tiles * BN);
+    // =========================== TMA producer (converged warp, one elected lane issues) ===========================
+    {
+      int stage = 0;
+      uint32_t phase = 0;
+      // completion bytes of both CTAs of a pair land on the pair leader's barrier
+      uint32_t full_addr[STAGES];
+#pragma unroll
+      for (int s = 0; s < STAGES; ++s) full_addr[s] = (CG == 2) ? ptx::mapa(full_bar(s), 0) : full_bar(s);
+      for (int item = cluster_id; item < total_items; item += n_clusters) {
+        const int qb = item % p.n_qblocks, chunk = item / p.n_qblocks;
+        const int t0 = chunk_tile_begin(p.n_tiles, p.n_chunks, chunk);
+        const int t1 = chunk_tile_begin(p.n_tiles, p.n_chunks, chunk + 1);
+        const int32_t q_row = (qb * CG + static_cast<int>(cta_rank)) * BM;
+        for (int tile = t0; tile < t1; ++tile) {
+          const int32_t b_row = tile * BN + static_cast<int>(cta_rank) * (BN / CG);
+          const bool pf_tile = p.prefetch_tiles > 0 && tile + p.prefetch_tiles < t1;
+          for (int kb = 0; kb < nkb; ++kb) {
+            ptx::mbar_wait(empty_bar(stage), phase ^ 1u, 1);
+            if (ptx::elect_one()) {
+              const uint32_t a_dst = smem_base + stage * L::kStageBytes;
+              if (is_leader) ptx::mbar_arrive_expect_tx(full_bar(stage), L::kStageBytes * CG);
+              ptx::tma_load_2d<CG>(a_dst, &tmap_q, full_addr[stage], kb * BK, q_row);
+              ptx::tma_load_2d<CG>(a_dst + L::kABytes, &tmap_bank, full_addr[stage], kb * BK, b_row);
+              // bank tiles are shared by all CTAs walking this chunk: each (tile, k-block) box is
+              // pulled into L2 ahead of time by exactly one of them
+              if (pf_tile && (tile * nkb + kb) % n_clusters == cluster_id)
+                ptx::tma_prefetch_2d(&tmap_bank, kb * BK, b_row + p.prefetch_tiles * BN);
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
-          __syncwarp();
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == kMmaWarp) {
-    // =========================== MMA issuer ===========================
+    // =========================== MMA issuer (pair leader; converged warp, one elected lane issues) ===========================
+    // The issue loop must stay well under the 512 tensor-pipe cycles one k-block is worth: every
+    // value feeding the descriptors is warp-uniform, so they live in uniform registers.
     if (is_leader) {
       constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(BM * CG, BN);
+      const uint64_t adesc0 = ptx::make_smem_desc_sw128(smem_base);
+      const uint64_t bdesc0 = ptx::make_smem_desc_sw128(smem_base + L::kABytes);
+      constexpr uint64_t kStageStep = L::kStageBytes >> 4;  // descriptor address field is in 16-byte units
       int stage = 0;
       uint32_t phase = 0;
       int abuf = 0;
@@ -250,10 +256,9 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
           for (int kb = 0; kb < nkb; ++kb) {
             ptx::mbar_wait(full_bar(stage), phase, 3);  // TMA bytes have landed
             ptx::tc_fence_after();
-            if (lane == 0) {
-              const uint32_t a_addr = smem_base + stage * L::kStageBytes;
-              const uint64_t adesc = ptx::make_smem_desc_sw128(a_addr);
-              const uint64_t bdesc = ptx::make_smem_desc_sw128(a_addr + L::kABytes);
+            if (ptx::elect_one()) {
+              const uint64_t adesc = adesc0 + kStageStep * stage;
+              const uint64_t bdesc = bdesc0 + kStageStep * stage;
 #pragma unroll
               for (int k = 0; k < BK / UMMA_K; ++k) {
                 // advance 16 bf16 = 32 B inside the swizzle atom: +2 in the (addr >> 4) field
@@ -312,19 +317,31 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         ptx::tc_fence_after();
         // software-pipelined refresh of the shared threshold: the value loaded during the previous
         // tile is applied now and the next load is issued, so its L2 latency is never waited on
-        if (seed_bits) seed = fmaxf(seed, ordered_to_f32(seed_bits));
-        tau = fmaxf(tau, seed);
-        seed_bits = __ldcg(seed_ptr);
+        if (((tile - t0) & 7) == 0) {
+          if (seed_bits) seed = fmaxf(seed, ordered_to_f32(seed_bits));
+          tau = fmaxf(tau, seed);
+          seed_bits = __ldcg(seed_ptr);
+        }
         const int64_t col_base = static_cast<int64_t>(tile) * BN + half * (BN / 2);
         const int64_t rem = p.n_rows - col_base;
         const int nvalid = rem >= BN / 2 ? BN / 2 : (rem > 0 ? static_cast<int>(rem) : 0);
         const uint32_t tacc = tmem_lane + static_cast<uint32_t>(abuf * BN);
 #pragma unroll 1
         for (int c0 = 0; c0 < BN / 2; c0 += 32) {
-          if (c0 >= nvalid || p.ablate == 1) break;  // warp-uniform
+          if (c0 >= nvalid || p.ablate == 1) break;  // warp-uniform (nvalid is a multiple of 32 except in the bank's last tile)
           uint32_t v[32];
           ptx::tmem_ld_32x32b_x32(tacc + c0, v);
           ptx::tmem_ld_wait();
+          if (c0 + 32 >= nvalid) {
+            // last chunk of this accumulator is now in registers: hand the TMEM buffer back to the
+            // MMA issuer (pair leader's barrier) before spending time on selection
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              const uint32_t bar = abuf ? tempty_leader1 : tempty_leader0;
+              if (CG == 2) ptx::mbar_arrive_cluster(bar); else ptx::mbar_arrive_local(bar);
+            }
+          }
           if (DUMP && q_row < p.n_queries) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
@@ -382,12 +399,22 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             } while (fold);
           }
         }
-        // release the accumulator to the MMA issuer (pair leader's barrier)
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          const uint32_t bar = abuf ? tempty_leader1 : tempty_leader0;
-          if (CG == 2) ptx::mbar_arrive_cluster(bar); else ptx::mbar_arrive_local(bar);
+        if (nvalid == 0 || p.ablate == 1) {  // nothing was read: release here
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            const uint32_t bar = abuf ? tempty_leader1 : tempty_leader0;
+            if (CG == 2) ptx::mbar_arrive_cluster(bar); else ptx::mbar_arrive_local(bar);
+          }
+        }
+        // (1) routine folds happen here, after the accumulator was released: keep at least 8 free
+        // queue slots per lane so that the next tile rarely has to fold while it holds TMEM
+        if (__any_sync(0xffffffffu, cnt > QC - 12)) {
+          fold_queue<KL, QC>(ls, lr, queue, cnt);
+          cnt = 0;
+          const float worst = ls[KL - 1];
+          if (worst > seed) atomicMax(seed_ptr, f32_to_ordered(worst));
+          tau = fmaxf(seed, worst);
         }
         abuf ^= 1;
         if (abuf == 0) aphase ^= 1u;
