@@ -116,6 +116,9 @@ int hb_search_config(hb_bank_t* bank, int cta_group, int max_chunks);
  * ablate is a MEASUREMENT-ONLY switch (results are wrong when it is non-zero): 1 = the epilogue
  * releases accumulators unread (pure GEMM pipeline), 2 = it scans but never inserts. */
 int hb_search_tune(hb_bank_t* bank, int prefetch_tiles, int ablate);
+/* L2 pacing window of the search kernel (default on): CTAs streaming the same bank chunk stay within
+ * ~100 tiles of each other so each tile is read from HBM once per wave. */
+int hb_search_pacing(hb_bank_t* bank, int enable);
 /* Number of kernel launches the last hb_search on this bank issued. */
 int hb_search_last_launches(const hb_bank_t* bank);
 

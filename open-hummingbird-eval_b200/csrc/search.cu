@@ -42,6 +42,11 @@ constexpr int kSearchThreads = 32 * (2 + kEpiWarps);
 constexpr int kProducerWarp = kEpiWarps;      // warp 8
 constexpr int kMmaWarp = kEpiWarps + 1;       // warp 9
 constexpr int kTmemCols = 512;
+// L2 pacing: CTAs that stream the same bank chunk may not run more than (kPaceLag + 1) groups of
+// kPaceTiles tiles ahead of the slowest one, so a bank tile is fetched from HBM once per wave and
+// then hit in the 126 MB L2 by everyone else.
+constexpr int kPaceTiles = 32;
+constexpr int kPaceLag = 2;
 
 struct SearchParams {
   int64_t n_rows;      // valid bank rows
@@ -54,6 +59,8 @@ struct SearchParams {
   uint32_t* tau_seed;  // (n_qblocks*128*CG) per-query shared threshold, ordered-float bits (0 = none yet)
   float* dump;         // optional (n_queries, n_rows) raw scores (validation only)
   int prefetch_tiles;  // > 0: L2-prefetch bank tiles this many tiles ahead (split over the CTAs)
+  uint32_t* pace;      // (rounds, pace_groups) arrival counters of the L2 pacing window (NULL = off)
+  int pace_groups;     // counters per round
   int ablate;          // measurement only: 1 = release accumulators unread, 2 = scan but never insert
 };
 
@@ -211,9 +218,22 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         const int t0 = chunk_tile_begin(p.n_tiles, p.n_chunks, chunk);
         const int t1 = chunk_tile_begin(p.n_tiles, p.n_chunks, chunk + 1);
         const int32_t q_row = (qb * CG + static_cast<int>(cta_rank)) * BM;
+        const int round = item / n_clusters;
+        const uint32_t n_part = static_cast<uint32_t>(min(n_clusters, total_items - round * n_clusters));
+        uint32_t* pace = p.pace ? p.pace + static_cast<size_t>(round) * p.pace_groups : nullptr;
         for (int tile = t0; tile < t1; ++tile) {
           const int32_t b_row = tile * BN + static_cast<int>(cta_rank) * (BN / CG);
           const bool pf_tile = p.prefetch_tiles > 0 && tile + p.prefetch_tiles < t1;
+          const int rel = tile - t0;
+          if (pace != nullptr && (rel % kPaceTiles) == 0 && rel / kPaceTiles > kPaceLag) {
+            // do not start group g before every CTA of this wave has loaded group g - 1 - kPaceLag
+            const volatile uint32_t* ctr = pace + (rel / kPaceTiles - 1 - kPaceLag);
+            const uint64_t t_start = ptx::globaltimer_ns();
+            while (*ctr < n_part) {
+              __nanosleep(256);
+              if (ptx::globaltimer_ns() - t_start > 4000000000ull) ptx::hang_trap(5, 0, 0);
+            }
+          }
           for (int kb = 0; kb < nkb; ++kb) {
             ptx::mbar_wait(empty_bar(stage), phase ^ 1u, 1);
             if (ptx::elect_one()) {
@@ -229,6 +249,8 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
+          if (pace != nullptr && is_leader && lane == 0 && ((rel % kPaceTiles) == kPaceTiles - 1 || tile == t1 - 1))
+            atomicAdd(pace + rel / kPaceTiles, 1u);  // this CTA (pair) has issued all loads of the group
         }
       }
     }
@@ -529,7 +551,11 @@ static int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_
   const size_t off_norm = align_up(off_q + sizeof(__nv_bfloat16) * static_cast<size_t>(Q) * b->dpad, 256);
   const size_t off_cand = align_up(off_norm + sizeof(float) * static_cast<size_t>(Q), 256);
   const size_t off_seed = align_up(off_cand + sizeof(uint64_t) * static_cast<size_t>(plan.n_chunks) * q_pad * kp, 256);
-  const size_t total = off_seed + sizeof(uint32_t) * static_cast<size_t>(q_pad);
+  const int n_units_used = std::max(1, std::min(b->num_sms / cg, plan.n_qblocks * plan.n_chunks));
+  const int n_rounds = (plan.n_qblocks * plan.n_chunks + n_units_used - 1) / n_units_used;
+  const int pace_groups = (plan.n_tiles / plan.n_chunks + 1) / kPaceTiles + 2;
+  const size_t off_pace = align_up(off_seed + sizeof(uint32_t) * static_cast<size_t>(q_pad), 256);
+  const size_t total = off_pace + sizeof(uint32_t) * static_cast<size_t>(n_rounds) * pace_groups;
   int rc = ensure_workspace(b, total);
   if (rc != HB_OK) return rc;
   uint8_t* ws = static_cast<uint8_t*>(b->ws);
@@ -537,7 +563,9 @@ static int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_
   float* qnorm = out_qnorm ? out_qnorm : reinterpret_cast<float*>(ws + off_norm);
   uint64_t* cand = reinterpret_cast<uint64_t*>(ws + off_cand);
   uint32_t* tau_seed = reinterpret_cast<uint32_t*>(ws + off_seed);
-  HB_CHECK_CUDA(cudaMemsetAsync(tau_seed, 0, sizeof(uint32_t) * static_cast<size_t>(q_pad), st));
+  uint32_t* pace = reinterpret_cast<uint32_t*>(ws + off_pace);
+  // seeds and pacing counters are contiguous: one memset
+  HB_CHECK_CUDA(cudaMemsetAsync(tau_seed, 0, total - off_seed, st));
 
   b->last_launches = 0;
   int64_t blocks = std::min<int64_t>(ceil_div64(Q, 8), static_cast<int64_t>(b->num_sms) * 8);
@@ -558,6 +586,8 @@ static int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_
   p.n_tiles = plan.n_tiles;
   p.cand = cand;
   p.tau_seed = tau_seed;
+  p.pace = b->cfg_pace ? pace : nullptr;
+  p.pace_groups = pace_groups;
   p.dump = dump;
   p.prefetch_tiles = b->cfg_prefetch_tiles >= 0 ? b->cfg_prefetch_tiles : (cg == 2 ? 4 : 0);
   p.ablate = b->cfg_ablate;
@@ -601,6 +631,12 @@ int hb_search(hb_bank_t* bank, const float* q_dev, int64_t Q, int k, int k_prime
   HB_CHECK_CUDA(cudaSetDevice(b->device));
   return hb::search_impl(b, q_dev, Q, k, k_prime, idx_offset, out_scores_dev, out_idx_dev, out_qnorm_dev,
                          nullptr, 0, static_cast<cudaStream_t>(stream));
+}
+
+int hb_search_pacing(hb_bank_t* bank, int enable) {
+  HB_REQUIRE(bank != nullptr, "hb_search_pacing: bank is NULL");
+  reinterpret_cast<Bank*>(bank)->cfg_pace = enable != 0;
+  return HB_OK;
 }
 
 int hb_search_tune(hb_bank_t* bank, int prefetch_tiles, int ablate) {

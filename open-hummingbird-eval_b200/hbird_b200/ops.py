@@ -144,6 +144,9 @@ class MemoryBank:
         """ablate != 0 is for measurement only (wrong results): 1 = GEMM pipeline alone, 2 = scan only."""
         check(lib.hb_search_tune(self._h, int(prefetch_tiles), int(ablate)))
 
+    def set_pacing(self, enable: bool = True) -> None:
+        check(lib.hb_search_pacing(self._h, int(enable)))
+
     def enable_kernel_timing(self, enable: bool = True) -> None:
         check(lib.hb_search_timing(self._h, int(enable)))
 
