@@ -38,6 +38,8 @@ constexpr int UMMA_K = 16;
 constexpr int kEpiWarps = 8;   // 4 TMEM lane quarters x 2 column halves
 constexpr int kQueueCap = 16;  // pending-candidate queue entries per epilogue thread
 constexpr int kEpiThreads = 32 * kEpiWarps;
+constexpr int kChunk = 64;     // accumulator columns per tcgen05.ld
+constexpr int kGroups = kChunk / 8;
 constexpr int kSearchThreads = 32 * (2 + kEpiWarps);
 constexpr int kProducerWarp = kEpiWarps;      // warp 8
 constexpr int kMmaWarp = kEpiWarps + 1;       // warp 9
@@ -349,12 +351,12 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         const int nvalid = rem >= BN / 2 ? BN / 2 : (rem > 0 ? static_cast<int>(rem) : 0);
         const uint32_t tacc = tmem_lane + static_cast<uint32_t>(abuf * BN);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN / 2; c0 += 32) {
-          if (c0 >= nvalid || p.ablate == 1) break;  // warp-uniform (nvalid is a multiple of 32 except in the bank's last tile)
-          uint32_t v[32];
-          ptx::tmem_ld_32x32b_x32(tacc + c0, v);
+        for (int c0 = 0; c0 < BN / 2; c0 += kChunk) {
+          if (c0 >= nvalid || p.ablate == 1) break;  // warp-uniform
+          uint32_t v[kChunk];
+          ptx::tmem_ld_32x32b_x64(tacc + c0, v);
           ptx::tmem_ld_wait();
-          if (c0 + 32 >= nvalid) {
+          if (c0 + kChunk >= nvalid) {
             // last chunk of this accumulator is now in registers: hand the TMEM buffer back to the
             // MMA issuer (pair leader's barrier) before spending time on selection
             ptx::tc_fence_before();
@@ -366,31 +368,33 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
           }
           if (DUMP && q_row < p.n_queries) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
+            for (int j = 0; j < kChunk; ++j)
               if (c0 + j < nvalid) p.dump[q_row * p.n_rows + col_base + c0 + j] = __uint_as_float(v[j]);
           }
-          if (c0 + 32 > nvalid) {  // last, partial tile of the bank: padded rows never win
+          if (c0 + kChunk > nvalid) {  // last, partial tile of the bank: padded rows never win
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
+            for (int j = 0; j < kChunk; ++j)
               if (c0 + j >= nvalid) v[j] = 0xff800000u;  // -inf
           }
-          // fast reject: max-tree over 4 groups of 8 columns, one compare, one vote
-          float mg[4];
+          // fast reject: max-tree over groups of 8 columns, one compare, one vote
+          float mg[kGroups];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
+          for (int g = 0; g < kGroups; ++g) {
             float m = __uint_as_float(v[8 * g]);
 #pragma unroll
             for (int j = 1; j < 8; ++j) m = fmaxf(m, __uint_as_float(v[8 * g + j]));
             mg[g] = m;
           }
-          const float m = fmaxf(fmaxf(mg[0], mg[1]), fmaxf(mg[2], mg[3]));
+          float m = mg[0];
+#pragma unroll
+          for (int g = 1; g < kGroups; ++g) m = fmaxf(m, mg[g]);
           if (__any_sync(0xffffffffu, m > tau) && p.ablate != 2) {
             uint32_t done = 0;  // groups already queued (bit g)
             bool fold;
             do {
               fold = false;
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
+              for (int g = 0; g < kGroups; ++g) {
                 if (!fold && !((done >> g) & 1u)) {
                   if (__any_sync(0xffffffffu, mg[g] > tau)) {
                     if (__any_sync(0xffffffffu, cnt > QC - 8)) {
@@ -411,7 +415,7 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
                   }
                 }
               }
-              if (fold) {  // the single fold site of the tile loop
+              if (fold) {  // the single in-tile fold site
                 fold_queue<KL, QC>(ls, lr, queue, cnt);
                 cnt = 0;
                 const float worst = ls[KL - 1];
