@@ -233,7 +233,17 @@ def cpu_reference_sample(w, bank, ring, n_img, repeats=1):
     return n_img * S * S / dt, dt, threads
 
 
+def _claim_stdout():
+    """Route everything libraries write to fd 1 (e.g. NCCL's version banner) to stderr and return a
+    file object on the real stdout, so that the only thing on stdout is the final JSON line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    real_stdout = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -290,7 +300,7 @@ def main():
             "e2e": {"value": value, "unit": "patch-queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), file=real_stdout, flush=True)
         return 0
 
     # ------------------------------------------------------------------ B200 arm
@@ -407,7 +417,7 @@ def main():
         }
         if sharded is not None:
             line["sharded"] = sharded
-        print(json.dumps(line))
+        print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
