@@ -397,8 +397,11 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
               for (int g = 0; g < kGroups; ++g) {
                 if (!fold && !((done >> g) & 1u)) {
                   if (__any_sync(0xffffffffu, mg[g] > tau)) {
-                    if (__any_sync(0xffffffffu, cnt > QC - 8)) {
-                      fold = true;  // some lane lacks room for 8 more: fold first, then resume at g
+                    int hits = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) hits += __uint_as_float(v[8 * g + j]) > tau ? 1 : 0;
+                    if (__any_sync(0xffffffffu, cnt + hits > QC)) {
+                      fold = true;  // some lane's queue cannot take its hits: fold first, then resume at g
                     } else {
                       const uint32_t col = static_cast<uint32_t>(col_base + c0 + 8 * g);
 #pragma unroll
@@ -433,9 +436,10 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             if (CG == 2) ptx::mbar_arrive_cluster(bar); else ptx::mbar_arrive_local(bar);
           }
         }
-        // (1) routine folds happen here, after the accumulator was released: keep at least 8 free
-        // queue slots per lane so that the next tile rarely has to fold while it holds TMEM
-        if (__any_sync(0xffffffffu, cnt > QC - 12)) {
+        // routine folds happen here, after the accumulator was released, and only when some lane's
+        // queue is nearly full: a fold costs ~1.5k cycles of this warp, and the MMA of the tile after
+        // next waits for the slowest of all epilogue warps, so folds must be rare
+        if (__any_sync(0xffffffffu, cnt > QC - 4)) {
           fold_queue<KL, QC>(ls, lr, queue, cnt);
           cnt = 0;
           const float worst = ls[KL - 1];
