@@ -17,7 +17,7 @@ bank.configure_search(cta_group=cg); bank.tune_search(4 if cg == 2 else 0, 0)
 for _ in range(3): bank.search(q, 30, 64)
 torch.cuda.synchronize()
 PY
-for cfg in "2 384 12544 1024000"; do
+for cfg in "1 384 12544 1024000" "2 768 21904 1024000"; do
   set -- $cfg
   ncu --set full --clock-control none --import-source on -k regex:search_topk -s 1 -c 1 \
       -o gpurun_out/prof_cg$1_d$2 -f python /tmp/prof_one.py $cfg > gpurun_out/prof_cg$1_d$2.stdout 2>&1
