@@ -15,15 +15,14 @@ template <int LABEL_MODE>
 __global__ void __launch_bounds__(kPackWarps * 32)
 pack_rows_kernel(const float* __restrict__ feats, const uint8_t* __restrict__ mask,
                  const float* __restrict__ soft, const int32_t* __restrict__ sel, int64_t n,
-                 int d, int dpad, int C, int S, int ps, int normalise,
+                 int d, int dpad, int C, int S, int ps, int pp, int normalise,
                  __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32,
                  uint16_t* __restrict__ out_hist) {
   extern __shared__ uint32_t s_hist[];  // kPackWarps * C
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t* hist = s_hist + warp * C;
   const int d4 = d >> 2;  // d % 4 == 0 is enforced on the host
-  const int pp = ps * ps;
-  const int W = S * ps;
+  const int W = S * ps;  // pp = pixels per patch (ps*ps when a mask is given; the bank's value otherwise)
 
   for (int64_t row = static_cast<int64_t>(blockIdx.x) * kPackWarps + warp; row < n;
        row += static_cast<int64_t>(gridDim.x) * kPackWarps) {
@@ -115,10 +114,10 @@ static int launch_pack(Bank* b, const float* feats, const uint8_t* mask, const f
   uint16_t* oh = b->label_hist + row0 * b->C;
   if (mask) {
     pack_rows_kernel<0><<<static_cast<unsigned>(blocks), kPackWarps * 32, smem, st>>>(
-        feats, mask, nullptr, sel, n, b->d, b->dpad, b->C, S, ps, normalise, ob, of, oh);
+        feats, mask, nullptr, sel, n, b->d, b->dpad, b->C, S, ps, b->pp, normalise, ob, of, oh);
   } else {
     pack_rows_kernel<1><<<static_cast<unsigned>(blocks), kPackWarps * 32, smem, st>>>(
-        feats, nullptr, soft, sel, n, b->d, b->dpad, b->C, S, ps, normalise, ob, of, oh);
+        feats, nullptr, soft, sel, n, b->d, b->dpad, b->C, S, ps, b->pp, normalise, ob, of, oh);
   }
   HB_CHECK_CUDA(cudaGetLastError());
   b->rows += n;

@@ -496,15 +496,16 @@ prep_queries_kernel(const float* __restrict__ q, int64_t Q, int d, int dpad,
   }
 }
 
+// Launch (or, with probe != nullptr, only size) the persistent search grid.  The kernel's CTAs wait
+// for each other (pair barriers, L2 pacing), so every CTA must be resident at once: the grid is
+// min(SMs / CG, work items, what the driver says fits) clusters.
 template <int CG, int STAGES, int KP, bool DUMP = false>
 static int launch_search(const Bank* b, const CUtensorMap& tmap_q, const SearchParams& p,
-                         cudaStream_t st) {
+                         cudaStream_t st, int* probe, int n_clusters) {
   using L = SearchSmem<CG, STAGES, KP>;
   auto kern = search_topk_kernel<CG, STAGES, KP, DUMP>;
   HB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic));
-  const int n_clusters = std::max(1, std::min(b->num_sms / CG, p.n_qblocks * p.n_chunks));
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(static_cast<unsigned>(n_clusters * CG));
   cfg.blockDim = dim3(kSearchThreads);
   cfg.dynamicSmemBytes = L::kDynamic;
   cfg.stream = st;
@@ -515,24 +516,34 @@ static int launch_search(const Bank* b, const CUtensorMap& tmap_q, const SearchP
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (probe != nullptr) {
+    int want = std::max(1, std::min(b->num_sms / CG, p.n_qblocks * p.n_chunks));
+    cfg.gridDim = dim3(static_cast<unsigned>(want * CG));
+    int fit = 0;
+    if (cudaOccupancyMaxActiveClusters(&fit, kern, &cfg) == cudaSuccess && fit > 0) want = std::min(want, fit);
+    else (void)cudaGetLastError();
+    *probe = want;
+    return HB_OK;
+  }
+  cfg.gridDim = dim3(static_cast<unsigned>(n_clusters * CG));
   const CUtensorMap& tmap_b = (CG == 2) ? b->tmap_bank_cg2 : b->tmap_bank_cg1;
   HB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmap_q, tmap_b, p));
   return HB_OK;
 }
 
-// Dispatch over (cta_group, k').  Ring depth is what fits beside the k' heap in 227 KB.
+// Dispatch over (cta_group, k').  Ring depth is what fits beside the queues in 227 KB.
 static int dispatch_search(const Bank* b, int cg, int kp, const CUtensorMap& tmap_q,
-                           const SearchParams& p, cudaStream_t st) {
+                           const SearchParams& p, cudaStream_t st, int* probe, int n_clusters) {
   if (p.dump != nullptr) {  // validation build of the same kernel that also writes the raw scores
-    if (cg == 2) return launch_search<2, 6, 64, true>(b, tmap_q, p, st);
-    return launch_search<1, 4, 64, true>(b, tmap_q, p, st);
+    if (cg == 2) return launch_search<2, 6, 64, true>(b, tmap_q, p, st, probe, n_clusters);
+    return launch_search<1, 4, 64, true>(b, tmap_q, p, st, probe, n_clusters);
   }
   if (cg == 2) {
-    if (kp == 32) return launch_search<2, 6, 32>(b, tmap_q, p, st);
-    if (kp == 64) return launch_search<2, 6, 64>(b, tmap_q, p, st);
+    if (kp == 32) return launch_search<2, 6, 32>(b, tmap_q, p, st, probe, n_clusters);
+    if (kp == 64) return launch_search<2, 6, 64>(b, tmap_q, p, st, probe, n_clusters);
   } else {
-    if (kp == 32) return launch_search<1, 4, 32>(b, tmap_q, p, st);
-    if (kp == 64) return launch_search<1, 4, 64>(b, tmap_q, p, st);
+    if (kp == 32) return launch_search<1, 4, 32>(b, tmap_q, p, st, probe, n_clusters);
+    if (kp == 64) return launch_search<1, 4, 64>(b, tmap_q, p, st, probe, n_clusters);
   }
   set_error("hb_search: k_prime=%d not in {32, 64}", kp);
   return HB_ERR_INVALID;
@@ -559,7 +570,16 @@ static int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_
   const size_t off_norm = align_up(off_q + sizeof(__nv_bfloat16) * static_cast<size_t>(Q) * b->dpad, 256);
   const size_t off_cand = align_up(off_norm + sizeof(float) * static_cast<size_t>(Q), 256);
   const size_t off_seed = align_up(off_cand + sizeof(uint64_t) * static_cast<size_t>(plan.n_chunks) * q_pad * kp, 256);
-  const int n_units_used = std::max(1, std::min(b->num_sms / cg, plan.n_qblocks * plan.n_chunks));
+  int n_units_used = 1;
+  {
+    SearchParams probe_p{};
+    probe_p.n_qblocks = plan.n_qblocks;
+    probe_p.n_chunks = plan.n_chunks;
+    probe_p.dump = dump;
+    CUtensorMap unused{};
+    int rc0 = dispatch_search(b, cg, kp, unused, probe_p, st, &n_units_used, 0);
+    if (rc0 != HB_OK) return rc0;
+  }
   const int n_rounds = (plan.n_qblocks * plan.n_chunks + n_units_used - 1) / n_units_used;
   const int pace_groups = (plan.n_tiles / plan.n_chunks + 1) / kPaceTiles + 2;
   const size_t off_pace = align_up(off_seed + sizeof(uint32_t) * static_cast<size_t>(q_pad), 256);
@@ -601,7 +621,7 @@ static int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_
   p.ablate = b->cfg_ablate;
   const int slot = b->timing_count & 63;
   if (b->timing) HB_CHECK_CUDA(cudaEventRecord(b->ev_begin[slot], st));
-  rc = dispatch_search(b, cg, kp, tmap_q, p, st);
+  rc = dispatch_search(b, cg, kp, tmap_q, p, st, nullptr, n_units_used);
   if (rc != HB_OK) return rc;
   if (b->timing) {
     HB_CHECK_CUDA(cudaEventRecord(b->ev_end[slot], st));

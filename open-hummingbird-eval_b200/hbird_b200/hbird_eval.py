@@ -174,6 +174,33 @@ class HbirdEvaluation:
         if self.l_mem_p is not None:
             torch.save(l.cpu(), self.l_mem_p)
 
+    def load_memory(self) -> bool:
+        """hbird_eval.py:380-400 — reload the tensors written by _save_memory (fp32 (N, d) unit rows and
+        (N, C) soft labels) and rebuild the HBM bank and the search backend from them."""
+        import os
+
+        if not (self.f_mem_p and self.l_mem_p and os.path.isfile(self.f_mem_p) and os.path.isfile(self.l_mem_p)):
+            logger.warning("Memory files not found or paths not provided; skipping load.")
+            return False
+        if self.world > 1:
+            raise NotImplementedError("load_memory rebuilds an unsharded bank; run it on one GPU")
+        f = torch.load(self.f_mem_p).to(torch.float32)
+        l = torch.load(self.l_mem_p).to(torch.float32)
+        pp = self.bank.patch_pixels
+        new_bank = ops.MemoryBank(f.shape[1], l.shape[1], pp, max(1, f.shape[0]), self.device.index, self.keep_f32)
+        step = 1 << 20
+        for a in range(0, f.shape[0], step):
+            new_bank.append_soft(f[a:a + step].to(self.device).contiguous(), l[a:a + step].to(self.device).contiguous(),
+                                 normalise=False)
+        new_bank.finalize()
+        self.bank.close()
+        self.bank = new_bank
+        self.shard_counts, self.idx_offset, self.total_rows = [new_bank.rows], 0, new_bank.rows
+        self.label_table = new_bank.label_table()
+        self.__dict__.pop("_export_cache", None)
+        self._create_nn(self.n_neighbours, nn_method=self.nn_method, **self.nn_params)
+        return True
+
     @property
     def feature_memory(self) -> torch.Tensor:
         """The reference's feature_memory (N, d) fp32 CPU tensor, materialised on demand."""

@@ -102,6 +102,22 @@ def test_bank_pack_matches_reference_golden(case):
     bank.close(), nb.close()
 
 
+def test_bank_append_soft_recovers_label_histogram(case):
+    """load_memory path (hbird_eval.py:380-400): a bank rebuilt from the reference's fp32 feature and
+    soft-label tensors exports exactly those tensors again."""
+    cfg, g, data = case
+    fm, lm = cuda(g["feature_memory"]), cuda(g["label_memory"])
+    bank = ops.MemoryBank(data.d, data.C, data.ps * data.ps, fm.shape[0], 0, True)
+    bank.append_soft(fm, lm, normalise=False)
+    bank.finalize()
+    f, l = bank.export()
+    np.testing.assert_array_equal(f.cpu().numpy(), g["feature_memory"])
+    np.testing.assert_array_equal(l.cpu().numpy(), g["label_memory"])
+    hist = bank.label_table().cpu().numpy().astype(np.int64)
+    assert (hist.sum(axis=1) == data.ps * data.ps).all()
+    bank.close()
+
+
 def test_bank_append_validation_errors():
     bank = ops.MemoryBank(64, 3, 16, 32, 0, True)
     feats = torch.zeros((1, 4, 64), device=DEV)
@@ -295,6 +311,39 @@ def test_engine_bounded_memory_matches_reference(name):
     miou = ev.evaluate(data.val_dataloader(), data.S, ignore_index=data.ignore_index)
     assert abs(miou - float(g["miou"])) <= 5e-4
     assert np.abs(ev.last_confusion - g["conf"]).sum() <= 5e-4 * g["conf"].sum()
+
+
+def test_memory_save_and_load_round_trip(tmp_path):
+    """hbird_eval.py:371-400: the saved tensors are the reference's feature/label memory, and a bank
+    rebuilt from them gives the same evaluation."""
+    cfg, g = load_golden("voc_tiny")
+    data = SyntheticSegmentationData(**cfg)
+    fp, lp = str(tmp_path / "f.pt"), str(tmp_path / "l.pt")
+    ev = run_engine(data, f_mem_p=fp, l_mem_p=lp)
+    np.testing.assert_allclose(torch.load(fp).numpy(), g["feature_memory"], atol=2e-7, rtol=0)
+    np.testing.assert_array_equal(torch.load(lp).numpy(), g["label_memory"])
+    m0 = ev.evaluate(data.val_dataloader(), data.S, ignore_index=data.ignore_index)
+    assert ev.load_memory() is True
+    m1 = ev.evaluate(data.val_dataloader(), data.S, ignore_index=data.ignore_index)
+    assert abs(m0 - m1) <= 1e-6 and abs(m1 - float(g["miou"])) <= 5e-4
+    ev.f_mem_p = None
+    assert ev.load_memory() is False
+
+
+def test_search_tuning_knobs_do_not_change_results():
+    """cta_group, L2 pacing, prefetch distance and chunking are performance knobs only."""
+    g = torch.Generator().manual_seed(9)
+    rows = torch.randn((60001, 384), generator=g)
+    q = torch.randn((777, 384), generator=g) * 2
+    bank = bank_from_rows(rows.to(DEV))
+    base_s, base_i, _ = bank.search(q.to(DEV), 30, 64)
+    for cg, pace, pf, chunks in [(1, False, 0, 0), (2, True, 8, 0), (2, False, 0, 1), (1, True, 0, 5), (2, True, 2, 64)]:
+        bank.configure_search(cta_group=cg, max_chunks=chunks)
+        bank.set_pacing(pace)
+        bank.tune_search(prefetch_tiles=pf)
+        s, i, _ = bank.search(q.to(DEV), 30, 64)
+        assert torch.equal(s, base_s) and torch.equal(i, base_i), (cg, pace, pf, chunks)
+    bank.close()
 
 
 def test_hbird_evaluation_entry_point():
