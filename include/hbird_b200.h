@@ -116,6 +116,10 @@ int hb_search_config(hb_bank_t* bank, int cta_group, int max_chunks);
  * ablate is a MEASUREMENT-ONLY switch (results are wrong when it is non-zero): 1 = the epilogue
  * releases accumulators unread (pure GEMM pipeline), 2 = it scans but never inserts. */
 int hb_search_tune(hb_bank_t* bank, int prefetch_tiles, int ablate);
+/* Diagnostics: when stats_dev (device, zeroed, 148*8*8 uint64) is non-NULL, hb_search runs an
+ * instrumented build that accumulates per-epilogue-warp cycle counters {wait, tmem load, slow path,
+ * post-release folds, slow-path entries, folds, tiles, -}.  NULL switches it off. */
+int hb_search_stats(hb_bank_t* bank, unsigned long long* stats_dev);
 /* L2 pacing window of the search kernel (default on): CTAs streaming the same bank chunk stay within
  * ~100 tiles of each other so each tile is read from HBM once per wave. */
 int hb_search_pacing(hb_bank_t* bank, int enable);

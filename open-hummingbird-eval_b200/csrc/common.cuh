@@ -56,6 +56,7 @@ struct Bank {
   int cfg_max_chunks = 0;
   int cfg_prefetch_tiles = -1;  // -1 = auto
   int cfg_ablate = 0;
+  unsigned long long* cfg_stats = nullptr;  // instrumented-build counters (hb_search_stats)
   bool cfg_pace = true;         // L2 pacing window of the search kernel
   int last_launches = 0;
   // optional kernel timing (hb_search_timing)

@@ -230,6 +230,8 @@ __device__ __forceinline__ void tmem_ld_32x32b_x64(uint32_t taddr, uint32_t (&r)
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32b_x32(taddr, r); }
+__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&r)[64]) { tmem_ld_32x32b_x64(taddr, r); }
 __device__ __forceinline__ uint32_t tmem_ld_32x32b_x1(uint32_t taddr) {
   uint32_t r;
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");

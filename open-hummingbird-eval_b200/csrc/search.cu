@@ -38,7 +38,7 @@ constexpr int UMMA_K = 16;
 constexpr int kEpiWarps = 8;   // 4 TMEM lane quarters x 2 column halves
 constexpr int kQueueCap = 16;  // pending-candidate queue entries per epilogue thread
 constexpr int kEpiThreads = 32 * kEpiWarps;
-constexpr int kChunk = 64;     // accumulator columns per tcgen05.ld
+constexpr int kChunk = 32;     // accumulator columns per tcgen05.ld
 constexpr int kGroups = kChunk / 8;
 constexpr int kSearchThreads = 32 * (2 + kEpiWarps);
 constexpr int kProducerWarp = kEpiWarps;      // warp 8
@@ -60,6 +60,7 @@ struct SearchParams {
   uint64_t* cand;      // (n_chunks, n_qblocks*128*CG, KP) candidate keys
   uint32_t* tau_seed;  // (n_qblocks*128*CG) per-query shared threshold, ordered-float bits (0 = none yet)
   float* dump;         // optional (n_queries, n_rows) raw scores (validation only)
+  unsigned long long* stats;  // optional (CTAs, 8 warps, 8) cycle counters (instrumented build only)
   int prefetch_tiles;  // > 0: L2-prefetch bank tiles this many tiles ahead (split over the CTAs)
   uint32_t* pace;      // (rounds, pace_groups) arrival counters of the L2 pacing window (NULL = off)
   int pace_groups;     // counters per round
@@ -73,7 +74,8 @@ struct SearchSmem {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kRingBytes = STAGES * kStageBytes;
   static constexpr int kQueueBytes = kQueueCap * kEpiThreads * 8;
-  static constexpr int kBarOffset = kRingBytes + kQueueBytes;
+  static constexpr int kRowsBytes = (KP / 2) * kEpiThreads * 4;  // bank rows of the list entries
+  static constexpr int kBarOffset = kRingBytes + kQueueBytes + kRowsBytes;
   static constexpr int kNumBars = 2 * STAGES + 4;
   static constexpr int kTotal = kBarOffset + kNumBars * 8 + 16;
   static constexpr int kDynamic = kTotal + 1024;  // slack to align the ring to 1024 B
@@ -123,40 +125,46 @@ __device__ __forceinline__ void reg_bitonic_sort(float (&s)[M], uint32_t (&r)[M]
   }
 }
 // Fold `cnt` queued (score,row) pairs (shared memory, entry j at queue[j*kEpiThreads]) into the
-// sorted-descending register list of KL entries.  QC <= KL / 2 ... KL.
+// sorted-descending list of KL entries.  Between folds only the scores stay in registers (the scan
+// needs nothing but the last one); the bank rows of the entries rest in shared memory
+// (rows[j*kEpiThreads]) and visit registers for the duration of the merge network.  A spill would be
+// ruinous here: with 227 KB of shared memory carved out there is next to no L1 behind local memory.
 template <int KL, int QC>
-__device__ __forceinline__ void fold_queue(float (&ls)[KL], uint32_t (&lr)[KL], const uint2* queue, int cnt) {
-  float qs[QC];
-  uint32_t qr[QC];
+__device__ __forceinline__ void fold_queue(float (&ls)[KL], uint32_t* rows, const uint2* queue, int cnt) {
+  constexpr int QB = 8;  // queue entries folded per pass: bounds the registers the merge needs
+  uint32_t lr[KL];
 #pragma unroll
-  for (int j = 0; j < QC; ++j) {
-    const uint2 e = queue[j * kEpiThreads];
-    const bool ok = j < cnt;
-    qs[j] = ok ? __uint_as_float(e.x) : -INFINITY;
-    qr[j] = ok ? e.y : 0xffffffffu;
-  }
-  reg_bitonic_sort<QC, false>(qs, qr);  // ascending
-  // the QC smallest list entries (descending) against the ascending queue: element-wise max
-  // keeps the QC largest of their union, as a bitonic sequence
+  for (int j = 0; j < KL; ++j) lr[j] = rows[j * kEpiThreads];
+#pragma unroll 1
+  for (int base = 0; base < QC; base += QB) {
+    if (base > 0 && !__any_sync(0xffffffffu, cnt > base)) break;
+    float qs[QB];
+    uint32_t qr[QB];
 #pragma unroll
-  for (int j = 0; j < QC; ++j) {
-    const bool take = qs[j] > ls[KL - QC + j];
-    ls[KL - QC + j] = take ? qs[j] : ls[KL - QC + j];
-    lr[KL - QC + j] = take ? qr[j] : lr[KL - QC + j];
-  }
-  reg_bitonic_merge<QC, KL - QC, true>(ls, lr);  // tail sorted descending
-  if constexpr (KL > QC) {
-    static_assert(KL == 2 * QC, "fold_queue expects KL == QC or KL == 2*QC");
-    // two descending runs of QC: compare i <-> KL-1-i makes both halves bitonic with every head
-    // element >= every tail element, then merge each half
+    for (int j = 0; j < QB; ++j) {
+      const uint2 e = queue[(base + j) * kEpiThreads];
+      const bool ok = base + j < cnt;
+      qs[j] = ok ? __uint_as_float(e.x) : -INFINITY;
+      qr[j] = ok ? e.y : 0xffffffffu;
+    }
+    reg_bitonic_sort<QB, false>(qs, qr);  // ascending
+    // the QB smallest list entries (descending) against the ascending batch: the element-wise max
+    // keeps the QB largest of their union, as a bitonic sequence
 #pragma unroll
-    for (int i = 0; i < QC; ++i) cmpx<true>(ls[i], lr[i], ls[KL - 1 - i], lr[KL - 1 - i]);
-      reg_bitonic_merge<QC, 0, true>(ls, lr);
-      reg_bitonic_merge<QC, QC, true>(ls, lr);
+    for (int j = 0; j < QB; ++j) {
+      const bool take = qs[j] > ls[KL - QB + j];
+      ls[KL - QB + j] = take ? qs[j] : ls[KL - QB + j];
+      lr[KL - QB + j] = take ? qr[j] : lr[KL - QB + j];
+    }
+    // tail ascending: [descending head | ascending tail] is bitonic, one merge sorts the list
+    reg_bitonic_merge<QB, KL - QB, false>(ls, lr);
+    reg_bitonic_merge<KL, 0, true>(ls, lr);
   }
+#pragma unroll
+  for (int j = 0; j < KL; ++j) rows[j * kEpiThreads] = lr[j];
 }
 
-template <int CG, int STAGES, int KP, bool DUMP>
+template <int CG, int STAGES, int KP, int MODE>
 __global__ void __launch_bounds__(kSearchThreads, 1)
 search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
                    const __grid_constant__ CUtensorMap tmap_bank, const SearchParams p) {
@@ -211,10 +219,6 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
     {
       int stage = 0;
       uint32_t phase = 0;
-      // completion bytes of both CTAs of a pair land on the pair leader's barrier
-      uint32_t full_addr[STAGES];
-#pragma unroll
-      for (int s = 0; s < STAGES; ++s) full_addr[s] = (CG == 2) ? ptx::mapa(full_bar(s), 0) : full_bar(s);
       for (int item = cluster_id; item < total_items; item += n_clusters) {
         const int qb = item % p.n_qblocks, chunk = item / p.n_qblocks;
         const int t0 = chunk_tile_begin(p.n_tiles, p.n_chunks, chunk);
@@ -240,9 +244,11 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             ptx::mbar_wait(empty_bar(stage), phase ^ 1u, 1);
             if (ptx::elect_one()) {
               const uint32_t a_dst = smem_base + stage * L::kStageBytes;
+              // completion bytes of both CTAs of a pair land on the pair leader's barrier
+              const uint32_t full_addr = (CG == 2) ? ptx::mapa(full_bar(stage), 0) : full_bar(stage);
               if (is_leader) ptx::mbar_arrive_expect_tx(full_bar(stage), L::kStageBytes * CG);
-              ptx::tma_load_2d<CG>(a_dst, &tmap_q, full_addr[stage], kb * BK, q_row);
-              ptx::tma_load_2d<CG>(a_dst + L::kABytes, &tmap_bank, full_addr[stage], kb * BK, b_row);
+              ptx::tma_load_2d<CG>(a_dst, &tmap_q, full_addr, kb * BK, q_row);
+              ptx::tma_load_2d<CG>(a_dst + L::kABytes, &tmap_bank, full_addr, kb * BK, b_row);
               // bank tiles are shared by all CTAs walking this chunk: each (tile, k-block) box is
               // pulled into L2 ahead of time by exactly one of them
               if (pf_tile && (tile * nkb + kb) % n_clusters == cluster_id)
@@ -300,7 +306,7 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         }
       }
     }
-  } else {
+  } else if (warp < kEpiWarps) {
     // =========================== epilogue: fused top-k' ===========================
     constexpr int KL = KP / 2;                    // list length per (row, column half)
     constexpr int QC = kQueueCap;
@@ -308,24 +314,34 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
     const int half = warp >> 2;                   // which 128 columns of the tile
     const int row_in_tile = quarter * 32 + lane;  // query row owned by this thread
     uint2* queue = reinterpret_cast<uint2*>(smem + L::kRingBytes) + threadIdx.x;  // entry j at [j*kEpiThreads]
+    uint32_t* rows = reinterpret_cast<uint32_t*>(smem + L::kRingBytes + L::kQueueBytes) + threadIdx.x;
     const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + half * (BN / 2);
     const uint32_t tempty_leader0 = (CG == 2) ? ptx::mapa(tempty_bar(0), 0) : tempty_bar(0);
     const uint32_t tempty_leader1 = (CG == 2) ? ptx::mapa(tempty_bar(1), 0) : tempty_bar(1);
     int abuf = 0;
     uint32_t aphase = 0;
+    // hand the current TMEM accumulator back to the MMA issuer (the pair leader's barrier)
+    auto release_accumulator = [&]() {
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        const uint32_t bar = abuf ? tempty_leader1 : tempty_leader0;
+        if (CG == 2) ptx::mbar_arrive_cluster(bar); else ptx::mbar_arrive_local(bar);
+      }
+    };
     for (int item = cluster_id; item < total_items; item += n_clusters) {
       const int qb = item % p.n_qblocks, chunk = item / p.n_qblocks;
       const int t0 = chunk_tile_begin(p.n_tiles, p.n_chunks, chunk);
       const int t1 = chunk_tile_begin(p.n_tiles, p.n_chunks, chunk + 1);
       const int64_t q_row = static_cast<int64_t>(qb * CG + static_cast<int>(cta_rank)) * BM + row_in_tile;
       float ls[KL];
-      uint32_t lr[KL];
 #pragma unroll
       for (int j = 0; j < KL; ++j) {
         ls[j] = -INFINITY;
-        lr[j] = 0xffffffffu;  // "no candidate"
+        rows[j * kEpiThreads] = 0xffffffffu;  // "no candidate"
       }
       int cnt = 0;  // queued, not yet folded
+      long long st_wait = 0, st_load = 0, st_slow = 0, st_fold = 0, st_nfold = 0, st_nslow = 0, st_tiles = 0, t_a = 0;
       // Live threshold sharing: every list that scans bank rows for this query (2 column halves x
       // n_chunks chunks, on different CTAs, possibly at the same time) publishes its current
       // k'/2-th best score with a global atomicMax and re-reads the maximum once per tile.  A
@@ -337,8 +353,10 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       float tau = -INFINITY;
       uint32_t seed_bits = __ldcg(seed_ptr);
       for (int tile = t0; tile < t1; ++tile) {
+        if (MODE == 2) t_a = clock64();
         ptx::mbar_wait(tfull_bar(abuf), aphase, 4);
         ptx::tc_fence_after();
+        if (MODE == 2) { st_wait += clock64() - t_a; ++st_tiles; }
         // software-pipelined refresh of the shared threshold: the value loaded during the previous
         // tile is applied now and the next load is issued, so its L2 latency is never waited on
         if (((tile - t0) & 7) == 0) {
@@ -354,19 +372,12 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         for (int c0 = 0; c0 < BN / 2; c0 += kChunk) {
           if (c0 >= nvalid || p.ablate == 1) break;  // warp-uniform
           uint32_t v[kChunk];
-          ptx::tmem_ld_32x32b_x64(tacc + c0, v);
+          if (MODE == 2) t_a = clock64();
+          ptx::tmem_ld_chunk(tacc + c0, v);
           ptx::tmem_ld_wait();
-          if (c0 + kChunk >= nvalid) {
-            // last chunk of this accumulator is now in registers: hand the TMEM buffer back to the
-            // MMA issuer (pair leader's barrier) before spending time on selection
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              const uint32_t bar = abuf ? tempty_leader1 : tempty_leader0;
-              if (CG == 2) ptx::mbar_arrive_cluster(bar); else ptx::mbar_arrive_local(bar);
-            }
-          }
-          if (DUMP && q_row < p.n_queries) {
+          if (MODE == 2) st_load += clock64() - t_a;
+          const bool last_chunk = c0 + kChunk >= nvalid;
+          if (MODE == 1 && q_row < p.n_queries) {
 #pragma unroll
             for (int j = 0; j < kChunk; ++j)
               if (c0 + j < nvalid) p.dump[q_row * p.n_rows + col_base + c0 + j] = __uint_as_float(v[j]);
@@ -376,7 +387,7 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             for (int j = 0; j < kChunk; ++j)
               if (c0 + j >= nvalid) v[j] = 0xff800000u;  // -inf
           }
-          // fast reject: max-tree over groups of 8 columns, one compare, one vote
+          // fast reject: per-group maxima against tau, one warp-wide OR of the 4-bit result
           float mg[kGroups];
 #pragma unroll
           for (int g = 0; g < kGroups; ++g) {
@@ -385,77 +396,97 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             for (int j = 1; j < 8; ++j) m = fmaxf(m, __uint_as_float(v[8 * g + j]));
             mg[g] = m;
           }
-          float m = mg[0];
+          uint32_t gmask = 0;
 #pragma unroll
-          for (int g = 1; g < kGroups; ++g) m = fmaxf(m, mg[g]);
-          if (__any_sync(0xffffffffu, m > tau) && p.ablate != 2) {
-            uint32_t done = 0;  // groups already queued (bit g)
-            bool fold;
-            do {
-              fold = false;
+          for (int g = 0; g < kGroups; ++g) gmask |= (mg[g] > tau ? 1u : 0u) << g;
+          uint32_t hot = __reduce_or_sync(0xffffffffu, gmask);  // groups in which some lane has a survivor
+          if (p.ablate == 2) hot = 0;
+          if (hot == 0) {
+            if (last_chunk) release_accumulator();
+          } else {
+            if (MODE == 2) { t_a = clock64(); ++st_nslow; }
+            // Survivors of a group are appended with independent stores (slot = cnt + rank of the
+            // column among the lane's hits).  If some lane's queue cannot take its hits, the warp
+            // folds first -- that needs the registers v occupies, so the chunk is re-read from TMEM
+            // afterwards (the accumulator is still ours) and appending resumes at that group.
+            int resume = 0;
+            for (;;) {
+              int blocked = -1;
 #pragma unroll
               for (int g = 0; g < kGroups; ++g) {
-                if (!fold && !((done >> g) & 1u)) {
-                  if (__any_sync(0xffffffffu, mg[g] > tau)) {
-                    int hits = 0;
+                if (blocked < 0 && g >= resume && ((hot >> g) & 1u)) {
+                  uint32_t hm = 0;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) hits += __uint_as_float(v[8 * g + j]) > tau ? 1 : 0;
-                    if (__any_sync(0xffffffffu, cnt + hits > QC)) {
-                      fold = true;  // some lane's queue cannot take its hits: fold first, then resume at g
-                    } else {
-                      const uint32_t col = static_cast<uint32_t>(col_base + c0 + 8 * g);
-#pragma unroll
-                      for (int j = 0; j < 8; ++j) {
-                        if (__uint_as_float(v[8 * g + j]) > tau) {
-                          queue[cnt * kEpiThreads] = make_uint2(v[8 * g + j], col + j);
-                          ++cnt;
-                        }
-                      }
-                      done |= 1u << g;
-                    }
+                  for (int j = 0; j < 8; ++j) hm |= (__uint_as_float(v[8 * g + j]) > tau ? 1u : 0u) << j;
+                  const int h = __popc(hm);
+                  if (__any_sync(0xffffffffu, cnt + h > QC)) {
+                    blocked = g;
                   } else {
-                    done |= 1u << g;
+                    const uint32_t col = static_cast<uint32_t>(col_base + c0 + 8 * g);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                      if ((hm >> j) & 1u)
+                        queue[(cnt + __popc(hm & ((1u << j) - 1u))) * kEpiThreads] = make_uint2(v[8 * g + j], col + j);
+                    }
+                    cnt += h;
                   }
                 }
               }
-              if (fold) {  // the single in-tile fold site
-                fold_queue<KL, QC>(ls, lr, queue, cnt);
-                cnt = 0;
-                const float worst = ls[KL - 1];
-                if (worst > seed) atomicMax(seed_ptr, f32_to_ordered(worst));
-                tau = fmaxf(seed, worst);
+              if (blocked < 0) break;
+              if (MODE == 2) ++st_nfold;
+              fold_queue<KL, QC>(ls, rows, queue, cnt);  // v is dead here
+              cnt = 0;
+              const float worst = ls[KL - 1];
+              if (worst > seed) atomicMax(seed_ptr, f32_to_ordered(worst));
+              tau = fmaxf(seed, worst);
+              resume = blocked;
+              ptx::tmem_ld_chunk(tacc + c0, v);
+              ptx::tmem_ld_wait();
+              if (c0 + kChunk > nvalid) {
+#pragma unroll
+                for (int j = 0; j < kChunk; ++j)
+                  if (c0 + j >= nvalid) v[j] = 0xff800000u;
               }
-            } while (fold);
+            }
+            if (last_chunk) release_accumulator();
+            if (MODE == 2) st_slow += clock64() - t_a;
           }
         }
-        if (nvalid == 0 || p.ablate == 1) {  // nothing was read: release here
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            const uint32_t bar = abuf ? tempty_leader1 : tempty_leader0;
-            if (CG == 2) ptx::mbar_arrive_cluster(bar); else ptx::mbar_arrive_local(bar);
-          }
-        }
+        if (nvalid == 0 || p.ablate == 1) release_accumulator();  // nothing was read
         // routine folds happen here, after the accumulator was released, and only when some lane's
         // queue is nearly full: a fold costs ~1.5k cycles of this warp, and the MMA of the tile after
         // next waits for the slowest of all epilogue warps, so folds must be rare
         if (__any_sync(0xffffffffu, cnt > QC - 4)) {
-          fold_queue<KL, QC>(ls, lr, queue, cnt);
+          if (MODE == 2) { t_a = clock64(); ++st_nfold; }
+          fold_queue<KL, QC>(ls, rows, queue, cnt);
           cnt = 0;
           const float worst = ls[KL - 1];
           if (worst > seed) atomicMax(seed_ptr, f32_to_ordered(worst));
           tau = fmaxf(seed, worst);
+          if (MODE == 2) st_fold += clock64() - t_a;
         }
         abuf ^= 1;
         if (abuf == 0) aphase ^= 1u;
       }
-      if (__any_sync(0xffffffffu, cnt > 0)) fold_queue<KL, QC>(ls, lr, queue, cnt);
+      if (__any_sync(0xffffffffu, cnt > 0)) fold_queue<KL, QC>(ls, rows, queue, cnt);
+      if (MODE == 2 && lane == 0) {
+        unsigned long long* o = p.stats + (static_cast<size_t>(blockIdx.x) * kEpiWarps + warp) * 8;
+        atomicAdd(o + 0, static_cast<unsigned long long>(st_wait));
+        atomicAdd(o + 1, static_cast<unsigned long long>(st_load));
+        atomicAdd(o + 2, static_cast<unsigned long long>(st_slow));
+        atomicAdd(o + 3, static_cast<unsigned long long>(st_fold));
+        atomicAdd(o + 4, static_cast<unsigned long long>(st_nslow));
+        atomicAdd(o + 5, static_cast<unsigned long long>(st_nfold));
+        atomicAdd(o + 6, static_cast<unsigned long long>(st_tiles));
+      }
       // emit this item's candidates (k'/2 per column half; the re-rank kernel merges them)
       const int64_t q_pad = static_cast<int64_t>(p.n_qblocks) * BM * CG;
       uint64_t* out = p.cand + (static_cast<int64_t>(chunk) * q_pad + q_row) * KP + half * KL;
 #pragma unroll
-      for (int j = 0; j < KL; ++j)
-        out[j] = (lr[j] == 0xffffffffu) ? 0ull : make_key(ls[j], lr[j]);
+      for (int j = 0; j < KL; ++j) {
+        const uint32_t r = rows[j * kEpiThreads];
+        out[j] = (r == 0xffffffffu) ? 0ull : make_key(ls[j], r);
+      }
     }
   }
 
@@ -499,11 +530,11 @@ prep_queries_kernel(const float* __restrict__ q, int64_t Q, int d, int dpad,
 // Launch (or, with probe != nullptr, only size) the persistent search grid.  The kernel's CTAs wait
 // for each other (pair barriers, L2 pacing), so every CTA must be resident at once: the grid is
 // min(SMs / CG, work items, what the driver says fits) clusters.
-template <int CG, int STAGES, int KP, bool DUMP = false>
+template <int CG, int STAGES, int KP, int MODE = 0>
 static int launch_search(const Bank* b, const CUtensorMap& tmap_q, const SearchParams& p,
                          cudaStream_t st, int* probe, int n_clusters) {
   using L = SearchSmem<CG, STAGES, KP>;
-  auto kern = search_topk_kernel<CG, STAGES, KP, DUMP>;
+  auto kern = search_topk_kernel<CG, STAGES, KP, MODE>;
   HB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic));
   cudaLaunchConfig_t cfg{};
   cfg.blockDim = dim3(kSearchThreads);
@@ -535,15 +566,19 @@ static int launch_search(const Bank* b, const CUtensorMap& tmap_q, const SearchP
 static int dispatch_search(const Bank* b, int cg, int kp, const CUtensorMap& tmap_q,
                            const SearchParams& p, cudaStream_t st, int* probe, int n_clusters) {
   if (p.dump != nullptr) {  // validation build of the same kernel that also writes the raw scores
-    if (cg == 2) return launch_search<2, 6, 64, true>(b, tmap_q, p, st, probe, n_clusters);
-    return launch_search<1, 4, 64, true>(b, tmap_q, p, st, probe, n_clusters);
+    if (cg == 2) return launch_search<2, 5, 64, 1>(b, tmap_q, p, st, probe, n_clusters);
+    return launch_search<1, 3, 64, 1>(b, tmap_q, p, st, probe, n_clusters);
+  }
+  if (p.stats != nullptr) {  // instrumented build: per-warp cycle counters of the epilogue
+    if (cg == 2) return launch_search<2, 5, 64, 2>(b, tmap_q, p, st, probe, n_clusters);
+    return launch_search<1, 3, 64, 2>(b, tmap_q, p, st, probe, n_clusters);
   }
   if (cg == 2) {
-    if (kp == 32) return launch_search<2, 6, 32>(b, tmap_q, p, st, probe, n_clusters);
-    if (kp == 64) return launch_search<2, 6, 64>(b, tmap_q, p, st, probe, n_clusters);
+    if (kp == 32) return launch_search<2, 5, 32>(b, tmap_q, p, st, probe, n_clusters);
+    if (kp == 64) return launch_search<2, 5, 64>(b, tmap_q, p, st, probe, n_clusters);
   } else {
-    if (kp == 32) return launch_search<1, 4, 32>(b, tmap_q, p, st, probe, n_clusters);
-    if (kp == 64) return launch_search<1, 4, 64>(b, tmap_q, p, st, probe, n_clusters);
+    if (kp == 32) return launch_search<1, 3, 32>(b, tmap_q, p, st, probe, n_clusters);
+    if (kp == 64) return launch_search<1, 3, 64>(b, tmap_q, p, st, probe, n_clusters);
   }
   set_error("hb_search: k_prime=%d not in {32, 64}", kp);
   return HB_ERR_INVALID;
@@ -558,9 +593,9 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_t idx_offset,
                        float* out_scores, int64_t* out_idx, float* out_qnorm, float* dump, int cg_override,
                        cudaStream_t st) {
-  // measured on B200 (profiles/): independent CTAs win for d <= 512, CTA pairs (half the B-operand
-  // traffic per SM) from d = 768 up
-  int cg = cg_override ? cg_override : (b->cfg_cta_group ? b->cfg_cta_group : (b->dpad <= 512 ? 1 : 2));
+  // measured on B200 (profiles/): CTA pairs (cta_group::2: half the B-operand shared-memory traffic
+  // per SM) win at every bank size and feature dim; cta_group 1 stays selectable
+  int cg = cg_override ? cg_override : (b->cfg_cta_group ? b->cfg_cta_group : 2);
   if (b->num_sms < 2) cg = 1;
   const SearchPlan plan = plan_search(b->rows, Q, cg, b->num_sms, b->cfg_max_chunks);
   const int64_t q_pad = static_cast<int64_t>(plan.n_qblocks) * BM * cg;
@@ -576,6 +611,7 @@ static int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_
     probe_p.n_qblocks = plan.n_qblocks;
     probe_p.n_chunks = plan.n_chunks;
     probe_p.dump = dump;
+    probe_p.stats = b->cfg_stats;
     CUtensorMap unused{};
     int rc0 = dispatch_search(b, cg, kp, unused, probe_p, st, &n_units_used, 0);
     if (rc0 != HB_OK) return rc0;
@@ -617,6 +653,7 @@ static int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_
   p.pace = b->cfg_pace ? pace : nullptr;
   p.pace_groups = pace_groups;
   p.dump = dump;
+  p.stats = b->cfg_stats;
   p.prefetch_tiles = b->cfg_prefetch_tiles >= 0 ? b->cfg_prefetch_tiles : (cg == 2 ? 4 : 0);
   p.ablate = b->cfg_ablate;
   const int slot = b->timing_count & 63;
@@ -659,6 +696,12 @@ int hb_search(hb_bank_t* bank, const float* q_dev, int64_t Q, int k, int k_prime
   HB_CHECK_CUDA(cudaSetDevice(b->device));
   return hb::search_impl(b, q_dev, Q, k, k_prime, idx_offset, out_scores_dev, out_idx_dev, out_qnorm_dev,
                          nullptr, 0, static_cast<cudaStream_t>(stream));
+}
+
+int hb_search_stats(hb_bank_t* bank, unsigned long long* stats_dev) {
+  HB_REQUIRE(bank != nullptr, "hb_search_stats: bank is NULL");
+  reinterpret_cast<Bank*>(bank)->cfg_stats = stats_dev;
+  return HB_OK;
 }
 
 int hb_search_pacing(hb_bank_t* bank, int enable) {

@@ -40,6 +40,7 @@ _SIGNATURES = [
     ("hb_search", c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     ("hb_search_config", c_int, [c_void_p, c_int, c_int]),
     ("hb_search_tune", c_int, [c_void_p, c_int, c_int]),
+    ("hb_search_stats", c_int, [c_void_p, c_void_p]),
     ("hb_search_pacing", c_int, [c_void_p, c_int]),
     ("hb_search_last_launches", c_int, [c_void_p]),
     ("hb_search_timing", c_int, [c_void_p, c_int]),

@@ -144,6 +144,11 @@ class MemoryBank:
         """ablate != 0 is for measurement only (wrong results): 1 = GEMM pipeline alone, 2 = scan only."""
         check(lib.hb_search_tune(self._h, int(prefetch_tiles), int(ablate)))
 
+    def set_stats_buffer(self, buf: Optional[torch.Tensor]) -> None:
+        """Diagnostics: int64 CUDA tensor of 148*8*8 zeros to collect epilogue cycle counters, or None."""
+        self._stats_buf = buf
+        check(lib.hb_search_stats(self._h, ptr(buf)))
+
     def set_pacing(self, enable: bool = True) -> None:
         check(lib.hb_search_pacing(self._h, int(enable)))
 

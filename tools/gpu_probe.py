@@ -160,28 +160,38 @@ def perf(res):
     except Exception:
         pass
     peak = peaks.get("bf16_tflops_sustained", 1425.8)
-    for (name, Q, N, d) in [("cfg1", 12544, 102400, 384), ("cfg2", 12544, 1024000, 384),
-                            ("cfg3_shard8", 21904, 1280000, 768), ("d768_1M", 21904, 1024000, 768)]:
+    shapes = [("cfg1", 12544, 102400, 384), ("cfg2", 12544, 1024000, 384),
+              ("cfg3_shard8", 21904, 1280000, 768), ("d768_1M", 21904, 1024000, 768)]
+    variants = [(1, -1, 0, 64), (2, -1, 0, 64), (1, -1, 2, 64), (2, -1, 2, 64), (2, -1, 1, 64), (1, -1, 0, 32), (2, -1, 0, 32)]
+    if os.environ.get("PROBE_SHAPES"):
+        shapes = [s for s in shapes if s[0] in os.environ["PROBE_SHAPES"].split(",")]
+    for (name, Q, N, d) in shapes:
         feats = synth_bank(N, d, seed=5)
         bank = make_bank(feats)
         del feats
         q = synth_bank(Q, d, seed=9) * 3.0
-        for cg, pf, ab in ((1, 0, 0), (2, 4, 0), (1, 0, 1), (2, 4, 1), (1, 0, 2), (2, 4, 2)):
+        for cg, pf, ab, kp in variants:
             bank.configure_search(cta_group=cg)
             bank.tune_search(prefetch_tiles=pf, ablate=ab)
             for _ in range(2):
-                bank.search(q, 30, 64)
+                bank.search(q, 30, kp)
             torch.cuda.synchronize()
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            # time-based: at least ~0.6 s per variant so power/clock state settles
+            bank.search(q, 30, kp)
+            torch.cuda.synchronize()
+            t0 = time.time()
+            bank.search(q, 30, kp)
+            torch.cuda.synchronize()
+            iters = max(5, int(0.6 / max(time.time() - t0, 1e-4)))
             ev0.record()
-            iters = 5
             for _ in range(iters):
-                bank.search(q, 30, 64)
+                bank.search(q, 30, kp)
             ev1.record()
             torch.cuda.synchronize()
             ms = ev0.elapsed_time(ev1) / iters
             tf = 2.0 * Q * N * d / (ms * 1e-3) / 1e12
-            res[f"perf_{name}_cg{cg}_pf{pf}_ab{ab}"] = {"ms": ms, "qps": Q / (ms * 1e-3), "tflops": tf, "frac_sustained": tf / peak}
+            res[f"perf_{name}_cg{cg}_kp{kp}_ab{ab}"] = {"ms": ms, "qps": Q / (ms * 1e-3), "tflops": tf, "frac_sustained": tf / peak}
         bank.close()
 
 
