@@ -228,9 +228,39 @@ def cpu_reference_sample(w, bank, ring, n_img, repeats=1):
         pass
     t0 = time.perf_counter()
     for _ in range(repeats):
-        O.evaluate(fm, lm, batches, w["C"], S, K_NEIGH, w["ignore"], BETA)
+        ref = O.evaluate(fm, lm, batches, w["C"], S, K_NEIGH, w["ignore"], BETA, return_details=True)
     dt = (time.perf_counter() - t0) / repeats
-    return n_img * S * S / dt, dt, threads
+    return n_img * S * S / dt, dt, threads, ref
+
+
+def parity_vs_oracle(ops, torch, w, bank, table, ring, n_img, ref):
+    """The same n_img images through the CUDA path, compared with what the oracle just computed:
+    the "mIoU delta" of the headline metric, measured on this workload's own bank."""
+    import numpy as np
+
+    from hbird_b200.utils.eval_metrics import miou_from_confusion
+
+    ref_miou, ref_conf, det = ref
+    S, d, H, C = w["S"], w["d"], w["S"] * w["ps"], w["C"]
+    q, y = ring[0]
+    qs, ys = q[:n_img * S * S].contiguous(), y[:n_img].contiguous()
+    scores, idx, qn = bank.search(qs, K_NEIGH, K_PRIME)
+    lh = ops.label_transfer(table, w["ps"] ** 2, scores, idx, qn, BETA)
+    pred = ops.upsample_argmax(lh, n_img, S, H, H)
+    conf = torch.zeros((C, C), dtype=torch.int64, device=q.device)
+    ops.confusion_accumulate(conf, ops.decode_mask(ys, False).view(n_img, H, H), pred, w["ignore"])
+    miou = miou_from_confusion(conf.cpu().numpy())[0]
+    ref_idx = np.concatenate(det["idx"])
+    ref_dist = np.concatenate(det["dist"])
+    got_idx, got_s = idx.cpu().numpy(), scores.cpu().numpy()
+    recall = float((got_idx[:, :, None] == ref_idx[:, None, :]).any(axis=2).mean())
+    rel = float((np.abs(got_s - ref_dist) / np.maximum(np.abs(ref_dist), 1e-6)).max())
+    ref_pred = np.concatenate(det["pred"])[:, 0]
+    agree = float((pred.cpu().numpy() == ref_pred).mean())
+    return {"images": n_img, "queries": n_img * S * S, "miou_b200": miou, "miou_oracle": ref_miou,
+            "miou_delta_points": abs(miou - ref_miou) * 100.0, "recall_at_30": recall, "score_max_rel_err": rel,
+            "pred_pixel_agreement": agree, "confusion_abs_diff": int(np.abs(conf.cpu().numpy() - ref_conf).sum()),
+            "gates": "recall>=0.999, rel<=1e-3, |dmIoU|<=0.05 points"}
 
 
 def _claim_stdout():
@@ -283,7 +313,7 @@ def main():
         n_img = 1 if w["N"] >= 1_000_000 else 4
         qps_list = []
         for i in range(args.warmup + args.steps):
-            qps, dt, threads = cpu_reference_sample(w, bank, ring, n_img)
+            qps, dt, threads, _ = cpu_reference_sample(w, bank, ring, n_img)
             if i >= args.warmup:
                 qps_list.append((qps, dt))
         tot_q = n_img * w["S"] ** 2 * len(qps_list)
@@ -377,9 +407,11 @@ def main():
 
     # ---- CPU baseline beside it (rank 0, N = 1 only)
     cpu = None
+    parity = None
     if world == 1 and not args.no_cpu_baseline:
         n_img = 4 if w["N"] >= 1_000_000 else 16
-        qps, dt, threads = cpu_reference_sample(w, bank, ring, n_img)
+        qps, dt, threads, ref = cpu_reference_sample(w, bank, ring, n_img)
+        parity = parity_vs_oracle(ops, torch, w, bank, table, ring, n_img, ref)
         cpu = {"value": qps, "unit": "patch-queries/s", "cores": threads, "kind": "port",
                "sample": f"{n_img} images = {n_img * w['S'] ** 2} patch-queries against the full {w['N']:,}-row bank, "
                          f"{dt:.1f} s of oracle (numpy/BLAS) time"}
@@ -405,10 +437,12 @@ def main():
             },
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic,
+                         "frac_of_nominal_2250": (achieved / 2250.0) if achieved else None,
                          "kernel": "search_topk_kernel (tcgen05 GEMM + fused top-k')", "kernel_ms": kern_ms,
                          "kernel_launches_timed": kern_n, "flop_per_launch": flop, "peak_source": peak_src,
                          "kernel_share_of_step": kern_ms / ms_per_step if ms_per_step else None},
             "cpu_baseline": cpu,
+            "parity": parity,
             "e2e": {"value": e2e_value, "unit": "patch-queries/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches_per_step * args.steps,
