@@ -29,6 +29,15 @@ def case(request):
     return cfg, g, SyntheticSegmentationData(**cfg)
 
 
+def batches_np_cpu(data, loader):
+    """numpy batches; the table model may have been moved to the GPU by an engine (same values)."""
+    out = []
+    for x, y in loader:
+        f, _ = data.ftr_extr_fn(data.model, x)
+        out.append((f.cpu().numpy(), y.numpy()))
+    return out
+
+
 def build_bank_from_loader(data, keep_f32=True):
     bank = None
     for x, y in data.train_dataloader():
@@ -344,6 +353,42 @@ def test_search_tuning_knobs_do_not_change_results():
         s, i, _ = bank.search(q.to(DEV), 30, 64)
         assert torch.equal(s, base_s) and torch.equal(i, base_i), (cg, pace, pf, chunks)
     bank.close()
+
+
+def test_engine_ade_shaped_151_classes_vs_oracle():
+    """ADE20K shape of BASELINE configs[3] in miniature: 151 classes, ignore_index 0, ps = 14."""
+    data = SyntheticSegmentationData(num_train=12, num_val=4, input_size=112, patch_size=14, d_model=256,
+                                     num_classes=151, batch_size=4, ignore_index=0, cells=6, seed=3)
+    ev = run_engine(data)
+    miou = ev.evaluate(data.val_dataloader(), data.S, ignore_index=0)
+    fm, lm = O.build_memory(batches_np_cpu(data, data.train_dataloader()), data.C, data.S)
+    ref_miou, ref_conf = O.evaluate(fm, lm, batches_np_cpu(data, data.val_dataloader()), data.C, data.S, 30, 0)
+    assert abs(miou - ref_miou) <= 5e-4
+    assert ev.last_confusion.sum() == ref_conf.sum()
+    assert np.abs(ev.last_confusion - ref_conf).sum() <= 5e-4 * ref_conf.sum()
+    assert ev.last_confusion[0].sum() == 0  # ignored gt class contributes no pixels
+
+
+def test_engine_augmentation_epochs_duplicate_rows_tie_handling():
+    """augmentation_epoch=2 over a deterministic loader stores every patch twice: top-k
+    membership among exact ties is ambiguous, the score multiset and the mIoU are not."""
+    cfg, g = load_golden("voc_tiny")
+    data = SyntheticSegmentationData(**cfg)
+    fe = FeatureExtractorSimple(data.model, data.ftr_extr_fn, data.S, data.d)
+    ev = HbirdEvaluation(fe, data.train_dataloader(), num_classes=data.C, n_neighbours=30, augmentation_epoch=2,
+                         device=DEV, nn_method="b200", dataset_size=data.get_train_dataset_size())
+    assert ev.bank.rows == 2 * g["feature_memory"].shape[0]
+    q = np.concatenate([f.reshape(-1, f.shape[-1]) for f, _ in batches_np_cpu(data, data.val_dataloader())])
+    s, i, _ = ev.bank.search(cuda(q), 30, 64)
+    bank2 = np.concatenate([g["feature_memory"], g["feature_memory"]])
+    ri, rd = O.search_exact_ip(q, bank2, 30)
+    np.testing.assert_allclose(s.cpu().numpy(), rd, rtol=1e-5, atol=1e-6)  # same score multiset, sorted
+    n = g["feature_memory"].shape[0]
+    assert recall(i.cpu().numpy() % n, ri % n) >= 0.999            # same patches up to the duplicate copy
+    miou = ev.evaluate(data.val_dataloader(), data.S, ignore_index=data.ignore_index)
+    fm2, lm2 = bank2, np.concatenate([g["label_memory"], g["label_memory"]])
+    ref_miou, _ = O.evaluate(fm2, lm2, batches_np_cpu(data, data.val_dataloader()), data.C, data.S, 30, data.ignore_index)
+    assert abs(miou - ref_miou) <= 5e-4
 
 
 def test_hbird_evaluation_entry_point():
