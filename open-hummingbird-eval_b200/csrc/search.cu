@@ -3,26 +3,29 @@
 // Replaces GpuIndexFlatIP.search as called from search_faiss.py:83-90 (first, bf16 pass; the
 // exact fp32 re-rank that restores the reference's metric is K2b in rerank.cu).
 //
-// Structure (one persistent CTA, or CTA pair with cta_group::2, per SM):
+// Structure (one persistent CTA pair with cta_group::2 -- or single CTA with cta_group::1 -- per SM):
 //   warp 8      TMA producer: streams 128x64 query tiles and (256/CG)x64 bank tiles (bf16,
-//               128B-swizzled) through a STAGES-deep shared-memory ring.
-//   warp 9      tcgen05.mma issuer (one lane; pair leader only): 128*CG x 256 x 16 UMMAs into one
-//               of two 256-column TMEM accumulators; tcgen05.commit frees ring slots and
-//               publishes finished accumulators.  Also owns TMEM alloc/dealloc.
+//               128B-swizzled) through a STAGES-deep shared-memory ring; L2-prefetches bank tiles
+//               ahead and paces itself against the other CTAs of the wave (see kPaceTiles).
+//   warp 9      tcgen05.mma issuer (pair leader only): 128*CG x 256 x 16 UMMAs into one of two
+//               256-column TMEM accumulators; tcgen05.commit frees ring slots and publishes finished
+//               accumulators.  Also owns TMEM alloc/dealloc.  Both issue warps stay converged and
+//               issue under elect.sync so that descriptors live in uniform registers.
 //   warps 0..7  epilogue: each thread owns ONE query row (TMEM lane) and one 128-column half of the
-//               tile, and keeps its k'/2 best (score, row) pairs as a SORTED LIST IN REGISTERS.
-//               A max-tree + one vote rejects 32 columns at a time against tau = the list's last
-//               score.  A survivor costs one predicated 8-byte store into a 16-entry per-thread
-//               queue in shared memory; when any lane's queue is nearly full the whole warp folds
-//               queues into lists with a fully unrolled bitonic network ON REGISTERS, in lock-step
-//               (no divergence), so the merge is amortised over all 32 queries of the warp.
-//               Accumulator double-buffering overlaps this scan with the MMAs of the next tile.
-// The two single-thread roles sit in the HIGHEST warp ids on purpose: the SM's warp arbiter
-// favours higher warp ids, so the TMA/MMA issue slots are never starved by the ALU-heavy
-// selection warps that share their scheduler.
+//               tile and keeps its k'/2 best candidates as a sorted list (scores in registers, bank
+//               rows in shared memory).  Per 32 columns: tcgen05.ld, max-trees over groups of 8, one
+//               warp-wide OR against tau = the list's last score.  Survivors (rare) go to a 16-entry
+//               per-thread queue in shared memory with independent predicated stores; when some
+//               lane's queue is nearly full the whole warp folds queues into lists with fully
+//               unrolled bitonic networks on registers, in lock-step (no divergence), so the fold
+//               is amortised over the warp's 32 queries.  The TMEM buffer is handed back as soon
+//               as its last chunk is in registers; accumulator double-buffering overlaps the scan
+//               with the MMAs of the next tile.  The epilogue must not spill: with 227 KB of shared
+//               memory carved out there is no L1 behind local memory.
 // Work item = (query block of 128*CG rows) x (bank chunk of consecutive 256-row tiles); items are
-// dealt round-robin to the persistent CTAs so that concurrently running CTAs walk the same bank
-// tiles (L2 reuse) with different queries.  Each item emits k' unsorted candidate keys per query.
+// dealt round-robin, chunk-major, to the persistent CTAs so that concurrently running CTAs walk
+// the same bank tiles (L2 reuse) with different queries.  Each item emits k' unsorted candidate
+// keys per query; thresholds are shared between the lists of one query through global memory.
 #include <algorithm>
 
 #include "common.cuh"
