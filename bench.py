@@ -217,7 +217,9 @@ def cpu_reference_sample(w, bank, ring, n_img, repeats=1):
     q, y = ring[0]
     feats = q.view(w["B"], S * S, d)[:n_img].cpu().numpy()
     yy = y[:n_img].cpu().numpy()
-    batches = [(feats[i:i + 1], yy[i:i + 1]) for i in range(n_img)]  # one image per block bounds host RAM
+    # score blocks of at most ~4 GB of host RAM: (images per block) * S*S * N * 4 B
+    per_block = max(1, min(n_img, int(4e9 // (S * S * fm.shape[0] * 4))))
+    batches = [(feats[i:i + per_block], yy[i:i + per_block]) for i in range(0, n_img, per_block)]
     threads = os.cpu_count() or 1
     try:
         from threadpoolctl import threadpool_info

@@ -102,27 +102,49 @@ def sample_patches(patchified: np.ndarray, num_classes: int, K: int, uniform: np
 
 
 # ------------------------------------------------------------------ search (A6)
-def search_exact_ip(q: np.ndarray, bank: np.ndarray, k: int, block: int = 4096) -> Tuple[np.ndarray, np.ndarray]:
+def _topk_rows(s: np.ndarray, kk: int) -> Tuple[np.ndarray, np.ndarray]:
+    """Per-row exact top-kk of a score block: descending score, ties by ascending index."""
+    N = s.shape[1]
+    if kk < N:
+        part = np.argpartition(-s, kk - 1, axis=1)[:, :kk]
+    else:
+        part = np.tile(np.arange(N), (s.shape[0], 1))
+    ps = np.take_along_axis(s, part, axis=1)
+    order = np.lexsort((part, -ps), axis=1)
+    return np.take_along_axis(part, order, axis=1), np.take_along_axis(ps, order, axis=1)
+
+
+def search_exact_ip(q: np.ndarray, bank: np.ndarray, k: int, block: int = 4096,
+                    threads: Optional[int] = None) -> Tuple[np.ndarray, np.ndarray]:
     """hbird/nn/search_faiss.py:39-41,83-90 — GpuIndexFlatIP.search: exact top-k by inner product
     of raw queries with the unit-norm bank, descending; faiss pads with (-inf, -1) when N < k.
-    Returns (indices int64 (Q, k), distances fp32 (Q, k)) — indices first, as the plugin does."""
+    Returns (indices int64 (Q, k), distances fp32 (Q, k)) — indices first, as the plugin does.
+    The GEMM uses the BLAS thread pool; the per-row selection is spread over `threads` host threads
+    (default: all cores) so that the CPU baseline uses the whole host, as faiss-cpu would."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+
     q = np.ascontiguousarray(q, dtype=F32)
     bank = np.ascontiguousarray(bank, dtype=F32)
     Q, N = q.shape[0], bank.shape[0]
     kk = min(k, N)
     idx = np.full((Q, k), -1, dtype=np.int64)
     dist = np.full((Q, k), -np.inf, dtype=F32)
+    threads = threads or os.cpu_count() or 1
     for a in range(0, Q, block):
         s = q[a:a + block] @ bank.T
-        if kk < N:
-            part = np.argpartition(-s, kk - 1, axis=1)[:, :kk]
+        rows = s.shape[0]
+        nsplit = max(1, min(threads, rows // 8))
+        if nsplit == 1:
+            i, d = _topk_rows(s, kk)
+            idx[a:a + rows, :kk], dist[a:a + rows, :kk] = i, d
         else:
-            part = np.tile(np.arange(N), (s.shape[0], 1))
-        ps = np.take_along_axis(s, part, axis=1)
-        # order by descending score, ties by ascending index
-        order = np.lexsort((part, -ps), axis=1)
-        idx[a:a + block, :kk] = np.take_along_axis(part, order, axis=1)
-        dist[a:a + block, :kk] = np.take_along_axis(ps, order, axis=1)
+            bounds = [rows * t // nsplit for t in range(nsplit + 1)]
+            with ThreadPoolExecutor(nsplit) as pool:
+                parts = list(pool.map(lambda t: _topk_rows(s[bounds[t]:bounds[t + 1]], kk), range(nsplit)))
+            for t, (i, d) in enumerate(parts):
+                idx[a + bounds[t]:a + bounds[t + 1], :kk] = i
+                dist[a + bounds[t]:a + bounds[t + 1], :kk] = d
     return idx, dist
 
 
