@@ -203,6 +203,13 @@ def timed_loop(torch, dist, world, fn, steps, warmup):
     return float(ms.item())
 
 
+def cpu_sample_images(w, seconds):
+    """How many images of the workload a ~`seconds` CPU sample holds, assuming ~0.4 TFLOP/s of host
+    GEMM + selection (one image at least, the ring's 8 batches at most)."""
+    per_img = 2.0 * w["S"] ** 2 * w["N"] * w["d"] * 1.6  # flop, with ~60 % on top for the top-k pass
+    return int(max(1, min(w["B"] * RING, seconds * 4e11 / per_img)))
+
+
 def cpu_reference_sample(w, bank, ring, n_img, repeats=1):
     """The oracle port of the reference path on the host cores, on `n_img` images of the workload's
     first validation batch against the FULL bank.  Returns (queries/s, seconds, threads)."""
@@ -214,9 +221,16 @@ def cpu_reference_sample(w, bank, ring, n_img, repeats=1):
     fm, lm = fm_t.cpu().numpy(), lm_t.cpu().numpy()
     del fm_t, lm_t
     S, d = w["S"], w["d"]
-    q, y = ring[0]
-    feats = q.view(w["B"], S * S, d)[:n_img].cpu().numpy()
-    yy = y[:n_img].cpu().numpy()
+    n_img = min(n_img, w["B"] * len(ring))
+    fl, yl, left = [], [], n_img
+    for q, y in ring:  # images are taken from as many of the ring's batches as needed
+        take = min(left, w["B"])
+        fl.append(q.view(w["B"], S * S, d)[:take].cpu().numpy())
+        yl.append(y[:take].cpu().numpy())
+        left -= take
+        if left == 0:
+            break
+    feats, yy = np.concatenate(fl), np.concatenate(yl)
     # score blocks of at most ~4 GB of host RAM: (images per block) * S*S * N * 4 B
     per_block = max(1, min(n_img, int(4e9 // (S * S * fm.shape[0] * 4))))
     batches = [(feats[i:i + per_block], yy[i:i + per_block]) for i in range(0, n_img, per_block)]
@@ -244,12 +258,13 @@ def parity_vs_oracle(ops, torch, w, bank, table, ring, n_img, ref):
 
     ref_miou, ref_conf, det = ref
     S, d, H, C = w["S"], w["d"], w["S"] * w["ps"], w["C"]
-    q, y = ring[0]
-    qs, ys = q[:n_img * S * S].contiguous(), y[:n_img].contiguous()
+    n_img = min(n_img, w["B"] * len(ring))
+    qs = torch.cat([q for q, _ in ring])[:n_img * S * S].contiguous()
+    ys = torch.cat([y for _, y in ring])[:n_img].contiguous()
     scores, idx, qn = bank.search(qs, K_NEIGH, K_PRIME)
     lh = ops.label_transfer(table, w["ps"] ** 2, scores, idx, qn, BETA)
     pred = ops.upsample_argmax(lh, n_img, S, H, H)
-    conf = torch.zeros((C, C), dtype=torch.int64, device=q.device)
+    conf = torch.zeros((C, C), dtype=torch.int64, device=qs.device)
     ops.confusion_accumulate(conf, ops.decode_mask(ys, False).view(n_img, H, H), pred, w["ignore"])
     miou = miou_from_confusion(conf.cpu().numpy())[0]
     ref_idx = np.concatenate(det["idx"])
@@ -312,7 +327,7 @@ def main():
     if args.impl == "reference":
         bank = build_bank(w, w["N"], device, seed=1)
         ring = make_query_ring(w, device, seed=2)
-        n_img = 1 if w["N"] >= 1_000_000 else 4
+        n_img = cpu_sample_images(w, seconds=1.5)  # per step
         qps_list = []
         for i in range(args.warmup + args.steps):
             qps, dt, threads, _ = cpu_reference_sample(w, bank, ring, n_img)
@@ -366,19 +381,41 @@ def main():
     ms_per_step = ms_total / args.steps
     value = world * Q / (ms_per_step * 1e-3)
 
-    # ---- e2e: host buffers in, host result out, copies inside the timed region
+    # ---- e2e: host buffers in, host result out, copies inside the timed region.  Every step copies its
+    # own inputs from pinned host memory and reads its result back; the copy of step i+1 is issued on a
+    # second stream while step i computes (double-buffered device inputs), as a serving loop would.
     host_ring = [(q.cpu().pin_memory(), y.cpu().pin_memory()) for q, y in ring]
-    q_dev, y_dev = torch.empty_like(ring[0][0]), torch.empty_like(ring[0][1])
+    dev_in = [(torch.empty_like(ring[0][0]), torch.empty_like(ring[0][1])) for _ in range(2)]
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device)
     conf_host = torch.zeros((w["C"], w["C"]), dtype=torch.int64).pin_memory()
+    issued = {"next": None}
+
+    def issue_copy(i):
+        b = i % 2
+        qh, yh = host_ring[i % RING]
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[b])
+            dev_in[b][0].copy_(qh, non_blocking=True)
+            dev_in[b][1].copy_(yh, non_blocking=True)
+            copied[b].record(copy_stream)
 
     def step_e2e(i):
-        qh, yh = host_ring[i % RING]
-        q_dev.copy_(qh, non_blocking=True)
-        y_dev.copy_(yh, non_blocking=True)
-        run_step(ops, bank, table, w, q_dev, y_dev, conf)
+        if issued["next"] != i:  # first step of a loop: nothing was prefetched
+            issue_copy(i)
+        issue_copy(i + 1)
+        issued["next"] = i + 1
+        b = i % 2
+        cur = torch.cuda.current_stream()
+        cur.wait_event(copied[b])
+        run_step(ops, bank, table, w, dev_in[b][0], dev_in[b][1], conf)
+        consumed[b].record(cur)
         conf_host.copy_(conf, non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the caller reads the step's result
+        cur.synchronize()  # the caller reads the step's result
 
+    for b in range(2):
+        consumed[b].record(torch.cuda.current_stream())
     ms_e2e = timed_loop(torch, dist, world, step_e2e, args.steps, warmup) / args.steps
     h2d = host_ring[0][0].numel() * 4 + host_ring[0][1].numel() * 4
     d2h = conf_host.numel() * 8
@@ -411,7 +448,7 @@ def main():
     cpu = None
     parity = None
     if world == 1 and not args.no_cpu_baseline:
-        n_img = 4 if w["N"] >= 1_000_000 else 16
+        n_img = cpu_sample_images(w, seconds=15.0)
         qps, dt, threads, ref = cpu_reference_sample(w, bank, ring, n_img)
         parity = parity_vs_oracle(ops, torch, w, bank, table, ring, n_img, ref)
         cpu = {"value": qps, "unit": "patch-queries/s", "cores": threads, "kind": "port",
