@@ -82,6 +82,16 @@ int hb_bank_append(hb_bank_t* bank, const float* feats_dev, const uint8_t* mask_
 int hb_bank_append_soft(hb_bank_t* bank, const float* feats_dev, const float* soft_dev,
                         int64_t n, int normalise, void* stream);
 
+/* Bounded-memory sampler (replaces _sample_features, hbird_eval.py:447-517): for each of the B
+ * images pick the K patches with the smallest score*U, score = sum over the classes present in the
+ * patch of the number of patches of the image containing that class (1e6 for an empty patch).
+ * mask_dev: uint8 (B, S*ps, S*ps) decoded class ids; uniform_dev: fp32 (B, S*S) = the reference's CPU
+ * RNG stream (torch.rand, image order) uploaded by the caller, so a seeded run picks the same
+ * patches; sel_out_dev: int32 (B, K) flat source rows b*S*S + patch, ascending score — ready to be
+ * passed to hb_bank_append as sel_dev. */
+int hb_sample_patches(const uint8_t* mask_dev, int B, int S, int ps, int C, const float* uniform_dev,
+                      int K, int32_t* sel_out_dev, void* stream);
+
 /* Freeze the bank (builds the TMA tensor map).  Must precede hb_search. */
 int hb_bank_finalize(hb_bank_t* bank);
 int64_t hb_bank_rows(const hb_bank_t* bank);

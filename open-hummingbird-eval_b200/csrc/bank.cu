@@ -100,6 +100,89 @@ __global__ void export_rows_kernel(const __nv_bfloat16* __restrict__ bf, const f
   }
 }
 
+// N1 — bounded-memory sampler (hbird_eval.py:447-517): one block per image.  For every patch: the set
+// of classes present (bitmap), then per image the number of patches containing each class, then
+// score = sum of those frequencies over the patch's classes, times the caller's U(0,1) draw (the
+// reference's CPU RNG stream, uploaded), 1e6 for an empty patch; the K smallest scores, ascending
+// (ties: lower patch index), are the picks.  Integer/float arithmetic is exact (small integers).
+constexpr int kSampleThreads = 256;
+constexpr int kSampleMaxPatches = 4096;
+
+__global__ void __launch_bounds__(kSampleThreads)
+sample_patches_kernel(const uint8_t* __restrict__ mask, int S, int ps, int C,
+                      const float* __restrict__ uniform, int K, int32_t* __restrict__ sel) {
+  extern __shared__ unsigned char s_raw[];
+  const int SS = S * S, W = S * ps;
+  int n2 = 1;
+  while (n2 < SS) n2 <<= 1;
+  uint32_t* present = reinterpret_cast<uint32_t*>(s_raw);           // SS * 8 words (256 class bits)
+  int* freq = reinterpret_cast<int*>(present + SS * 8);             // 256
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(freq + 256);  // n2
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < 256; c += blockDim.x) freq[c] = 0;
+  __syncthreads();
+  for (int p = threadIdx.x; p < SS; p += blockDim.x) {
+    uint32_t bits[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int py = p / S, px = p % S;
+    const uint8_t* base = mask + (static_cast<int64_t>(b) * W + py * ps) * W + px * ps;
+    for (int i = 0; i < ps; ++i)
+      for (int j = 0; j < ps; ++j) {
+        const int cls = base[i * W + j];
+        if (cls < C) bits[cls >> 5] |= 1u << (cls & 31);
+      }
+#pragma unroll
+    for (int wd = 0; wd < 8; ++wd) {
+      present[p * 8 + wd] = bits[wd];
+      uint32_t m = bits[wd];
+      while (m) {
+        const int bit = __ffs(m) - 1;
+        m &= m - 1;
+        atomicAdd(&freq[wd * 32 + bit], 1);
+      }
+    }
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < n2; p += blockDim.x) {
+    unsigned long long key = ~0ull;  // padding sorts last
+    if (p < SS) {
+      float score = 0.f;
+      bool any = false;
+#pragma unroll
+      for (int wd = 0; wd < 8; ++wd) {
+        uint32_t m = present[p * 8 + wd];
+        any |= m != 0;
+        while (m) {
+          const int bit = __ffs(m) - 1;
+          m &= m - 1;
+          score += static_cast<float>(freq[wd * 32 + bit]);
+        }
+      }
+      score = any ? __fmul_rn(score, uniform[static_cast<int64_t>(b) * SS + p]) : 1e6f;
+      key = (static_cast<unsigned long long>(f32_to_ordered(score)) << 32) | static_cast<uint32_t>(p);
+    }
+    keys[p] = key;
+  }
+  __syncthreads();
+  for (int k = 2; k <= n2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+        const int partner = i ^ j;
+        if (partner > i) {
+          const bool asc = (i & k) == 0;
+          const unsigned long long a = keys[i], c2 = keys[partner];
+          if ((a > c2) == asc) {
+            keys[i] = c2;
+            keys[partner] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int j = threadIdx.x; j < K; j += blockDim.x)
+    sel[static_cast<int64_t>(b) * K + j] = b * SS + static_cast<int32_t>(keys[j] & 0xffffffffu);
+}
+
 static int launch_pack(Bank* b, const float* feats, const uint8_t* mask, const float* soft,
                        const int32_t* sel, int64_t n, int S, int ps, int normalise,
                        cudaStream_t st) {
@@ -212,6 +295,23 @@ int hb_bank_append_soft(hb_bank_t* bank, const float* feats_dev, const float* so
   HB_REQUIRE(b->rows + n <= b->capacity, "hb_bank_append_soft: %lld + %lld rows exceed capacity %lld", (long long)b->rows, (long long)n, (long long)b->capacity);
   HB_CHECK_CUDA(cudaSetDevice(b->device));
   return hb::launch_pack(b, feats_dev, nullptr, soft_dev, nullptr, n, 1, 1, normalise, static_cast<cudaStream_t>(stream));
+}
+
+int hb_sample_patches(const uint8_t* mask_dev, int B, int S, int ps, int C, const float* uniform_dev,
+                      int K, int32_t* sel_out_dev, void* stream) {
+  HB_REQUIRE(B >= 0 && S >= 1 && ps >= 1 && C >= 1 && C <= 256, "hb_sample_patches: bad shape B=%d S=%d ps=%d C=%d", B, S, ps, C);
+  HB_REQUIRE(S * S <= hb::kSampleMaxPatches, "hb_sample_patches: S*S=%d exceeds %d patches per image", S * S, hb::kSampleMaxPatches);
+  HB_REQUIRE(K >= 1 && K <= S * S, "hb_sample_patches: K=%d not in [1, S*S=%d]", K, S * S);
+  if (B == 0) return HB_OK;
+  HB_REQUIRE(mask_dev && uniform_dev && sel_out_dev, "hb_sample_patches: NULL pointer");
+  int n2 = 1;
+  while (n2 < S * S) n2 <<= 1;
+  const size_t smem = static_cast<size_t>(S) * S * 32 + 256 * 4 + static_cast<size_t>(n2) * 8;
+  HB_CHECK_CUDA(cudaFuncSetAttribute(hb::sample_patches_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  hb::sample_patches_kernel<<<B, hb::kSampleThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      mask_dev, S, ps, C, uniform_dev, K, sel_out_dev);
+  HB_CHECK_CUDA(cudaGetLastError());
+  return HB_OK;
 }
 
 int hb_bank_finalize(hb_bank_t* bank) {

@@ -32,6 +32,7 @@ _SIGNATURES = [
     ("hb_bank_destroy", c_int, [c_void_p]),
     ("hb_bank_append", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int64, c_void_p]),
     ("hb_bank_append_soft", c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    ("hb_sample_patches", c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     ("hb_bank_finalize", c_int, [c_void_p]),
     ("hb_bank_rows", c_int64, [c_void_p]),
     ("hb_bank_capacity", c_int64, [c_void_p]),

@@ -142,27 +142,16 @@ class HbirdEvaluation:
 
     def _sample_patches(self, mask: torch.Tensor, S: int, ps: int, num_classes: int) -> torch.Tensor:
         """Bounded-memory sampler, hbird_eval.py:447-517: per image keep the K patches with the
-        smallest score*U(0,1), score = sum over the classes present in the patch of the number of
-        patches of the image containing that class.  U is drawn with the CPU generator in image
-        order exactly as the reference does, so a seeded run picks the same patches.
-        Returns int32 flat source rows (b*S*S + patch) on the device."""
+        smallest score*U(0,1) (hb_sample_patches).  U is drawn with the CPU generator, one value
+        per patch in image order exactly as the reference does (:497-508; every patch is non-empty
+        once 255 -> 0 is applied), and uploaded, so a seeded run picks the same patches.
+        Returns int32 flat source rows (b*S*S + patch) on the device, ascending score per image."""
         B = mask.shape[0]
         K = int(self.num_sampled_features)
-        patches = mask.view(B, S, ps, S, ps).permute(0, 1, 3, 2, 4).reshape(B, S * S, ps * ps).long()
-        presence = torch.zeros((B, S * S, num_classes), dtype=torch.bool, device=mask.device)
-        presence.scatter_(2, patches.clamp_max(num_classes - 1), True)
-        class_freq = presence.sum(dim=1).float()
-        scores = torch.einsum("bpc,bc->bp", presence.float(), class_freq).cpu()
-        nonzero = presence.any(dim=2).cpu()
-        scores.masked_fill_(~nonzero, 1e6)
-        total = int(nonzero.sum())
-        if total > 0:
-            noise = torch.ones_like(scores)
-            noise[nonzero] = torch.rand(total)  # row-major fill == per-image order of the reference
-            scores.mul_(noise)
-        _, picks = torch.topk(scores, K, largest=False)
-        flat = picks + torch.arange(B).unsqueeze(1) * (S * S)
-        return flat.reshape(-1).to(device=mask.device, dtype=torch.int32)
+        if K > S * S:
+            raise ValueError(f"memory_size asks for {K} patches per image but an image has only {S * S}")
+        uniform = torch.rand(B * S * S).to(mask.device, non_blocking=True)
+        return ops.sample_patches(mask, S, ps, num_classes, uniform, K)
 
     def _save_memory(self) -> None:
         """hbird_eval.py:371-378 — same on-disk format: fp32 (N,d) and (N,C) tensors."""

@@ -174,6 +174,20 @@ class MemoryBank:
         return out
 
 
+def sample_patches(mask_u8: torch.Tensor, S: int, ps: int, num_classes: int, uniform: torch.Tensor, K: int) -> torch.Tensor:
+    """N1: bounded-memory sampler (hbird_eval.py:447-517).  mask_u8 uint8 (B, S*ps, S*ps); uniform fp32
+    (B, S*S) U(0,1) draws.  Returns int32 (B*K,) flat source rows for MemoryBank.append(sel=...)."""
+    mask_u8 = _require_cuda(mask_u8, "mask", torch.uint8)
+    uniform = _require_cuda(uniform, "uniform", torch.float32)
+    B = mask_u8.shape[0]
+    if uniform.numel() != B * S * S:
+        raise ValueError(f"uniform must hold B*S*S = {B * S * S} draws, got {uniform.numel()}")
+    sel = torch.empty((B * K,), dtype=torch.int32, device=mask_u8.device)
+    check(lib.hb_sample_patches(ptr(mask_u8), B, S, ps, int(num_classes), ptr(uniform), int(K), ptr(sel),
+                                stream_ptr(mask_u8.device)))
+    return sel
+
+
 def merge_topk(shard_scores: torch.Tensor, shard_idx: torch.Tensor):
     """K3: (G, Q, k) gathered per-shard results -> (Q, k) global top-k."""
     shard_scores = _require_cuda(shard_scores, "shard_scores", torch.float32)

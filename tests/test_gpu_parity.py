@@ -391,6 +391,34 @@ def test_engine_augmentation_epochs_duplicate_rows_tie_handling():
     assert abs(miou - ref_miou) <= 5e-4
 
 
+@pytest.mark.parametrize("name", CASES)
+def test_sampler_kernel_picks_the_reference_rows_in_order(name):
+    """hb_sample_patches with the reference's CPU RNG stream (torch.manual_seed(123)) selects, image by
+    image and in the same order, the patches whose features the reference's bounded bank holds; it
+    also agrees with the oracle sampler on raw indices."""
+    cfg, g = load_golden(name + "_bounded")
+    data = SyntheticSegmentationData(**cfg)
+    K = max(1, int(g["memory_size"]) // data.get_train_dataset_size())
+    torch.manual_seed(123)
+    row = 0
+    for (x, y) in data.train_dataloader():
+        B = x.shape[0]
+        ids = O.decode_mask(y.numpy(), True)
+        u = torch.rand(B * data.S * data.S)
+        sel = ops.sample_patches(cuda(ids[:, 0].astype(np.uint8)), data.S, data.ps, data.C, u.to(DEV), K).cpu().long()
+        ref_sel = O.sample_patches(O.patchify_gt(ids, data.ps), data.C, K, u.numpy())
+        flat_ref = (ref_sel + np.arange(B)[:, None] * data.S * data.S).reshape(-1)
+        np.testing.assert_array_equal(sel.numpy(), flat_ref)
+        feats = data.ftr_extr_fn(data.model, x)[0].flatten(0, 1).cpu()[sel].numpy()
+        mine = O.normalise_rows(feats)
+        ref = g["feature_memory"][row:row + mine.shape[0]]
+        row += mine.shape[0]
+        for b in range(B):  # same set per image (the reference's topk may order exact ties differently)
+            dist = np.abs(mine[b * K:(b + 1) * K, None] - ref[None, b * K:(b + 1) * K]).max(axis=2)
+            assert (dist.min(axis=1) <= 1e-6).all() and (dist.min(axis=0) <= 1e-6).all()
+    assert row == g["feature_memory"].shape[0]
+
+
 def test_hbird_evaluation_entry_point():
     cfg, g = load_golden("voc_tiny")
     data = SyntheticSegmentationData(**cfg)

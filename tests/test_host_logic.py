@@ -12,7 +12,6 @@ import torch
 from helpers import GOLDEN, load_golden
 from hbird_b200 import _capi
 from hbird_b200.data import SyntheticSegmentationData
-from hbird_b200.hbird_eval import HbirdEvaluation
 from hbird_b200.registry import NN_BACKENDS, create_nn_backend, register_nn_backend
 from hbird_b200.utils.eval_metrics import miou_from_confusion
 from oracle import hbird_oracle as O
@@ -47,32 +46,6 @@ def test_registry_dispatch_and_errors():
     register_nn_backend("dummy", lambda fm, n_neighbors=30, **kw: ("dummy", n_neighbors, kw))
     assert create_nn_backend("dummy", None, n_neighbors=7, a=1) == ("dummy", 7, {"a": 1})
     NN_BACKENDS.pop("dummy")
-
-
-@pytest.mark.parametrize("name", ["voc_tiny", "ade_tiny"])
-def test_bounded_sampler_host_logic_picks_the_reference_rows(name):
-    """HbirdEvaluation._sample_patches (torch host code + CPU RNG) selects, per image, exactly the
-    patches whose features the reference's bounded bank holds."""
-    cfg, g = load_golden(name + "_bounded")
-    data = SyntheticSegmentationData(**cfg)
-    ms = int(np.load(os.path.join(GOLDEN, f"ref_{name}_bounded.npz"))["memory_size"])
-    K = max(1, ms // data.get_train_dataset_size())
-    stub = HbirdEvaluation.__new__(HbirdEvaluation)
-    stub.num_sampled_features = K
-    torch.manual_seed(123)
-    row = 0
-    for (x, y) in data.train_dataloader():
-        ids = torch.from_numpy(O.decode_mask(y.numpy(), True)).to(torch.uint8)[:, 0]
-        sel = stub._sample_patches(ids, data.S, data.ps, data.C).long()
-        feats = data.ftr_extr_fn(data.model, x)[0].flatten(0, 1)[sel].numpy()
-        mine = O.normalise_rows(feats)
-        ref = g["feature_memory"][row:row + mine.shape[0]]
-        row += mine.shape[0]
-        B = x.shape[0]
-        for b in range(B):
-            dist = np.abs(mine[b * K:(b + 1) * K, None] - ref[None, b * K:(b + 1) * K]).max(axis=2)
-            assert (dist.min(axis=1) <= 1e-6).all()
-    assert row == g["feature_memory"].shape[0]
 
 
 def _plan(rows, Q, cg, sms=148, max_chunks=0):
