@@ -67,7 +67,8 @@ struct SearchParams {
   int prefetch_tiles;  // > 0: L2-prefetch bank tiles this many tiles ahead (split over the CTAs)
   uint32_t* pace;      // (rounds, pace_groups) arrival counters of the L2 pacing window (NULL = off)
   int pace_groups;     // counters per round
-  int ablate;          // measurement only: 1 = release accumulators unread, 2 = scan but never insert
+  int ablate;          // measurement only (selects an ablated kernel build): 1 = release accumulators
+                       // unread, 2 = scan but never insert
 };
 
 template <int CG, int STAGES, int KP>
@@ -373,7 +374,7 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         const uint32_t tacc = tmem_lane + static_cast<uint32_t>(abuf * BN);
 #pragma unroll 1
         for (int c0 = 0; c0 < BN / 2; c0 += kChunk) {
-          if (c0 >= nvalid || p.ablate == 1) break;  // warp-uniform
+          if (c0 >= nvalid || MODE == 3) break;  // warp-uniform
           uint32_t v[kChunk];
           if (MODE == 2) t_a = clock64();
           ptx::tmem_ld_chunk(tacc + c0, v);
@@ -403,7 +404,7 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
 #pragma unroll
           for (int g = 0; g < kGroups; ++g) gmask |= (mg[g] > tau ? 1u : 0u) << g;
           uint32_t hot = __reduce_or_sync(0xffffffffu, gmask);  // groups in which some lane has a survivor
-          if (p.ablate == 2) hot = 0;
+          if (MODE == 4) hot = 0;
           if (hot == 0) {
             if (last_chunk) release_accumulator();
           } else {
@@ -455,7 +456,7 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             if (MODE == 2) st_slow += clock64() - t_a;
           }
         }
-        if (nvalid == 0 || p.ablate == 1) release_accumulator();  // nothing was read
+        if (nvalid == 0 || MODE == 3) release_accumulator();  // nothing was read
         // routine folds happen here, after the accumulator was released, and only when some lane's
         // queue is nearly full: a fold costs ~1.5k cycles of this warp, and the MMA of the tile after
         // next waits for the slowest of all epilogue warps, so folds must be rare
@@ -572,6 +573,10 @@ static int dispatch_search(const Bank* b, int cg, int kp, const CUtensorMap& tma
     if (cg == 2) return launch_search<2, 5, 64, 1>(b, tmap_q, p, st, probe, n_clusters);
     return launch_search<1, 3, 64, 1>(b, tmap_q, p, st, probe, n_clusters);
   }
+  if (p.ablate == 1) return cg == 2 ? launch_search<2, 5, 64, 3>(b, tmap_q, p, st, probe, n_clusters)
+                                    : launch_search<1, 3, 64, 3>(b, tmap_q, p, st, probe, n_clusters);
+  if (p.ablate == 2) return cg == 2 ? launch_search<2, 5, 64, 4>(b, tmap_q, p, st, probe, n_clusters)
+                                    : launch_search<1, 3, 64, 4>(b, tmap_q, p, st, probe, n_clusters);
   if (p.stats != nullptr) {  // instrumented build: per-warp cycle counters of the epilogue
     if (cg == 2) return launch_search<2, 5, 64, 2>(b, tmap_q, p, st, probe, n_clusters);
     return launch_search<1, 3, 64, 2>(b, tmap_q, p, st, probe, n_clusters);
@@ -609,15 +614,25 @@ static int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_
   const size_t off_cand = align_up(off_norm + sizeof(float) * static_cast<size_t>(Q), 256);
   const size_t off_seed = align_up(off_cand + sizeof(uint64_t) * static_cast<size_t>(plan.n_chunks) * q_pad * kp, 256);
   int n_units_used = 1;
-  {
+  const int variant = dump ? 1 : (b->cfg_ablate ? 2 + b->cfg_ablate : (b->cfg_stats ? 2 : 0));
+  int& cached_fit = b->fit_cache[cg - 1][kp == 64 ? 1 : 0][variant];
+  const int want_units = std::max(1, std::min(b->num_sms / cg, plan.n_qblocks * plan.n_chunks));
+  if (cached_fit > 0) {
+    n_units_used = std::min(want_units, cached_fit);
+  } else {
     SearchParams probe_p{};
     probe_p.n_qblocks = plan.n_qblocks;
     probe_p.n_chunks = plan.n_chunks;
     probe_p.dump = dump;
     probe_p.stats = b->cfg_stats;
+    probe_p.ablate = b->cfg_ablate;
     CUtensorMap unused{};
-    int rc0 = dispatch_search(b, cg, kp, unused, probe_p, st, &n_units_used, 0);
+    // probe with a grid that wants every SM, so the cached answer is the device's capacity
+    probe_p.n_qblocks = b->num_sms;
+    probe_p.n_chunks = 1;
+    int rc0 = dispatch_search(b, cg, kp, unused, probe_p, st, &cached_fit, 0);
     if (rc0 != HB_OK) return rc0;
+    n_units_used = std::min(want_units, cached_fit);
   }
   const int n_rounds = (plan.n_qblocks * plan.n_chunks + n_units_used - 1) / n_units_used;
   const int pace_groups = (plan.n_tiles / plan.n_chunks + 1) / kPaceTiles + 2;
