@@ -369,6 +369,23 @@ def test_engine_ade_shaped_151_classes_vs_oracle():
     assert ev.last_confusion[0].sum() == 0  # ignored gt class contributes no pixels
 
 
+def test_engine_cfg3_geometry_vs_oracle():
+    """BASELINE configs[2] geometry (DINOv2 ViT-B/14 at 518 px: S = 37, ps = 14 so soft labels are
+    counts/196, d = 768) on a small bank: bank rows, confusion matrix and mIoU against the oracle."""
+    data = SyntheticSegmentationData(num_train=10, num_val=2, input_size=518, patch_size=14, d_model=768,
+                                     num_classes=21, batch_size=4, ignore_index=255, cells=8, seed=7)
+    ev = run_engine(data)
+    assert ev.bank.rows == 10 * 37 * 37
+    miou = ev.evaluate(data.val_dataloader(), data.S, ignore_index=255)
+    fm, lm = O.build_memory(batches_np_cpu(data, data.train_dataloader()), data.C, data.S)
+    np.testing.assert_allclose(ev.feature_memory.numpy(), fm, atol=2e-7, rtol=0)
+    np.testing.assert_array_equal(ev.label_memory.numpy(), lm)
+    ref_miou, ref_conf = O.evaluate(fm, lm, batches_np_cpu(data, data.val_dataloader()), data.C, data.S, 30, 255)
+    assert abs(miou - ref_miou) <= 5e-4
+    assert ev.last_confusion.sum() == ref_conf.sum()
+    assert np.abs(ev.last_confusion - ref_conf).sum() <= 5e-4 * ref_conf.sum()
+
+
 def test_engine_augmentation_epochs_duplicate_rows_tie_handling():
     """augmentation_epoch=2 over a deterministic loader stores every patch twice: top-k
     membership among exact ties is ambiguous, the score multiset and the mIoU are not."""
