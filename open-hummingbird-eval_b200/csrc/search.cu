@@ -11,8 +11,9 @@
 //               256-column TMEM accumulators; tcgen05.commit frees ring slots and publishes finished
 //               accumulators.  Also owns TMEM alloc/dealloc.  Both issue warps stay converged and
 //               issue under elect.sync so that descriptors live in uniform registers.
-//   warps 0..7  epilogue: each thread owns ONE query row (TMEM lane) and one 128-column half of the
-//               tile and keeps its k'/2 best candidates as a sorted list (scores in registers, bank
+//   warps 0..7  epilogue: each thread owns ONE query row (TMEM lane) and every other 32-column chunk
+//               of the tile (two interleaved column sets, so runs of consecutive bank rows -- the
+//               patches of one training image -- are shared out between the two lists) and keeps its k'/2 best candidates as a sorted list (scores in registers, bank
 //               rows in shared memory).  Per 32 columns: tcgen05.ld, max-trees over groups of 8, one
 //               warp-wide OR against tau = the list's last score.  Survivors (rare) go to a 16-entry
 //               per-thread queue in shared memory with independent predicated stores; when some
@@ -315,11 +316,11 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
     constexpr int KL = KP / 2;                    // list length per (row, column half)
     constexpr int QC = kQueueCap;
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
-    const int half = warp >> 2;                   // which 128 columns of the tile
+    const int half = warp >> 2;                   // column set: 32-column chunks half, half+2, half+4, half+6
     const int row_in_tile = quarter * 32 + lane;  // query row owned by this thread
     uint2* queue = reinterpret_cast<uint2*>(smem + L::kRingBytes) + threadIdx.x;  // entry j at [j*kEpiThreads]
     uint32_t* rows = reinterpret_cast<uint32_t*>(smem + L::kRingBytes + L::kQueueBytes) + threadIdx.x;
-    const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + half * (BN / 2);
+    const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const uint32_t tempty_leader0 = (CG == 2) ? ptx::mapa(tempty_bar(0), 0) : tempty_bar(0);
     const uint32_t tempty_leader1 = (CG == 2) ? ptx::mapa(tempty_bar(1), 0) : tempty_bar(1);
     int abuf = 0;
@@ -368,19 +369,20 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
           tau = fmaxf(tau, seed);
           seed_bits = __ldcg(seed_ptr);
         }
-        const int64_t col_base = static_cast<int64_t>(tile) * BN + half * (BN / 2);
+        const int64_t col_base = static_cast<int64_t>(tile) * BN;
         const int64_t rem = p.n_rows - col_base;
-        const int nvalid = rem >= BN / 2 ? BN / 2 : (rem > 0 ? static_cast<int>(rem) : 0);
+        const int nvalid = rem >= BN ? BN : static_cast<int>(rem);  // valid columns of this tile (>= 1)
         const uint32_t tacc = tmem_lane + static_cast<uint32_t>(abuf * BN);
+        const int c_first = half * kChunk;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN / 2; c0 += kChunk) {
+        for (int c0 = c_first; c0 < BN; c0 += 2 * kChunk) {  // this warp's interleaved column set
           if (c0 >= nvalid || MODE == 3) break;  // warp-uniform
           uint32_t v[kChunk];
           if (MODE == 2) t_a = clock64();
           ptx::tmem_ld_chunk(tacc + c0, v);
           ptx::tmem_ld_wait();
           if (MODE == 2) st_load += clock64() - t_a;
-          const bool last_chunk = c0 + kChunk >= nvalid;
+          const bool last_chunk = c0 + 2 * kChunk >= nvalid || c0 + 2 * kChunk >= BN;  // no further chunk of this set
           if (MODE == 1 && q_row < p.n_queries) {
 #pragma unroll
             for (int j = 0; j < kChunk; ++j)
@@ -456,7 +458,7 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             if (MODE == 2) st_slow += clock64() - t_a;
           }
         }
-        if (nvalid == 0 || MODE == 3) release_accumulator();  // nothing was read
+        if (c_first >= nvalid || MODE == 3) release_accumulator();  // nothing was read
         // routine folds happen here, after the accumulator was released, and only when some lane's
         // queue is nearly full: a fold costs ~1.5k cycles of this warp, and the MMA of the tile after
         // next waits for the slowest of all epilogue warps, so folds must be rare
@@ -483,7 +485,7 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         atomicAdd(o + 5, static_cast<unsigned long long>(st_nfold));
         atomicAdd(o + 6, static_cast<unsigned long long>(st_tiles));
       }
-      // emit this item's candidates (k'/2 per column half; the re-rank kernel merges them)
+      // emit this item's candidates (k'/2 per column set; the re-rank kernel merges them)
       const int64_t q_pad = static_cast<int64_t>(p.n_qblocks) * BM * CG;
       uint64_t* out = p.cand + (static_cast<int64_t>(chunk) * q_pad + q_row) * KP + half * KL;
 #pragma unroll

@@ -183,6 +183,28 @@ def test_search_vs_oracle_seeded(N, d, Q, kp):
     bank.close()
 
 
+def test_search_recall_when_neighbours_are_consecutive_bank_rows():
+    """Patches of one training image are consecutive bank rows and look alike, so a query's whole
+    neighbourhood can sit in one run of rows.  48 near-duplicates per query are planted as a
+    consecutive run at a 256-row tile boundary; all of the exact top-30 must still be found."""
+    g = torch.Generator().manual_seed(21)
+    N, d, Q, run = 65536, 384, 256, 48
+    rows = torch.randn((N, d), generator=g)
+    protos = torch.randn((Q, d), generator=g)
+    protos = protos / protos.norm(dim=1, keepdim=True)
+    for qi in range(Q):
+        start = 256 * (qi % (N // 256))  # run starts exactly at a tile boundary
+        rows[start:start + run] = protos[qi] * 6.0 + 0.35 * torch.randn((run, d), generator=g)
+    q = protos * 3.3 + 0.02 * torch.randn((Q, d), generator=g)
+    bank = bank_from_rows(rows.to(DEV))
+    fb, _ = bank.export()
+    for cg in (1, 2):
+        bank.configure_search(cta_group=cg)
+        s, i, _ = bank.search(q.to(DEV), 30, 64)
+        check_search(s, i, q.numpy(), fb.cpu().numpy(), min_recall=0.9995)
+    bank.close()
+
+
 def test_search_pads_like_faiss_when_bank_smaller_than_k():
     rows = torch.eye(8, 64)
     bank = bank_from_rows(rows.to(DEV))
