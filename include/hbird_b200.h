@@ -109,7 +109,7 @@ int hb_bank_export(const hb_bank_t* bank, int64_t row0, int64_t n, float* feats_
  * Replaces NearestNeighborSearchFaiss.find_nearest_neighbors (search_faiss.py:83-90),
  * i.e. GpuIndexFlatIP.search: exact top-k by inner product of the raw (un-normalised)
  * queries against the unit-norm bank rows, sorted by descending score.
- * q_dev: fp32 (Q, d).  k <= k_prime, k_prime in {32, 64}: the tcgen05 bf16 pass keeps
+ * q_dev: fp32 (Q, d).  k <= k_prime, k_prime in {32, 64, 128}: the tcgen05 bf16 pass keeps
  * k_prime candidates per query, the fp32 pass re-scores them exactly and keeps k.
  * out_scores_dev fp32 (Q, k); out_idx_dev int64 (Q, k) = row index + idx_offset (the
  * shard's first global row); out_qnorm_dev fp32 (Q,) = ||q||_2 or NULL.  If the bank

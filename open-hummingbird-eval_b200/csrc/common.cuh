@@ -59,7 +59,7 @@ struct Bank {
   unsigned long long* cfg_stats = nullptr;  // instrumented-build counters (hb_search_stats)
   bool cfg_pace = true;         // L2 pacing window of the search kernel
   int last_launches = 0;
-  int fit_cache[2][2][5] = {};  // co-resident clusters per (cta_group, k', kernel variant); 0 = unknown
+  int fit_cache[2][3][5] = {};  // co-resident clusters per (cta_group, k', kernel variant); 0 = unknown
   // optional kernel timing (hb_search_timing)
   bool timing = false;
   int timing_count = 0;

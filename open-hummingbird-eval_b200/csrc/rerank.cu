@@ -148,6 +148,7 @@ int rerank_launch(const Bank* b, const float* q, const float* qnorm_ws, int64_t 
                                            b->d, b->dpad, k, idx_offset, out_scores, out_idx)
   if (kp == 32) HB_RERANK(1);
   else if (kp == 64) HB_RERANK(2);
+  else if (kp == 128) HB_RERANK(4);
   else {
     set_error("rerank: k_prime=%d not in {32, 64, 128}", kp);
     return HB_ERR_INVALID;

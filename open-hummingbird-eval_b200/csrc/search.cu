@@ -586,11 +586,13 @@ static int dispatch_search(const Bank* b, int cg, int kp, const CUtensorMap& tma
   if (cg == 2) {
     if (kp == 32) return launch_search<2, 5, 32>(b, tmap_q, p, st, probe, n_clusters);
     if (kp == 64) return launch_search<2, 5, 64>(b, tmap_q, p, st, probe, n_clusters);
+    if (kp == 128) return launch_search<2, 4, 128>(b, tmap_q, p, st, probe, n_clusters);
   } else {
     if (kp == 32) return launch_search<1, 3, 32>(b, tmap_q, p, st, probe, n_clusters);
     if (kp == 64) return launch_search<1, 3, 64>(b, tmap_q, p, st, probe, n_clusters);
+    if (kp == 128) return launch_search<1, 2, 128>(b, tmap_q, p, st, probe, n_clusters);
   }
-  set_error("hb_search: k_prime=%d not in {32, 64}", kp);
+  set_error("hb_search: k_prime=%d not in {32, 64, 128}", kp);
   return HB_ERR_INVALID;
 }
 
@@ -617,7 +619,7 @@ static int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_
   const size_t off_seed = align_up(off_cand + sizeof(uint64_t) * static_cast<size_t>(plan.n_chunks) * q_pad * kp, 256);
   int n_units_used = 1;
   const int variant = dump ? 1 : (b->cfg_ablate ? 2 + b->cfg_ablate : (b->cfg_stats ? 2 : 0));
-  int& cached_fit = b->fit_cache[cg - 1][kp == 64 ? 1 : 0][variant];
+  int& cached_fit = b->fit_cache[cg - 1][kp == 128 ? 2 : (kp == 64 ? 1 : 0)][variant];
   const int want_units = std::max(1, std::min(b->num_sms / cg, plan.n_qblocks * plan.n_chunks));
   if (cached_fit > 0) {
     n_units_used = std::min(want_units, cached_fit);
@@ -709,7 +711,7 @@ int hb_search(hb_bank_t* bank, const float* q_dev, int64_t Q, int k, int k_prime
   }
   HB_REQUIRE(Q >= 0 && Q < (int64_t(1) << 31), "hb_search: Q=%lld out of range", (long long)Q);
   HB_REQUIRE(k >= 1 && k <= k_prime, "hb_search: need 1 <= k (%d) <= k_prime (%d)", k, k_prime);
-  HB_REQUIRE(k_prime == 32 || k_prime == 64, "hb_search: k_prime=%d not in {32, 64}", k_prime);
+  HB_REQUIRE(k_prime == 32 || k_prime == 64 || k_prime == 128, "hb_search: k_prime=%d not in {32, 64, 128}", k_prime);
   if (Q == 0) return HB_OK;
   HB_REQUIRE(q_dev && out_scores_dev && out_idx_dev, "hb_search: NULL pointer");
   HB_REQUIRE(b->rows >= 1, "hb_search: the bank is empty");

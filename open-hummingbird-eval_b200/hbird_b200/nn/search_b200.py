@@ -49,8 +49,8 @@ class NearestNeighborSearchB200(NearestNeighborSearchBase):
         self.gpu_id = int(gpu_ids[0])
         ops.device_check(self.gpu_id)
         self.k_prime = max(int(k_prime), 32)
-        if self.k_prime not in (32, 64) or self.n_neighbors > self.k_prime:
-            raise ValueError(f"k_prime={k_prime} must be 32 or 64 and >= n_neighbors={n_neighbors}")
+        if self.k_prime not in (32, 64, 128) or self.n_neighbors > self.k_prime:
+            raise ValueError(f"k_prime={k_prime} must be 32, 64 or 128 and >= n_neighbors={n_neighbors}")
         self.idx_offset = int(idx_offset)
         self.keep_f32 = bool(keep_f32)
         self._label_memory = label_memory

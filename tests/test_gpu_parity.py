@@ -170,7 +170,7 @@ def test_search_matches_reference_golden(case):
 
 
 @pytest.mark.parametrize("N,d,Q,kp", [(102400, 384, 1536, 64), (5000, 384, 1000, 64), (40000, 768, 300, 32),
-                                      (257, 64, 129, 64), (2049, 1024, 1, 64), (70000, 200, 333, 64)])
+                                      (257, 64, 129, 64), (2049, 1024, 1, 64), (70000, 200, 333, 64), (30000, 384, 500, 128)])
 def test_search_vs_oracle_seeded(N, d, Q, kp):
     g = torch.Generator().manual_seed(N + d)
     rows = torch.randn((N, d), generator=g)
@@ -222,7 +222,7 @@ def test_search_argument_errors_and_empty_query():
     with pytest.raises(ValueError):
         bank.search(torch.zeros((2, 32), device=DEV))  # wrong d
     with pytest.raises(ValueError):
-        bank.search(torch.zeros((2, 64), device=DEV), 30, 48)  # k_prime not in {32, 64}
+        bank.search(torch.zeros((2, 64), device=DEV), 30, 48)  # k_prime not in {32, 64, 128}
     with pytest.raises(ValueError):
         bank.search(torch.zeros((2, 64), device=DEV), 65, 64)  # k > k_prime
     with pytest.raises(RuntimeError):

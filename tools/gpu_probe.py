@@ -162,7 +162,7 @@ def perf(res):
     peak = peaks.get("bf16_tflops_sustained", 1425.8)
     shapes = [("cfg1", 12544, 102400, 384), ("cfg2", 12544, 1024000, 384),
               ("cfg3_shard8", 21904, 1280000, 768), ("d768_1M", 21904, 1024000, 768)]
-    variants = [(1, -1, 0, 64), (2, -1, 0, 64), (1, -1, 2, 64), (2, -1, 2, 64), (2, -1, 1, 64), (1, -1, 0, 32), (2, -1, 0, 32)]
+    variants = [(1, -1, 0, 64), (2, -1, 0, 64), (1, -1, 2, 64), (2, -1, 2, 64), (2, -1, 1, 64), (2, -1, 0, 32), (2, -1, 0, 128)]
     if os.environ.get("PROBE_SHAPES"):
         shapes = [s for s in shapes if s[0] in os.environ["PROBE_SHAPES"].split(",")]
     for (name, Q, N, d) in shapes:
