@@ -42,7 +42,8 @@ typedef enum hb_status {
 
 /* hb_bank_create flags */
 #define HB_BANK_KEEP_F32 1u   /* keep an fp32 copy of the normalised rows for the exact re-rank */
-#define HB_BANK_L2 2u         /* reserved: L2 metric (search_faiss.py:45-46), not implemented   */
+#define HB_BANK_L2 2u         /* squared-L2 metric (GpuIndexFlatL2, search_faiss.py:45-46): hb_search
+                                 returns ||q-x||^2 ascending; rows are NOT expected to be unit-norm  */
 
 typedef struct hb_bank hb_bank_t; /* opaque: one HBM-resident shard of the memory bank */
 

@@ -15,7 +15,7 @@ template <int LABEL_MODE>
 __global__ void __launch_bounds__(kPackWarps * 32)
 pack_rows_kernel(const float* __restrict__ feats, const uint8_t* __restrict__ mask,
                  const float* __restrict__ soft, const int32_t* __restrict__ sel, int64_t n,
-                 int d, int dpad, int C, int S, int ps, int pp, int normalise,
+                 int d, int dpad, int C, int S, int ps, int pp, int normalise, int l2,
                  __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32,
                  uint16_t* __restrict__ out_hist) {
   extern __shared__ uint32_t s_hist[];  // kPackWarps * C
@@ -39,9 +39,11 @@ pack_rows_kernel(const float* __restrict__ feats, const uint8_t* __restrict__ ma
     const float nrm = normalise ? sqrtf(ss) : 1.0f;
     __nv_bfloat16* ob = out_bf16 + row * dpad;
     float4* of = out_f32 ? reinterpret_cast<float4*>(out_f32 + row * d) : nullptr;
+    float ss_out = 0.f;  // ||stored row||^2, only needed by the L2 metric
     for (int i = lane; i < d4; i += 32) {
       float4 v = __ldg(in4 + i);  // second read hits L1/L2
       v.x /= nrm; v.y /= nrm; v.z /= nrm; v.w /= nrm;
+      ss_out += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
       if (of) of[i] = v;
       __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
       __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
@@ -51,6 +53,21 @@ pack_rows_kernel(const float* __restrict__ feats, const uint8_t* __restrict__ ma
       *reinterpret_cast<uint2*>(ob + 4 * i) = pk;
     }
     for (int i = d + lane; i < dpad; i += 32) ob[i] = __float2bfloat16(0.f);
+    if (l2) {
+      // L2 metric (search_faiss.py:45-46): ||q-x||^2 = ||q||^2 - 2 (q.x - ||x||^2/2).  The tensor
+      // pass ranks by q.x - ||x||^2/2: three extra bank columns carry -||x||^2/2 split into
+      // bf16 hi/mid/lo parts (~24 bits), the query carries 1.0 in the same columns.
+      ss_out = warp_sum(ss_out);
+      __syncwarp();
+      if (lane == 0) {
+        const float h = -0.5f * ss_out;
+        const __nv_bfloat16 h0 = __float2bfloat16(h);
+        const float r1 = h - __bfloat162float(h0);
+        const __nv_bfloat16 h1 = __float2bfloat16(r1);
+        const __nv_bfloat16 h2 = __float2bfloat16(r1 - __bfloat162float(h1));
+        ob[d] = h0; ob[d + 1] = h1; ob[d + 2] = h2;
+      }
+    }
 
     // ---- label record: per-patch class histogram ----
     if (LABEL_MODE == 0) {
@@ -197,10 +214,10 @@ static int launch_pack(Bank* b, const float* feats, const uint8_t* mask, const f
   uint16_t* oh = b->label_hist + row0 * b->C;
   if (mask) {
     pack_rows_kernel<0><<<static_cast<unsigned>(blocks), kPackWarps * 32, smem, st>>>(
-        feats, mask, nullptr, sel, n, b->d, b->dpad, b->C, S, ps, b->pp, normalise, ob, of, oh);
+        feats, mask, nullptr, sel, n, b->d, b->dpad, b->C, S, ps, b->pp, normalise, (b->flags & HB_BANK_L2) ? 1 : 0, ob, of, oh);
   } else {
     pack_rows_kernel<1><<<static_cast<unsigned>(blocks), kPackWarps * 32, smem, st>>>(
-        feats, nullptr, soft, sel, n, b->d, b->dpad, b->C, S, ps, b->pp, normalise, ob, of, oh);
+        feats, nullptr, soft, sel, n, b->d, b->dpad, b->C, S, ps, b->pp, normalise, (b->flags & HB_BANK_L2) ? 1 : 0, ob, of, oh);
   }
   HB_CHECK_CUDA(cudaGetLastError());
   b->rows += n;
@@ -224,13 +241,12 @@ int hb_bank_create(int device, int d, int num_classes, int patch_pixels, int64_t
   HB_REQUIRE(num_classes >= 1 && num_classes <= 256, "hb_bank_create: num_classes=%d not in [1, 256]", num_classes);
   HB_REQUIRE(patch_pixels >= 1 && patch_pixels <= 65535, "hb_bank_create: patch_pixels=%d not in [1, 65535]", patch_pixels);
   HB_REQUIRE(capacity_rows >= 1 && capacity_rows < (int64_t(1) << 31), "hb_bank_create: capacity_rows=%lld not in [1, 2^31)", (long long)capacity_rows);
-  HB_REQUIRE((flags & HB_BANK_L2) == 0, "hb_bank_create: only the dot_product metric is implemented (Unsupported distance measure)");
   HB_CHECK_CUDA(cudaSetDevice(device));
   Bank* b = new Bank();
   b->device = device;
   b->num_sms = num_sms;
   b->d = d;
-  b->dpad = (d + 63) / 64 * 64;
+  b->dpad = (d + ((flags & HB_BANK_L2) ? 3 : 0) + 63) / 64 * 64;  // L2: + 3 norm columns
   b->C = num_classes;
   b->pp = patch_pixels;
   b->flags = flags;

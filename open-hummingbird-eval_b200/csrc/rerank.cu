@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(128)
 rerank_kernel(const float* __restrict__ q, const float* __restrict__ bank_f32,
               const __nv_bfloat16* __restrict__ bank_bf16, const uint64_t* __restrict__ cand,
               int n_chunks, int64_t q_pad, int64_t Q, int d, int dpad, int k, int64_t idx_offset,
-              float* __restrict__ out_scores, int64_t* __restrict__ out_idx) {
+              int l2, float* __restrict__ out_scores, int64_t* __restrict__ out_idx) {
   constexpr int KP = 32 * R;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t qi = static_cast<int64_t>(blockIdx.x) * 4 + warp;
@@ -102,7 +102,12 @@ rerank_kernel(const float* __restrict__ q, const float* __restrict__ bank_f32,
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const float4 m = __ldg(reinterpret_cast<const float4*>(bank_f32 + static_cast<int64_t>(rows[u]) * d) + i);
-            acc[u] += qv.x * m.x + qv.y * m.y + qv.z * m.z + qv.w * m.w;
+            if (l2) {
+              const float a = qv.x - m.x, b2 = qv.y - m.y, c = qv.z - m.z, e = qv.w - m.w;
+              acc[u] -= a * a + b2 * b2 + c * c + e * e;  // -||q-x||^2: larger is nearer
+            } else {
+              acc[u] += qv.x * m.x + qv.y * m.y + qv.z * m.z + qv.w * m.w;
+            }
           }
         }
       } else {
@@ -113,7 +118,13 @@ rerank_kernel(const float* __restrict__ q, const float* __restrict__ bank_f32,
             const uint2 pk = __ldg(reinterpret_cast<const uint2*>(bank_bf16 + static_cast<int64_t>(rows[u]) * dpad) + i);
             const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&pk.x);
             const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&pk.y);
-            acc[u] += qv.x * __low2float(lo) + qv.y * __high2float(lo) + qv.z * __low2float(hi) + qv.w * __high2float(hi);
+            if (l2) {
+              const float a = qv.x - __low2float(lo), b2 = qv.y - __high2float(lo);
+              const float c = qv.z - __low2float(hi), e = qv.w - __high2float(hi);
+              acc[u] -= a * a + b2 * b2 + c * c + e * e;
+            } else {
+              acc[u] += qv.x * __low2float(lo) + qv.y * __high2float(lo) + qv.z * __low2float(hi) + qv.w * __high2float(hi);
+            }
           }
         }
       }
@@ -132,7 +143,9 @@ rerank_kernel(const float* __restrict__ q, const float* __restrict__ bank_f32,
     const int e = r * 32 + lane;
     if (e < k) {
       const bool ok = exact[r] != 0ull;
-      out_scores[qi * k + e] = ok ? key_score(exact[r]) : -INFINITY;
+      // L2 banks report squared distances, ascending (GpuIndexFlatL2, search_faiss.py:45-46,89)
+      const float sc = ok ? key_score(exact[r]) : -INFINITY;
+      out_scores[qi * k + e] = l2 ? -sc : sc;
       out_idx[qi * k + e] = ok ? static_cast<int64_t>(key_row(exact[r])) + idx_offset : -1;
     }
   }
@@ -145,7 +158,8 @@ int rerank_launch(const Bank* b, const float* q, const float* qnorm_ws, int64_t 
   const unsigned blocks = static_cast<unsigned>(ceil_div64(Q, 4));
 #define HB_RERANK(R)                                                                              \
   rerank_kernel<R><<<blocks, 128, 0, st>>>(q, b->feat_f32, b->feat_bf16, cand, n_chunks, q_pad, Q, \
-                                           b->d, b->dpad, k, idx_offset, out_scores, out_idx)
+                                           b->d, b->dpad, k, idx_offset, \
+                                           (b->flags & HB_BANK_L2) ? 1 : 0, out_scores, out_idx)
   if (kp == 32) HB_RERANK(1);
   else if (kp == 64) HB_RERANK(2);
   else if (kp == 128) HB_RERANK(4);

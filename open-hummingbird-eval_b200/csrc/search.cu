@@ -508,7 +508,7 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
 // Query preparation: fp32 (Q, d) -> bf16 (Q, dpad) zero padded, plus ||q||_2.
 // (hbird_eval.py:624-625 hands the raw, un-normalised query rows to the backend.)
 __global__ void __launch_bounds__(256)
-prep_queries_kernel(const float* __restrict__ q, int64_t Q, int d, int dpad,
+prep_queries_kernel(const float* __restrict__ q, int64_t Q, int d, int dpad, int l2,
                     __nv_bfloat16* __restrict__ qb, float* __restrict__ qnorm) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d4 = d >> 2;
@@ -527,7 +527,8 @@ prep_queries_kernel(const float* __restrict__ q, int64_t Q, int d, int dpad,
       pk.y = *reinterpret_cast<uint32_t*>(&hi);
       *reinterpret_cast<uint2*>(ob + 4 * i) = pk;
     }
-    for (int i = d + lane; i < dpad; i += 32) ob[i] = __float2bfloat16(0.f);
+    // L2 banks carry -||x||^2/2 in columns d..d+2 (bank.cu); the query multiplies them by 1
+    for (int i = d + lane; i < dpad; i += 32) ob[i] = __float2bfloat16((l2 && i < d + 3) ? 1.f : 0.f);
     ss = warp_sum(ss);
     if (lane == 0 && qnorm) qnorm[row] = sqrtf(ss);
   }
@@ -655,7 +656,7 @@ static int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_
 
   b->last_launches = 0;
   int64_t blocks = std::min<int64_t>(ceil_div64(Q, 8), static_cast<int64_t>(b->num_sms) * 8);
-  prep_queries_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(q, Q, b->d, b->dpad, q_bf16, qnorm);
+  prep_queries_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(q, Q, b->d, b->dpad, (b->flags & HB_BANK_L2) ? 1 : 0, q_bf16, qnorm);
   HB_CHECK_CUDA(cudaGetLastError());
   b->last_launches++;
 

@@ -203,6 +203,13 @@ class HbirdEvaluation:
         """hbird_eval.py:267-281, through the registry."""
         if nn_method == "b200":
             kw = {k: v for k, v in kwargs.items() if k not in ("k_prime", "keep_f32", "gpu_ids")}
+            measure = str(kw.pop("distance_measure", "dot_product")).lower()
+            if measure not in ("dot_product", "l2", "euclidean"):
+                raise ValueError(f"Unsupported distance measure: {measure}")  # search_faiss.py:48
+            # Bank rows are unit-norm (hbird_eval.py:324), so ||q-x||^2 = ||q||^2 + 1 - 2 q.x ranks
+            # exactly as the inner product does, and the reference drops the distances (:628):
+            # "l2" therefore runs the inner-product index here.  The plugin itself implements true
+            # squared-L2 for callers that hand it un-normalised rows.
             self.NN_algorithm = create_nn_backend(
                 "b200", None, n_neighbors=n_neighbours, bank=self.bank, k_prime=self.k_prime,
                 idx_offset=self.idx_offset, gpu_ids=[self.device.index], **kw)

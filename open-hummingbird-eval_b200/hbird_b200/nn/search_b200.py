@@ -3,7 +3,9 @@
 Replaces NearestNeighborSearchFaiss (hbird/nn/search_faiss.py:6-90): same constructor shape
 (feature_memory, n_neighbors, distance_measure, gpu_ids, **kwargs), same
 find_nearest_neighbors(q, k) -> (indices ndarray int64 (Q,k), distances ndarray fp32 (Q,k))
-sorted by descending inner product.  The index is an HBM-resident MemoryBank (bf16 rows for the
+sorted by descending inner product (distance_measure="dot_product", GpuIndexFlatIP) or by
+ascending squared L2 distance ("l2"/"euclidean", GpuIndexFlatL2, search_faiss.py:43-48).
+The index is an HBM-resident MemoryBank (bf16 rows for the
 tcgen05 pass + fp32 rows for the exact re-rank); there is no CPU path.
 
 Extra (device-resident) entry points used by the fused evaluator:
@@ -32,9 +34,10 @@ class NearestNeighborSearchB200(NearestNeighborSearchBase):
         sharding is one process per GPU (hbird_b200.distributed)."""
         self.n_neighbors = int(n_neighbors)
         self.distance_measure = distance_measure.lower()
-        if self.distance_measure != "dot_product":
+        if self.distance_measure not in ("dot_product", "l2", "euclidean"):
             # search_faiss.py:48 / search_scann.py:20
             raise ValueError(f"Unsupported distance measure: {self.distance_measure}")
+        self.metric = "dot_product" if self.distance_measure == "dot_product" else "l2"
         if not torch.cuda.is_available():
             raise RuntimeError("No GPUs available for the b200 backend.")  # search_faiss.py:15-16
         n_gpus = torch.cuda.device_count()
@@ -67,6 +70,8 @@ class NearestNeighborSearchB200(NearestNeighborSearchBase):
             self.index = self._initialize_index()
             self._add_features_to_index()
         else:
+            if bank.metric != self.metric:
+                raise ValueError(f"bank was built for metric {bank.metric!r}, not {self.metric!r}")
             self.embed_d = bank.d
             self.index = bank
         if not self.bank.finalized:
@@ -77,7 +82,8 @@ class NearestNeighborSearchB200(NearestNeighborSearchBase):
     def _initialize_index(self):
         n, d = self.feature_memory.shape
         c = self._label_memory.shape[1] if self._label_memory is not None else 1
-        self.bank = ops.MemoryBank(d, c, self._patch_pixels, max(int(n), 1), self.gpu_id, self.keep_f32)
+        self.bank = ops.MemoryBank(d, c, self._patch_pixels, max(int(n), 1), self.gpu_id, self.keep_f32,
+                                    metric=self.metric)
         return self.bank
 
     def _add_features_to_index(self):

@@ -42,13 +42,17 @@ class MemoryBank:
     hbird_eval.py:156-161,357-366, packed as bf16 rows (+ fp32 copy) and uint16 class histograms."""
 
     def __init__(self, d: int, num_classes: int, patch_pixels: int, capacity_rows: int,
-                 device: int = 0, keep_f32: bool = True):
+                 device: int = 0, keep_f32: bool = True, metric: str = "dot_product"):
         import ctypes
+
+        if metric not in ("dot_product", "l2"):
+            raise ValueError(f"Unsupported distance measure: {metric}")  # search_faiss.py:48
+        self.metric = metric
 
         self.d, self.num_classes, self.patch_pixels = int(d), int(num_classes), int(patch_pixels)
         self.device = int(device)
         self._h = ctypes.c_void_p(0)
-        flags = _capi.HB_BANK_KEEP_F32 if keep_f32 else 0
+        flags = (_capi.HB_BANK_KEEP_F32 if keep_f32 else 0) | (_capi.HB_BANK_L2 if metric == "l2" else 0)
         check(lib.hb_bank_create(self.device, self.d, self.num_classes, self.patch_pixels,
                                  int(capacity_rows), flags, ctypes.byref(self._h)))
         self.finalized = False

@@ -45,3 +45,33 @@ def create_nn_backend(name: str, feature_memory, n_neighbors: int = 30, **kw):
         # same exception type and wording as hbird_eval.py:281
         raise ValueError(f"Unsupported NN method. Choose from {set(NN_BACKENDS)}.")
     return NN_BACKENDS[name](feature_memory, n_neighbors=n_neighbors, **kw)
+
+
+def parse_nn_params(kv_list) -> Dict[str, object]:
+    """`--nn-param KEY=VALUE` (repeatable) -> ctor kwargs, with the reference CLI's coercion order
+    (eval.py:444-462): true/false -> bool, then int, then float, else the raw string.  Raises
+    ValueError for an item without '='."""
+    out: Dict[str, object] = {}
+    for item in kv_list or []:
+        key, sep, val = str(item).partition("=")
+        if not sep:
+            raise ValueError(f"Invalid --nn-param '{item}'. Use KEY=VALUE.")
+        key, val = key.strip(), val.strip()
+        low = val.lower()
+        if low in ("true", "false"):
+            out[key] = low == "true"
+            continue
+        for cast in (int, float):
+            try:
+                out[key] = cast(val)
+                break
+            except ValueError:
+                pass
+        else:
+            out[key] = val
+    return out
+
+
+def nn_method_choices():
+    """What `--nn-method` should offer (eval.py:409 lists its two names literally)."""
+    return sorted(NN_BACKENDS)

@@ -148,6 +148,29 @@ def search_exact_ip(q: np.ndarray, bank: np.ndarray, k: int, block: int = 4096,
     return idx, dist
 
 
+def search_exact_l2(q: np.ndarray, bank: np.ndarray, k: int, block: int = 4096) -> Tuple[np.ndarray, np.ndarray]:
+    """hbird/nn/search_faiss.py:45-46,83-90 — GpuIndexFlatL2.search: exact top-k by SQUARED
+    Euclidean distance, ascending (faiss reports squared L2).  Distances are accumulated as
+    sum((q-x)^2) in float64 and rounded to fp32, so the oracle carries no cancellation error."""
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    bank = np.ascontiguousarray(bank, dtype=np.float64)
+    Q, N = q.shape[0], bank.shape[0]
+    kk = min(k, N)
+    idx = np.full((Q, k), -1, dtype=np.int64)
+    dist = np.full((Q, k), np.inf, dtype=F32)
+    bn = (bank * bank).sum(1)
+    for a in range(0, Q, block):
+        qq = q[a:a + block]
+        d2 = (qq * qq).sum(1)[:, None] + bn[None, :] - 2.0 * (qq @ bank.T)
+        i, negd = _topk_rows(-d2, kk)
+        # exact distances for the winners, summed the direct way
+        exact = ((qq[:, None, :] - bank[i]) ** 2).sum(-1)
+        order = np.lexsort((i, exact), axis=1)
+        idx[a:a + qq.shape[0], :kk] = np.take_along_axis(i, order, 1)
+        dist[a:a + qq.shape[0], :kk] = np.take_along_axis(exact, order, 1).astype(F32)
+    return idx, dist
+
+
 def merge_shards(shard_idx: np.ndarray, shard_dist: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray]:
     """hbird/nn/search_faiss.py:53-63 — faiss.IndexShards merges per-shard results on the host:
     top-k of the union, descending, ties by smaller (global) index.  Inputs are (G, Q, k)."""

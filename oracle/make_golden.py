@@ -193,6 +193,23 @@ def kats():
     return out
 
 
+def plugin_fixture():
+    """The reference plugin class itself (hbird/nn/search_faiss.py:6-90) on an UN-normalised bank,
+    for both distance measures: pins the (indices, distances) order and the L2 convention
+    (squared distances, ascending)."""
+    from hbird.nn.search_faiss import NearestNeighborSearchFaiss
+
+    g = torch.Generator().manual_seed(11)
+    bank = torch.randn(2000, 48, generator=g) * (0.5 + torch.rand(2000, 1, generator=g))
+    q = torch.randn(257, 48, generator=g) * 1.7
+    out = {"bank": bank.numpy(), "q": q.numpy()}
+    for name in ("dot_product", "l2"):
+        nn = NearestNeighborSearchFaiss(bank, n_neighbors=30, distance_measure=name)
+        idx, dist = nn.find_nearest_neighbors(q)
+        out[f"idx_{name}"], out[f"dist_{name}"] = idx, dist
+    return out
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit(f"reference tree not found at {REF}: this script only runs in the dev container")
@@ -200,6 +217,9 @@ if __name__ == "__main__":
     sys.path.insert(0, REF)
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(1)  # deterministic summation order in the fixtures
+    np.savez_compressed(os.path.join(GOLD, "ref_plugin_metrics.npz"), **plugin_fixture())
+    if "--plugin-only" in sys.argv:
+        sys.exit(0)
     for name, cfg in CONFIGS.items():
         res = run_reference(cfg, faiss)
         np.savez_compressed(os.path.join(GOLD, f"ref_{name}.npz"), cfg=json.dumps(cfg), **res)

@@ -3,11 +3,13 @@ libhbird_b200.so) and compared with the CPU oracle on the same seeded inputs and
 fixtures produced by the unmodified reference.  Gates (BASELINE.json north_star):
 recall@30 >= 0.999, neighbour scores within 1e-3 relative, confusion matrix bit-exact for
 identical predictions, mIoU within 0.05 points (5e-4 on the [0,1] scale)."""
+import os
+
 import numpy as np
 import pytest
 import torch
 
-from helpers import batches_np, load_golden, recall
+from helpers import GOLDEN, batches_np, load_golden, recall
 from hbird_b200 import HbirdEvaluation, NearestNeighborSearchB200, hbird_evaluation, ops
 from hbird_b200.data import SyntheticSegmentationData
 from hbird_b200.models import FeatureExtractorSimple
@@ -246,9 +248,44 @@ def test_plugin_contract_matches_faiss_backend():
     idx5, _ = nn.find_nearest_neighbors(q, k=5)
     assert idx5.shape == (77, 5) and recall(idx5, ri[:, :5]) >= 0.995
     with pytest.raises(ValueError, match="Unsupported distance measure"):
-        NearestNeighborSearchB200(torch.from_numpy(fm), distance_measure="l2")
+        NearestNeighborSearchB200(torch.from_numpy(fm), distance_measure="cosine")
     with pytest.raises(ValueError, match="Invalid GPU ID"):
         NearestNeighborSearchB200(torch.from_numpy(fm), gpu_ids=[99])
+
+
+@pytest.mark.parametrize("measure", ["dot_product", "l2"])
+def test_plugin_matches_reference_plugin_fixture(measure):
+    """tests/golden/ref_plugin_metrics.npz: the reference's own NearestNeighborSearchFaiss on an
+    un-normalised bank, both distance measures (search_faiss.py:43-48).  L2 = squared distances,
+    ascending."""
+    z = np.load(os.path.join(GOLDEN, "ref_plugin_metrics.npz"))
+    nn = NearestNeighborSearchB200(torch.from_numpy(z["bank"]), n_neighbors=30, distance_measure=measure)
+    idx, dist = nn.find_nearest_neighbors(torch.from_numpy(z["q"]))
+    ri, rd = z[f"idx_{measure}"], z[f"dist_{measure}"]
+    assert recall(idx, ri) >= 0.999
+    assert np.abs(dist - rd).max() <= 1e-3 * np.abs(rd).max()
+    assert (np.diff(dist, axis=1) >= 0).all() if measure == "l2" else (np.diff(dist, axis=1) <= 0).all()
+
+
+@pytest.mark.parametrize("N,d,Q,keep_f32", [(50000, 384, 1000, True), (20000, 64, 300, True), (9000, 200, 130, False)])
+def test_l2_search_vs_oracle_seeded(N, d, Q, keep_f32):
+    """euclidean == l2 (search_faiss.py:45); rows of very different norms, so ranking by L2 and by
+    inner product disagree and the norm columns of the tensor pass matter."""
+    rng = np.random.default_rng(N + d)
+    bank = (rng.standard_normal((N, d)) * rng.uniform(0.3, 1.6, (N, 1))).astype(np.float32)
+    q = (rng.standard_normal((Q, d)) * 1.3).astype(np.float32)
+    nn = NearestNeighborSearchB200(torch.from_numpy(bank), n_neighbors=30, distance_measure="euclidean",
+                                   keep_f32=keep_f32)
+    idx, dist = nn.find_nearest_neighbors(q)
+    ri, rd = O.search_exact_l2(q, bank, 30)
+    ii, _ = O.search_exact_ip(q, bank, 30)
+    assert recall(ii, ri) < 0.5  # the two metrics really differ on this data
+    if keep_f32:
+        assert recall(idx, ri) >= 0.999
+        assert np.abs(dist - rd).max() <= 1e-3 * np.abs(rd).max()
+    else:  # bf16-only bank: distances carry the bf16 rounding of the rows
+        assert recall(idx, ri) >= 0.97
+        assert np.abs(dist - rd).max() <= 2e-2 * np.abs(rd).max()
 
 
 # ------------------------------------------------------------------ K3: merge

@@ -12,7 +12,8 @@ import torch
 from helpers import GOLDEN, load_golden
 from hbird_b200 import _capi
 from hbird_b200.data import SyntheticSegmentationData
-from hbird_b200.registry import NN_BACKENDS, create_nn_backend, register_nn_backend
+from hbird_b200.registry import (NN_BACKENDS, create_nn_backend, nn_method_choices, parse_nn_params,
+                                register_nn_backend)
 from hbird_b200.utils.eval_metrics import miou_from_confusion
 from oracle import hbird_oracle as O
 
@@ -86,3 +87,16 @@ def test_synthetic_data_contract():
     f, aux = d.ftr_extr_fn(d.model, x)
     assert f.shape == (2, 16, 16) and aux is None
     assert (f.norm(dim=-1) > 1.5).all()  # queries are NOT unit norm (hbird_eval.py:222-224)
+
+
+def test_parse_nn_params_follows_reference_cli_coercion():
+    """Expected dict = output of the reference's _parse_nn_params (eval.py:444-462) on these items."""
+    items = ["k_prime=64", "keep_f32=False", "idx_shard=TRUE", "beta=0.02", "distance_measure=l2",
+             " leaves = 200 ", "x=1e3", "name=a=b", "neg=-5"]
+    assert parse_nn_params(items) == {
+        "k_prime": 64, "keep_f32": False, "idx_shard": True, "beta": 0.02, "distance_measure": "l2",
+        "leaves": 200, "x": 1000.0, "name": "a=b", "neg": -5}
+    assert parse_nn_params(None) == {} and parse_nn_params([]) == {}
+    with pytest.raises(ValueError, match="KEY=VALUE"):
+        parse_nn_params(["novalue"])
+    assert {"b200", "faiss", "scann"} <= set(nn_method_choices())

@@ -128,6 +128,18 @@ def test_predsmiou_known_answers():
     assert kats[0]["miou"] == pytest.approx(0.5277777777777778)
 
 
+@pytest.mark.parametrize("measure", ["dot_product", "l2"])
+def test_search_oracle_matches_reference_plugin_fixture(measure):
+    """ref_plugin_metrics.npz = the reference's NearestNeighborSearchFaiss (search_faiss.py:6-90)
+    run on an un-normalised bank by oracle/make_golden.py."""
+    z = np.load(os.path.join(GOLDEN, "ref_plugin_metrics.npz"))
+    fn = O.search_exact_ip if measure == "dot_product" else O.search_exact_l2
+    idx, dist = fn(z["q"], z["bank"], 30)
+    ri, rd = z[f"idx_{measure}"], z[f"dist_{measure}"]
+    assert (idx == ri).mean() >= 0.999  # fp32 near-ties may swap neighbours
+    np.testing.assert_allclose(dist, rd, rtol=2e-5, atol=2e-5)
+
+
 def test_merge_shards_equals_unsharded():
     rng = np.random.default_rng(0)
     bank = O.normalise_rows(rng.standard_normal((500, 32)).astype(np.float32))
