@@ -163,15 +163,22 @@ def run_step(ops, bank, table, w, q, y, conf, shard=None):
     """One pass: decode -> search -> label transfer -> upsample+argmax -> confusion."""
     B, S, H = w["B"], w["S"], w["S"] * w["ps"]
     gt = ops.decode_mask(y, False)
-    scores, idx, qn = bank.search(q, K_NEIGH, K_PRIME, 0 if shard is None else shard["offset"])
+    if shard is not None and shard.get("xchg") is not None:
+        qn = shard["xchg"].search_scatter(bank, q, shard["qsplit"], K_NEIGH, K_PRIME, shard["offset"])
+    else:
+        scores, idx, qn = bank.search(q, K_NEIGH, K_PRIME, 0 if shard is None else shard["offset"])
     if shard is not None:
         from hbird_b200 import distributed as hdist
 
-        gs, gi = hdist.all_gather_topk(scores, idx)
-        scores, idx = ops.merge_topk(gs, gi)
         b0, b1 = hdist.split_range(B, shard["world"], shard["rank"])
         n = S * S
-        lh = ops.label_transfer(table, w["ps"] ** 2, scores[b0 * n:b1 * n], idx[b0 * n:b1 * n], qn[b0 * n:b1 * n], BETA)
+        if shard.get("xchg") is not None:  # fused exchange: K2b scatters over NVLink, merge waits
+            scores, idx = shard["xchg"].merge()
+        else:
+            gs, gi = hdist.all_gather_topk(scores, idx)
+            scores, idx = ops.merge_topk(gs, gi)
+            scores, idx = scores[b0 * n:b1 * n], idx[b0 * n:b1 * n]
+        lh = ops.label_transfer(table, w["ps"] ** 2, scores, idx, qn[b0 * n:b1 * n], BETA)
         pred = ops.upsample_argmax(lh, b1 - b0, S, H, H)
         ops.confusion_accumulate(conf, gt.view(B, H, H)[b0:b1], pred, w["ignore"])
     else:
@@ -438,10 +445,27 @@ def main():
             q, y = shared_ring[i % RING]
             run_step(ops, shard_bank, full_table, w, q, y, conf2, shard=info)
 
-        ms_sh = timed_loop(torch, dist, world, step_sh, args.steps, warmup) / args.steps
+        ms_nccl = timed_loop(torch, dist, world, step_sh, args.steps, warmup) / args.steps
+        conf_nccl = conf2.clone()
+        # fused exchange over NVLink peer memory (K2b peer stores + waiting merge kernel)
+        per_rank = -(-w["B"] // world) * w["S"] ** 2
+        xchg = hdist.connect_shard_exchange(per_rank, K_NEIGH, device)
+        ms_sh, collective = ms_nccl, "NCCL all-gather of (score f32, idx i64)[Q,k] + k-way merge kernel"
+        exchange_parity = None
+        if xchg is not None:
+            info["xchg"], info["qsplit"] = xchg, hdist.query_split(w["B"], w["S"] ** 2, world)
+            conf2.zero_()
+            ms_sh = timed_loop(torch, dist, world, step_sh, args.steps, warmup) / args.steps
+            collective = ("fused: K2b stores each query's shard top-k into the owner rank's window over "
+                          "NVLink (CUDA IPC), merge kernel waits on per-rank step flags; no NCCL call")
+            exchange_parity = bool(torch.equal(conf2, conf_nccl))  # same steps, same batches
         sharded = {"value": Q / (ms_sh * 1e-3), "unit": "patch-queries/s", "ms_per_step": ms_sh,
                    "bank_rows_total": w["N"], "bank_rows_per_gpu": b - a, "scaling": "strong",
-                   "collective": "NCCL all-gather of (score f32, idx i64)[Q,k] + k-way merge kernel"}
+                   "collective": collective, "nccl_path_ms_per_step": ms_nccl,
+                   "confusion_equals_nccl_path": exchange_parity}
+        if xchg is not None:
+            torch.cuda.synchronize()
+            dist.barrier()
         shard_bank.close()
 
     # ---- CPU baseline beside it (rank 0, N = 1 only)

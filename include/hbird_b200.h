@@ -46,6 +46,8 @@ typedef enum hb_status {
                                  returns ||q-x||^2 ascending; rows are NOT expected to be unit-norm  */
 
 typedef struct hb_bank hb_bank_t; /* opaque: one HBM-resident shard of the memory bank */
+typedef struct hb_exchange hb_exchange_t; /* opaque: one rank's end of the fused shard exchange */
+#define HB_EXCHANGE_HANDLE_BYTES 64 /* sizeof(cudaIpcMemHandle_t) */
 
 /* ---- library ------------------------------------------------------------------- */
 
@@ -162,6 +164,39 @@ int hb_search_dump_scores(hb_bank_t* bank, const float* q_dev, int64_t Q, float*
 int hb_merge_topk(const float* shard_scores_dev, const int64_t* shard_idx_dev, int G,
                   int64_t Q, int k, float* out_scores_dev, int64_t* out_idx_dev,
                   void* stream);
+
+/* ---- K3x: fused shard exchange over NVLink peer memory -------------------------------------
+ * The B200 form of faiss.IndexShards' search (search_faiss.py:53-63,89) for one process per GPU:
+ * every rank searches all Q queries against its row shard; rank p post-processes the queries
+ * [qsplit[p], qsplit[p+1]).  hb_search_scatter runs K2 + K2b and stores each query's shard top-k
+ * DIRECTLY into the owner rank's window (peer memory mapped through CUDA IPC, NVLink stores), then
+ * publishes a step counter there; hb_exchange_merge waits for the counters of all ranks and merges
+ * the G lists of the local slice.  No NCCL call and no host synchronisation on the data path.
+ * All ranks must make the same sequence of scatter/merge calls (one merge per scatter).
+ *
+ * Set-up: each rank creates its window (slice_capacity = most rows any rank will own per call,
+ * max_k = largest k), exports a 64-byte handle, the host side all-gathers the handles (any
+ * transport; hbird_b200 uses torch.distributed) and every rank connects.  world == 1 needs no
+ * connect.  HB_ERR_UNSUPPORTED from connect = no peer access / no CUDA IPC: use the NCCL
+ * all-gather + hb_merge_topk path instead.  hb_exchange_connect_local wires exchanges created in
+ * ONE process on one device to each other by pointer (tests; the ranks then run one after the
+ * other on a stream: all scatters of a step before its merges). */
+int hb_exchange_create(int device, int rank, int world, int64_t slice_capacity, int max_k,
+                       hb_exchange_t** out);
+int hb_exchange_destroy(hb_exchange_t* xchg);
+int hb_exchange_handle(hb_exchange_t* xchg, void* handle_out, int handle_bytes);
+int hb_exchange_connect(hb_exchange_t* xchg, const void* handles, int n_handles);
+int hb_exchange_connect_local(hb_exchange_t* xchg, hb_exchange_t* const* peers, int n_peers);
+/* qsplit_host: world+1 ascending int64 on the HOST, qsplit[0] = 0, qsplit[world] = Q.
+ * out_qnorm_dev: optional fp32 (Q,) query norms, as hb_search. */
+int hb_search_scatter(hb_bank_t* bank, hb_exchange_t* xchg, const float* q_dev, int64_t Q, int k,
+                      int k_prime, int64_t idx_offset, const int64_t* qsplit_host,
+                      float* out_qnorm_dev, void* stream);
+/* Outputs: fp32 / int64 (rows, k) for this rank's slice of the last scatter, sorted descending,
+ * global indices; rows = hb_exchange_slice_rows().  A peer that never arrives makes the kernel
+ * trap after 60 s instead of hanging the GPU. */
+int hb_exchange_merge(hb_exchange_t* xchg, float* out_scores_dev, int64_t* out_idx_dev, void* stream);
+int64_t hb_exchange_slice_rows(const hb_exchange_t* xchg);
 
 /* ---- K4: label transfer ------------------------------------------------------------------
  * Replaces the neighbour gather (hbird_eval.py:611-637) and _cross_attention

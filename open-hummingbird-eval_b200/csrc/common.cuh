@@ -67,6 +67,45 @@ struct Bank {
   cudaEvent_t ev_end[64] = {};
 };
 
+// ---- fused shard exchange (exchange.cu, rerank.cu) ----------------------------------------
+constexpr int kMaxPeers = 16;
+
+// Where K2b's output rows go when the bank is row-sharded over `world` GPUs: query qi belongs to
+// the rank p with qsplit[p] <= qi < qsplit[p+1] and is stored straight into p's window (peer
+// memory over NVLink), slot `rank`; the last CTA then publishes `step` in every peer's flag.
+struct Scatter {
+  int world = 0;  // 0: plain local output
+  int rank = 0;
+  uint32_t step = 0;
+  int64_t qsplit[kMaxPeers + 1] = {};
+  float* scores[kMaxPeers] = {};     // peer p: window buffer (step & 1), slot `rank`
+  int64_t* idx[kMaxPeers] = {};
+  uint32_t* flag[kMaxPeers] = {};    // peer p: arrival flag of source `rank`
+  unsigned int* done_ctas = nullptr; // local counter of finished CTAs
+};
+
+// One rank's end of the exchange: a cudaMalloc'ed window other ranks map through CUDA IPC.
+//   window = [flags: kMaxPeers x u32, padded to 256 B]
+//            2 x [scores: world x cap x kmax f32][idx: world x cap x kmax i64]
+struct Exchange {
+  int device = 0, rank = 0, world = 1;
+  int64_t cap = 0;  // rows per slot
+  int kmax = 0;
+  uint32_t step = 0;        // exchanges started so far
+  int64_t last_rows = 0;    // slice rows of the last scatter
+  int last_k = 0;
+  size_t bytes = 0;
+  bool connected = false;
+  bool ipc_opened[kMaxPeers] = {};
+  uint8_t* window[kMaxPeers] = {};  // [rank] = own allocation, others = mapped peers
+  unsigned int* done_ctas = nullptr;
+  unsigned int* timeout_flag = nullptr;
+  size_t scores_off(int parity) const { return 256 + static_cast<size_t>(parity) * buffer_bytes(); }
+  size_t idx_off(int parity) const { return scores_off(parity) + sizeof(float) * slot_elems() * world; }
+  size_t slot_elems() const { return static_cast<size_t>(cap) * kmax; }
+  size_t buffer_bytes() const { return (sizeof(float) + sizeof(int64_t)) * slot_elems() * world; }
+};
+
 int ensure_workspace(Bank* b, size_t bytes);
 // Encode a 2-D bf16 row-major (rows, cols_pad) tensor map with a (64 x box_rows) box and
 // 128-byte swizzle.  Resolved through cudaGetDriverEntryPoint: no link-time libcuda.

@@ -1,0 +1,198 @@
+// K3x — fused shard exchange over NVLink peer memory.
+// The reference merges its per-GPU shard results on the host (faiss.IndexShards,
+// search_faiss.py:53-63).  Here each rank owns a row shard of the bank, every rank searches every
+// query, and only the rank that post-processes a query needs its merged neighbours.  So the
+// exchange is an all-to-all of (score f32, idx i64)[rows, k] slices, and it is fused into the
+// kernels on either side of it instead of being a collective call:
+//   * K2b (rerank.cu) stores each query's top-k straight into the owner rank's window through a
+//     CUDA-IPC mapping (NVLink stores), and its last CTA publishes a step counter on every peer;
+//   * K3x (merge_window_kernel) waits on those counters and merges the G lists of its slice.
+// No NCCL call, no staging copy, no host synchronisation; two window buffers alternate by step
+// (a rank can be at most one exchange ahead of a peer, because its own merge waits for that
+// peer's previous scatter).
+#include <string.h>
+
+#include "common.cuh"
+
+namespace hb {
+
+int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_t idx_offset,
+                float* out_scores, int64_t* out_idx, float* out_qnorm, float* dump, int cg_override,
+                cudaStream_t st, const Scatter* sc);  // search.cu
+int merge_window_launch(const Exchange* x, uint32_t step, int64_t rows, int k, float* out_scores,
+                        int64_t* out_idx, cudaStream_t st);  // rerank.cu
+
+}  // namespace hb
+
+using hb::Bank;
+using hb::Exchange;
+
+extern "C" {
+
+int hb_exchange_create(int device, int rank, int world, int64_t slice_capacity, int max_k,
+                       hb_exchange_t** out) {
+  HB_REQUIRE(out != nullptr, "hb_exchange_create: out is NULL");
+  *out = nullptr;
+  HB_REQUIRE(world >= 1 && world <= hb::kMaxPeers, "hb_exchange_create: world=%d not in [1, %d]", world, hb::kMaxPeers);
+  HB_REQUIRE(rank >= 0 && rank < world, "hb_exchange_create: rank=%d not in [0, %d)", rank, world);
+  HB_REQUIRE(slice_capacity >= 1 && slice_capacity < (int64_t(1) << 31), "hb_exchange_create: slice_capacity=%lld out of range", (long long)slice_capacity);
+  HB_REQUIRE(max_k >= 1 && max_k <= 128, "hb_exchange_create: max_k=%d not in [1, 128]", max_k);
+  int rc = hb_device_check(device, nullptr);
+  if (rc != HB_OK) return rc;
+  HB_CHECK_CUDA(cudaSetDevice(device));
+  Exchange* x = new Exchange();
+  x->device = device;
+  x->rank = rank;
+  x->world = world;
+  x->cap = slice_capacity;
+  x->kmax = max_k;
+  x->bytes = 256 + 2 * x->buffer_bytes();
+  cudaError_t e = cudaMalloc(&x->window[rank], x->bytes);
+  if (e == cudaSuccess) e = cudaMemset(x->window[rank], 0, 256);
+  if (e == cudaSuccess) e = cudaMalloc(&x->done_ctas, 2 * sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(x->done_ctas, 0, 2 * sizeof(unsigned int));
+  if (e != cudaSuccess) {
+    hb::set_error("hb_exchange_create: allocating a %zu-byte window failed: %s", x->bytes, cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    hb_exchange_destroy(reinterpret_cast<hb_exchange_t*>(x));
+    return e == cudaErrorMemoryAllocation ? HB_ERR_OOM : HB_ERR_CUDA;
+  }
+  x->timeout_flag = x->done_ctas + 1;
+  HB_CHECK_CUDA(cudaDeviceSynchronize());
+  x->connected = world == 1;
+  *out = reinterpret_cast<hb_exchange_t*>(x);
+  return HB_OK;
+}
+
+int hb_exchange_destroy(hb_exchange_t* xchg) {
+  if (!xchg) return HB_OK;
+  Exchange* x = reinterpret_cast<Exchange*>(xchg);
+  cudaSetDevice(x->device);
+  cudaDeviceSynchronize();
+  for (int p = 0; p < x->world; ++p)
+    if (p != x->rank && x->ipc_opened[p] && x->window[p]) cudaIpcCloseMemHandle(x->window[p]);
+  if (x->window[x->rank]) cudaFree(x->window[x->rank]);
+  if (x->done_ctas) cudaFree(x->done_ctas);
+  (void)cudaGetLastError();
+  delete x;
+  return HB_OK;
+}
+
+int hb_exchange_handle(hb_exchange_t* xchg, void* handle_out, int handle_bytes) {
+  HB_REQUIRE(xchg && handle_out, "hb_exchange_handle: NULL argument");
+  HB_REQUIRE(handle_bytes == HB_EXCHANGE_HANDLE_BYTES, "hb_exchange_handle: handle_bytes=%d, expected %d", handle_bytes, HB_EXCHANGE_HANDLE_BYTES);
+  static_assert(sizeof(cudaIpcMemHandle_t) == HB_EXCHANGE_HANDLE_BYTES, "IPC handle size");
+  Exchange* x = reinterpret_cast<Exchange*>(xchg);
+  HB_CHECK_CUDA(cudaSetDevice(x->device));
+  cudaIpcMemHandle_t h;
+  HB_CHECK_CUDA(cudaIpcGetMemHandle(&h, x->window[x->rank]));
+  memcpy(handle_out, &h, sizeof(h));
+  return HB_OK;
+}
+
+int hb_exchange_connect(hb_exchange_t* xchg, const void* handles, int n_handles) {
+  HB_REQUIRE(xchg && handles, "hb_exchange_connect: NULL argument");
+  Exchange* x = reinterpret_cast<Exchange*>(xchg);
+  HB_REQUIRE(n_handles == x->world, "hb_exchange_connect: %d handles for world=%d", n_handles, x->world);
+  HB_CHECK_CUDA(cudaSetDevice(x->device));
+  const uint8_t* hs = static_cast<const uint8_t*>(handles);
+  for (int p = 0; p < x->world; ++p) {
+    if (p == x->rank || x->window[p]) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, hs + static_cast<size_t>(p) * sizeof(h), sizeof(h));
+    void* ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      hb::set_error("hb_exchange_connect: cannot map the window of rank %d (no peer access between the "
+                    "GPUs, or CUDA IPC unavailable): %s", p, cudaGetErrorString(e));
+      (void)cudaGetLastError();
+      return HB_ERR_UNSUPPORTED;
+    }
+    x->window[p] = static_cast<uint8_t*>(ptr);
+    x->ipc_opened[p] = true;
+  }
+  x->connected = true;
+  return HB_OK;
+}
+
+int hb_exchange_connect_local(hb_exchange_t* xchg, hb_exchange_t* const* peers, int n_peers) {
+  HB_REQUIRE(xchg && peers, "hb_exchange_connect_local: NULL argument");
+  Exchange* x = reinterpret_cast<Exchange*>(xchg);
+  HB_REQUIRE(n_peers == x->world, "hb_exchange_connect_local: %d peers for world=%d", n_peers, x->world);
+  for (int p = 0; p < x->world; ++p) {
+    const Exchange* y = reinterpret_cast<const Exchange*>(peers[p]);
+    HB_REQUIRE(y && y->rank == p && y->world == x->world && y->cap == x->cap && y->kmax == x->kmax,
+               "hb_exchange_connect_local: peer %d does not match (rank/world/capacity/max_k)", p);
+    if (p != x->rank) x->window[p] = y->window[p];
+  }
+  x->connected = true;
+  return HB_OK;
+}
+
+int hb_search_scatter(hb_bank_t* bank, hb_exchange_t* xchg, const float* q_dev, int64_t Q, int k,
+                      int k_prime, int64_t idx_offset, const int64_t* qsplit_host,
+                      float* out_qnorm_dev, void* stream) {
+  HB_REQUIRE(bank && xchg, "hb_search_scatter: NULL handle");
+  Bank* b = reinterpret_cast<Bank*>(bank);
+  Exchange* x = reinterpret_cast<Exchange*>(xchg);
+  if (!b->finalized) {
+    hb::set_error("hb_search_scatter: bank not finalized (call hb_bank_finalize first)");
+    return HB_ERR_STATE;
+  }
+  if (!x->connected) {
+    hb::set_error("hb_search_scatter: exchange not connected (call hb_exchange_connect first)");
+    return HB_ERR_STATE;
+  }
+  HB_REQUIRE(b->device == x->device, "hb_search_scatter: bank on device %d, exchange on device %d", b->device, x->device);
+  HB_REQUIRE(Q >= 1 && Q < (int64_t(1) << 31), "hb_search_scatter: Q=%lld out of range", (long long)Q);
+  HB_REQUIRE(k >= 1 && k <= k_prime && k <= x->kmax, "hb_search_scatter: need 1 <= k (%d) <= min(k_prime %d, max_k %d)", k, k_prime, x->kmax);
+  HB_REQUIRE(k_prime == 32 || k_prime == 64 || k_prime == 128, "hb_search_scatter: k_prime=%d not in {32, 64, 128}", k_prime);
+  HB_REQUIRE(q_dev && qsplit_host, "hb_search_scatter: NULL pointer");
+  HB_REQUIRE(b->rows >= 1, "hb_search_scatter: the bank shard is empty");
+  HB_REQUIRE(qsplit_host[0] == 0 && qsplit_host[x->world] == Q, "hb_search_scatter: qsplit must run from 0 to Q");
+  for (int p = 0; p < x->world; ++p) {
+    const int64_t n = qsplit_host[p + 1] - qsplit_host[p];
+    HB_REQUIRE(n >= 0 && n <= x->cap, "hb_search_scatter: slice %d has %lld rows, window capacity is %lld", p, (long long)n, (long long)x->cap);
+  }
+  HB_CHECK_CUDA(cudaSetDevice(b->device));
+
+  x->step += 1;
+  const int parity = static_cast<int>(x->step & 1u);
+  hb::Scatter sc;
+  sc.world = x->world;
+  sc.rank = x->rank;
+  sc.step = x->step;
+  sc.done_ctas = x->done_ctas;
+  for (int p = 0; p <= x->world; ++p) sc.qsplit[p] = qsplit_host[p];
+  for (int p = 0; p < x->world; ++p) {
+    uint8_t* win = x->window[p];
+    sc.scores[p] = reinterpret_cast<float*>(win + x->scores_off(parity)) + x->slot_elems() * x->rank;
+    sc.idx[p] = reinterpret_cast<int64_t*>(win + x->idx_off(parity)) + x->slot_elems() * x->rank;
+    sc.flag[p] = reinterpret_cast<uint32_t*>(win) + x->rank;
+  }
+  x->last_rows = qsplit_host[x->rank + 1] - qsplit_host[x->rank];
+  x->last_k = k;
+  return hb::search_impl(b, q_dev, Q, k, k_prime, idx_offset, nullptr, nullptr, out_qnorm_dev, nullptr, 0,
+                         static_cast<cudaStream_t>(stream), &sc);
+}
+
+int hb_exchange_merge(hb_exchange_t* xchg, float* out_scores_dev, int64_t* out_idx_dev, void* stream) {
+  HB_REQUIRE(xchg != nullptr, "hb_exchange_merge: exchange is NULL");
+  Exchange* x = reinterpret_cast<Exchange*>(xchg);
+  if (x->step == 0 || x->last_k == 0) {
+    hb::set_error("hb_exchange_merge: no scatter to merge (call hb_search_scatter first)");
+    return HB_ERR_STATE;
+  }
+  HB_REQUIRE(x->last_rows == 0 || (out_scores_dev && out_idx_dev), "hb_exchange_merge: NULL output");
+  HB_CHECK_CUDA(cudaSetDevice(x->device));
+  const int k = x->last_k;
+  x->last_k = 0;  // one merge per scatter
+  return hb::merge_window_launch(x, x->step, x->last_rows, k, out_scores_dev, out_idx_dev,
+                                 static_cast<cudaStream_t>(stream));
+}
+
+int64_t hb_exchange_slice_rows(const hb_exchange_t* xchg) {
+  return xchg ? reinterpret_cast<const Exchange*>(xchg)->last_rows : -1;
+}
+
+}  // extern "C"

@@ -50,12 +50,21 @@ __device__ __forceinline__ void warp_bitonic_sort(uint64_t (&a)[R], int lane) {
   }
 }
 
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 template <int R>
-__global__ void __launch_bounds__(128)
-rerank_kernel(const float* __restrict__ q, const float* __restrict__ bank_f32,
-              const __nv_bfloat16* __restrict__ bank_bf16, const uint64_t* __restrict__ cand,
-              int n_chunks, int64_t q_pad, int64_t Q, int d, int dpad, int k, int64_t idx_offset,
-              int l2, float* __restrict__ out_scores, int64_t* __restrict__ out_idx) {
+__device__ __forceinline__ void
+rerank_query(const float* __restrict__ q, const float* __restrict__ bank_f32,
+             const __nv_bfloat16* __restrict__ bank_bf16, const uint64_t* __restrict__ cand,
+             int n_chunks, int64_t q_pad, int64_t Q, int d, int dpad, int k, int64_t idx_offset,
+             int l2, float* __restrict__ out_scores, int64_t* __restrict__ out_idx, const Scatter& sc) {
   constexpr int KP = 32 * R;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t qi = static_cast<int64_t>(blockIdx.x) * 4 + warp;
@@ -137,29 +146,64 @@ rerank_kernel(const float* __restrict__ q, const float* __restrict__ bank_f32,
   }
   warp_bitonic_sort<R, true>(exact, lane);
 
-  // ---- emit the top-k ----
+  // ---- emit the top-k: locally, or into the window of the rank that owns this query ----
+  float* os = out_scores + qi * k;
+  int64_t* oi = out_idx + qi * k;
+  if (sc.world) {
+    int p = 0;
+    while (p + 1 < sc.world && qi >= sc.qsplit[p + 1]) ++p;
+    const int64_t row = qi - sc.qsplit[p];
+    os = sc.scores[p] + row * k;  // peer memory (NVLink) unless p == rank
+    oi = sc.idx[p] + row * k;
+  }
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int e = r * 32 + lane;
     if (e < k) {
       const bool ok = exact[r] != 0ull;
       // L2 banks report squared distances, ascending (GpuIndexFlatL2, search_faiss.py:45-46,89)
-      const float sc = ok ? key_score(exact[r]) : -INFINITY;
-      out_scores[qi * k + e] = l2 ? -sc : sc;
-      out_idx[qi * k + e] = ok ? static_cast<int64_t>(key_row(exact[r])) + idx_offset : -1;
+      const float v = ok ? key_score(exact[r]) : -INFINITY;
+      os[e] = l2 ? -v : v;
+      oi[e] = ok ? static_cast<int64_t>(key_row(exact[r])) + idx_offset : -1;
+    }
+  }
+}
+
+template <int R>
+__global__ void __launch_bounds__(128)
+rerank_kernel(const float* __restrict__ q, const float* __restrict__ bank_f32,
+              const __nv_bfloat16* __restrict__ bank_bf16, const uint64_t* __restrict__ cand,
+              int n_chunks, int64_t q_pad, int64_t Q, int d, int dpad, int k, int64_t idx_offset,
+              int l2, float* __restrict__ out_scores, int64_t* __restrict__ out_idx,
+              const __grid_constant__ Scatter sc) {
+  rerank_query<R>(q, bank_f32, bank_bf16, cand, n_chunks, q_pad, Q, d, dpad, k, idx_offset, l2,
+                  out_scores, out_idx, sc);
+  if (sc.world) {
+    // Fused exchange: every thread's peer stores are ordered before the CTA counts itself done;
+    // the last CTA of the grid then raises this rank's arrival flag on every peer.
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned prev = atomicAdd(sc.done_ctas, 1u);
+      if (prev == gridDim.x - 1) {
+        *sc.done_ctas = 0u;  // ready for the next launch on this stream
+        __threadfence_system();
+        for (int p = 0; p < sc.world; ++p) st_release_sys(sc.flag[p], sc.step);
+      }
     }
   }
 }
 
 int rerank_launch(const Bank* b, const float* q, const float* qnorm_ws, int64_t Q, int k, int kp,
                   int n_chunks, int64_t q_pad, const uint64_t* cand, int64_t idx_offset,
-                  float* out_scores, int64_t* out_idx, cudaStream_t st) {
+                  float* out_scores, int64_t* out_idx, const Scatter* sc, cudaStream_t st) {
   (void)qnorm_ws;
   const unsigned blocks = static_cast<unsigned>(ceil_div64(Q, 4));
+  const Scatter scatter = sc ? *sc : Scatter();
 #define HB_RERANK(R)                                                                              \
   rerank_kernel<R><<<blocks, 128, 0, st>>>(q, b->feat_f32, b->feat_bf16, cand, n_chunks, q_pad, Q, \
                                            b->d, b->dpad, k, idx_offset, \
-                                           (b->flags & HB_BANK_L2) ? 1 : 0, out_scores, out_idx)
+                                           (b->flags & HB_BANK_L2) ? 1 : 0, out_scores, out_idx, scatter)
   if (kp == 32) HB_RERANK(1);
   else if (kp == 64) HB_RERANK(2);
   else if (kp == 128) HB_RERANK(4);
@@ -173,14 +217,13 @@ int rerank_launch(const Bank* b, const float* q, const float* qnorm_ws, int64_t 
 }
 
 // K3: merge G per-shard sorted top-k lists per query.  One warp per query; k <= 128.
+// List g of query qi starts at g * slot_stride + qi * k.
 template <int R>
-__global__ void __launch_bounds__(128)
-merge_topk_kernel(const float* __restrict__ ss, const int64_t* __restrict__ si, int G, int64_t Q,
-                  int k, float* __restrict__ out_scores, int64_t* __restrict__ out_idx) {
+__device__ __forceinline__ void
+merge_query(const float* ss, const int64_t* si, int G, int64_t slot_stride, int64_t qi, int k,
+            float* __restrict__ out_scores, int64_t* __restrict__ out_idx) {
   // keys here carry a 64-bit index, so sort (ordered score, then index) pairs held as two words
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t qi = static_cast<int64_t>(blockIdx.x) * 4 + warp;
-  if (qi >= Q) return;
+  const int lane = threadIdx.x & 31;
   // candidate slots: position in the gathered (G, k) list, encoded as g*k + j in the low word
   uint64_t top[R];
 #pragma unroll
@@ -194,11 +237,11 @@ merge_topk_kernel(const float* __restrict__ ss, const int64_t* __restrict__ si, 
       nxt[r] = 0ull;
       if (e < total) {
         const int g = e / k, j = e % k;
-        const int64_t off = (static_cast<int64_t>(g) * Q + qi) * k + j;
-        const int64_t id = si[off];
+        const int64_t off = static_cast<int64_t>(g) * slot_stride + qi * k + j;
+        const int64_t id = __ldcg(si + off);
         // position e doubles as the tie-break: shards hold ascending global rows, and within a
         // shard ties are already ordered by row, so smaller e <=> smaller global index
-        if (id >= 0) nxt[r] = make_key(ss[off], static_cast<uint32_t>(e));
+        if (id >= 0) nxt[r] = make_key(__ldcg(ss + off), static_cast<uint32_t>(e));
       }
     }
     warp_bitonic_sort<R, false>(nxt, lane);
@@ -216,14 +259,78 @@ merge_topk_kernel(const float* __restrict__ ss, const int64_t* __restrict__ si, 
       if (ok) {
         const uint32_t pos = key_row(top[r]);
         const int g = pos / k, j = pos % k;
-        const int64_t off = (static_cast<int64_t>(g) * Q + qi) * k + j;
-        id = si[off];
-        s = ss[off];
+        const int64_t off = static_cast<int64_t>(g) * slot_stride + qi * k + j;
+        id = __ldcg(si + off);
+        s = __ldcg(ss + off);
       }
       out_scores[qi * k + e] = s;
       out_idx[qi * k + e] = id;
     }
   }
+}
+
+template <int R>
+__global__ void __launch_bounds__(128)
+merge_topk_kernel(const float* __restrict__ ss, const int64_t* __restrict__ si, int G, int64_t Q,
+                  int k, float* __restrict__ out_scores, int64_t* __restrict__ out_idx) {
+  const int64_t qi = static_cast<int64_t>(blockIdx.x) * 4 + (threadIdx.x >> 5);
+  if (qi >= Q) return;
+  merge_query<R>(ss, si, G, Q * k, qi, k, out_scores, out_idx);
+}
+
+// K3x: the receiving half of the fused exchange.  Waits until every source rank has published
+// `step` in this rank's window (the rows were stored by the peers' K2b kernels over NVLink), then
+// merges the G lists of each query of the local slice.  The wait is bounded: after `timeout_ns`
+// the kernel records the missing rank and traps instead of hanging the GPU.
+template <int R>
+__global__ void __launch_bounds__(128)
+merge_window_kernel(const float* ss, const int64_t* si, const uint32_t* flags, uint32_t step, int G,
+                    int64_t slot_stride, int64_t rows, int k, unsigned long long timeout_ns,
+                    unsigned int* timeout_flag, float* __restrict__ out_scores,
+                    int64_t* __restrict__ out_idx) {
+  if (threadIdx.x < G) {
+    unsigned long long t0 = 0;
+    // flags count exchanges; a peer may already be one step ahead (its data for that step went
+    // to the other buffer), hence >= on the wrapped difference
+    while (static_cast<int32_t>(ld_acquire_sys(flags + threadIdx.x) - step) < 0) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      if (now - t0 > timeout_ns) {
+        atomicExch(timeout_flag, 0x80000000u | threadIdx.x);
+        __threadfence_system();
+        __trap();
+      }
+      __nanosleep(200);
+    }
+  }
+  __syncthreads();
+  const int64_t qi = static_cast<int64_t>(blockIdx.x) * 4 + (threadIdx.x >> 5);
+  if (qi >= rows) return;
+  merge_query<R>(ss, si, G, slot_stride, qi, k, out_scores, out_idx);
+}
+
+int merge_window_launch(const Exchange* x, uint32_t step, int64_t rows, int k, float* out_scores,
+                        int64_t* out_idx, cudaStream_t st) {
+  const uint8_t* win = x->window[x->rank];
+  const int parity = static_cast<int>(step & 1u);
+  const float* ss = reinterpret_cast<const float*>(win + x->scores_off(parity));
+  const int64_t* si = reinterpret_cast<const int64_t*>(win + x->idx_off(parity));
+  const uint32_t* flags = reinterpret_cast<const uint32_t*>(win);
+  // at least one CTA even for an empty slice: the wait keeps the ranks within one step of each
+  // other, which is what makes two window buffers enough
+  const unsigned blocks = static_cast<unsigned>(rows > 0 ? ceil_div64(rows, 4) : 1);
+  const unsigned long long timeout_ns = 60ull * 1000000000ull;
+  const int64_t stride = static_cast<int64_t>(x->slot_elems());
+#define HB_MERGE_WIN(R)                                                                         \
+  merge_window_kernel<R><<<blocks, 128, 0, st>>>(ss, si, flags, step, x->world, stride, rows, k, \
+                                                 timeout_ns, x->timeout_flag, out_scores, out_idx)
+  if (k <= 32) HB_MERGE_WIN(1);
+  else if (k <= 64) HB_MERGE_WIN(2);
+  else HB_MERGE_WIN(4);
+#undef HB_MERGE_WIN
+  HB_CHECK_CUDA(cudaGetLastError());
+  return HB_OK;
 }
 
 }  // namespace hb

@@ -599,13 +599,13 @@ static int dispatch_search(const Bank* b, int cg, int kp, const CUtensorMap& tma
 
 int rerank_launch(const Bank* b, const float* q, const float* qnorm_ws, int64_t Q, int k, int kp,
                   int n_chunks, int64_t q_pad, const uint64_t* cand, int64_t idx_offset,
-                  float* out_scores, int64_t* out_idx, cudaStream_t st);  // rerank.cu
+                  float* out_scores, int64_t* out_idx, const Scatter* sc, cudaStream_t st);  // rerank.cu
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-static int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_t idx_offset,
-                       float* out_scores, int64_t* out_idx, float* out_qnorm, float* dump, int cg_override,
-                       cudaStream_t st) {
+int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_t idx_offset,
+                float* out_scores, int64_t* out_idx, float* out_qnorm, float* dump, int cg_override,
+                cudaStream_t st, const Scatter* sc) {
   // measured on B200 (profiles/): CTA pairs (cta_group::2: half the B-operand shared-memory traffic
   // per SM) win at every bank size and feature dim; cta_group 1 stays selectable
   int cg = cg_override ? cg_override : (b->cfg_cta_group ? b->cfg_cta_group : 2);
@@ -688,9 +688,9 @@ static int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_
     b->timing_count++;
   }
   b->last_launches++;
-  if (out_scores == nullptr) return HB_OK;  // dump-only call
+  if (out_scores == nullptr && sc == nullptr) return HB_OK;  // dump-only call
 
-  rc = rerank_launch(b, q, qnorm, Q, k, kp, plan.n_chunks, q_pad, cand, idx_offset, out_scores, out_idx, st);
+  rc = rerank_launch(b, q, qnorm, Q, k, kp, plan.n_chunks, q_pad, cand, idx_offset, out_scores, out_idx, sc, st);
   if (rc != HB_OK) return rc;
   b->last_launches++;
   return HB_OK;
@@ -718,7 +718,7 @@ int hb_search(hb_bank_t* bank, const float* q_dev, int64_t Q, int k, int k_prime
   HB_REQUIRE(b->rows >= 1, "hb_search: the bank is empty");
   HB_CHECK_CUDA(cudaSetDevice(b->device));
   return hb::search_impl(b, q_dev, Q, k, k_prime, idx_offset, out_scores_dev, out_idx_dev, out_qnorm_dev,
-                         nullptr, 0, static_cast<cudaStream_t>(stream));
+                         nullptr, 0, static_cast<cudaStream_t>(stream), nullptr);
 }
 
 int hb_search_stats(hb_bank_t* bank, unsigned long long* stats_dev) {
@@ -814,7 +814,7 @@ int hb_search_dump_scores(hb_bank_t* bank, const float* q_dev, int64_t Q, float*
   HB_REQUIRE(Q * b->rows <= (int64_t(1) << 28), "hb_search_dump_scores: Q*rows too large for a debug dump");
   HB_CHECK_CUDA(cudaSetDevice(b->device));
   return hb::search_impl(b, q_dev, Q, 1, 64, 0, nullptr, nullptr, nullptr, out_dev, cta_group,
-                         static_cast<cudaStream_t>(stream));
+                         static_cast<cudaStream_t>(stream), nullptr);
 }
 
 }  // extern "C"

@@ -22,6 +22,7 @@ HB_ERR_STATE = -5
 
 HB_BANK_KEEP_F32 = 1
 HB_BANK_L2 = 2
+HB_EXCHANGE_HANDLE_BYTES = 64
 
 # every symbol include/hbird_b200.h declares: (name, restype, argtypes)
 _SIGNATURES = [
@@ -49,6 +50,14 @@ _SIGNATURES = [
     ("hb_plan_search", c_int, [c_int64, c_int64, c_int, c_int, c_int, POINTER(c_int)]),
     ("hb_search_dump_scores", c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p]),
     ("hb_merge_topk", c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    ("hb_exchange_create", c_int, [c_int, c_int, c_int, c_int64, c_int, POINTER(c_void_p)]),
+    ("hb_exchange_destroy", c_int, [c_void_p]),
+    ("hb_exchange_handle", c_int, [c_void_p, c_void_p, c_int]),
+    ("hb_exchange_connect", c_int, [c_void_p, c_void_p, c_int]),
+    ("hb_exchange_connect_local", c_int, [c_void_p, POINTER(c_void_p), c_int]),
+    ("hb_search_scatter", c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int64, POINTER(c_int64), c_void_p, c_void_p]),
+    ("hb_exchange_merge", c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    ("hb_exchange_slice_rows", c_int64, [c_void_p]),
     ("hb_label_transfer", c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p]),
     ("hb_upsample_argmax", c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     ("hb_decode_mask", c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),

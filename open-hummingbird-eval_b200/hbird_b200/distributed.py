@@ -1,9 +1,11 @@
 """One-process-per-GPU plumbing for a row-sharded memory bank.
 
 The bank is split row-wise: rank r owns a contiguous block of global rows.  Every rank searches
-every query against its shard (K2/K2b); the per-shard (score, global index) top-k lists are
-all-gathered over NCCL/NVLink and merged by the K3 kernel (ops.merge_topk) — the exchange step
-faiss.IndexShards performs on the host (search_faiss.py:53-63).  The label table is replicated by
+every query against its shard (K2/K2b).  The exchange step faiss.IndexShards performs on the host
+(search_faiss.py:53-63) is fused into the kernels around it: K2b stores each query's shard top-k
+into the window of the rank that post-processes it (NVLink peer stores, ops.ShardExchange) and
+that rank's merge kernel waits for all sources — no collective call.  Where peer mapping is not
+available the per-shard lists are all-gathered over NCCL and merged by K3 (ops.merge_topk).  The label table is replicated by
 an all-gather at build time; the (C, C) confusion matrix is all-reduced once at the end
 (eval_metrics.py:251-252).  All functions below are backend-agnostic torch.distributed calls, so
 the host logic is covered on CPU with gloo (tests/test_distributed_gloo.py).
@@ -81,6 +83,61 @@ def all_gather_topk(scores: torch.Tensor, idx: torch.Tensor, group=None) -> Tupl
     dist.all_gather_into_tensor(gs, scores.contiguous(), group=group)
     dist.all_gather_into_tensor(gi, idx.contiguous(), group=group)
     return gs.view(world, Q, k), gi.view(world, Q, k)
+
+
+def all_gather_bytes(blob: bytes, device, group=None) -> List[bytes]:
+    """Fixed-size byte strings of every rank, in rank order (IPC handles of the shard exchange)."""
+    _, world = dist_info(group)
+    if world == 1:
+        return [blob]
+    t = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(device)
+    out = torch.empty((world * len(blob),), dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(out, t, group=group)
+    raw = out.cpu().numpy().tobytes()
+    return [raw[r * len(blob):(r + 1) * len(blob)] for r in range(world)]
+
+
+def all_ranks_ok(ok: bool, device, group=None) -> bool:
+    """True only if `ok` holds on every rank (so that all ranks pick the same exchange path)."""
+    _, world = dist_info(group)
+    if world == 1:
+        return bool(ok)
+    t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return bool(int(t.item()))
+
+
+def query_split(n_images: int, queries_per_image: int, world: int) -> List[int]:
+    """qsplit for the fused exchange: rank p post-processes images split_range(n_images, world, p),
+    i.e. queries [qsplit[p], qsplit[p+1])."""
+    return [shard_bounds(n_images, world, p)[0] * queries_per_image for p in range(world)] + \
+        [n_images * queries_per_image]
+
+
+def connect_shard_exchange(slice_capacity: int, max_k: int, device: torch.device, group=None):
+    """Create this rank's ShardExchange window and map every peer's (CUDA IPC handles travel by
+    all-gather).  Returns None — on ALL ranks — if any rank cannot map its peers, in which case the
+    caller uses the NCCL all-gather + merge path."""
+    from . import ops
+
+    rank, world = dist_info(group)
+    xchg, ok = None, True
+    try:
+        xchg = ops.ShardExchange(rank, world, slice_capacity, max_k, device.index)
+        handle = xchg.handle()
+    except RuntimeError:
+        ok, handle = False, bytes(64)
+    handles = all_gather_bytes(handle, device, group)
+    if ok:
+        try:
+            xchg.connect(handles)
+        except RuntimeError:
+            ok = False
+    if not all_ranks_ok(ok, device, group):
+        if xchg is not None:
+            xchg.close()
+        return None
+    return xchg
 
 
 def split_range(n: int, world: int, rank: int) -> Tuple[int, int]:

@@ -218,19 +218,50 @@ class HbirdEvaluation:
             self.NN_algorithm = create_nn_backend(nn_method, self.feature_memory, n_neighbors=n_neighbours, **kwargs)
 
     # ------------------------------------------------------------------ evaluation
-    def _search(self, q: torch.Tensor):
-        """(scores, global idx, qnorm) for all queries; merges shards when world_size > 1."""
-        if self.nn_method == "b200":
-            scores, idx, qn = self.NN_algorithm.search_device(q, self.n_neighbours)
-        else:
+    def _search(self, q: torch.Tensor, n_images: int):
+        """(scores, global idx, qnorm, b0, b1): neighbours of the queries of images [b0, b1) — the
+        slice of the batch this rank post-processes (all of it when the bank is not sharded)."""
+        per_img = q.shape[0] // n_images
+        b0, b1 = hdist.split_range(n_images, self.world, self.rank)
+        sl = slice(b0 * per_img, b1 * per_img)
+        if self.nn_method != "b200":
             idx_np, dist_np = self.NN_algorithm.find_nearest_neighbors(q.cpu())
             idx = torch.as_tensor(idx_np.astype("int64"), device=self.device)
             scores = torch.as_tensor(dist_np, dtype=torch.float32, device=self.device)
             qn = torch.linalg.vector_norm(q, dim=1)
+        elif self.world > 1 and self._exchange_for(q.shape[0], n_images) is not None:
+            # fused exchange: K2b scatters over NVLink, the merge kernel waits for every shard
+            qsplit = hdist.query_split(n_images, per_img, self.world)
+            qn = self._xchg.search_scatter(self.bank, q, qsplit, self.n_neighbours, self.k_prime, self.idx_offset)
+            scores, idx = self._xchg.merge()
+            return scores, idx, qn[sl], b0, b1
+        else:
+            scores, idx, qn = self.NN_algorithm.search_device(q, self.n_neighbours)
         if self.world > 1:
             gs, gi = hdist.all_gather_topk(scores, idx)
             scores, idx = ops.merge_topk(gs, gi)
-        return scores, idx, qn
+        return scores[sl], idx[sl], qn[sl], b0, b1
+
+    def _exchange_for(self, n_queries: int, n_images: int):
+        """The ShardExchange, (re)built when a batch needs a larger window.  Every rank sees the
+        same batches, so every rank takes the same decision here."""
+        mode = str(self.nn_params.get("exchange", "p2p")).lower()
+        if mode not in ("p2p", "nccl"):
+            raise ValueError(f"nn_params['exchange']={mode!r} must be 'p2p' or 'nccl'")
+        if mode == "nccl" or getattr(self, "_xchg_failed", False):
+            return None
+        per_img = n_queries // n_images
+        need = -(-n_images // self.world) * per_img
+        xchg = getattr(self, "_xchg", None)
+        if xchg is None or xchg.slice_capacity < need or xchg.max_k < self.n_neighbours:
+            if xchg is not None:
+                # peers still map the old window: keep it alive instead of freeing it under them
+                self._retired_xchg = getattr(self, "_retired_xchg", []) + [xchg]
+            self._xchg = hdist.connect_shard_exchange(need, self.n_neighbours, self.device)
+            if self._xchg is None:
+                logger.warning("peer-memory exchange unavailable; using NCCL all-gather + merge")
+                self._xchg_failed = True
+        return self._xchg
 
     @torch.no_grad()
     def evaluate(self, val_loader, eval_spatial_resolution: int, return_knn_details: bool = False,
@@ -247,17 +278,14 @@ class HbirdEvaluation:
             feats = feats.to(torch.float32).contiguous()
             N, d = feats.shape[1], feats.shape[2]
             gt = ops.decode_mask(y.to(self.device, dtype=torch.float32).contiguous(), False).view(B, h, w)
-            scores, idx, qn = self._search(feats.view(B * N, d))
-            # after the merge every rank holds all results; each post-processes its image slice
-            b0, b1 = hdist.split_range(B, self.world, self.rank)
+            scores, idx, qn, b0, b1 = self._search(feats.view(B * N, d), B)
+            # each rank post-processes its image slice of the batch
             if b1 > b0:
-                sl = slice(b0 * N, b1 * N)
-                label_hat = ops.label_transfer(self.label_table, self.bank.patch_pixels, scores[sl], idx[sl],
-                                               qn[sl], BETA)
+                label_hat = ops.label_transfer(self.label_table, self.bank.patch_pixels, scores, idx, qn, BETA)
                 pred = ops.upsample_argmax(label_hat, b1 - b0, S, h, w)
                 metric.update(gt[b0:b1], pred)
                 if return_knn_details:
-                    kf, kl = self._gather_details(idx[sl])
+                    kf, kl = self._gather_details(idx)
                     k = self.n_neighbours
                     knns.append(kf.view(b1 - b0, N, k, -1).cpu())
                     knns_labels.append(kl.view(b1 - b0, N, k, -1).cpu())

@@ -192,6 +192,84 @@ def sample_patches(mask_u8: torch.Tensor, S: int, ps: int, num_classes: int, uni
     return sel
 
 
+class ShardExchange:
+    """K3x: one rank's end of the fused shard exchange (include/hbird_b200.h).  K2b stores each
+    query's shard top-k into the owner rank's window over NVLink; `merge` waits for all ranks and
+    merges the local slice.  Replaces all-gather + merge (faiss.IndexShards, search_faiss.py:53-63)."""
+
+    def __init__(self, rank: int, world: int, slice_capacity: int, max_k: int = 30, device: int = 0):
+        import ctypes
+
+        self.rank, self.world, self.device = int(rank), int(world), int(device)
+        self.slice_capacity, self.max_k = int(slice_capacity), int(max_k)
+        self._h = ctypes.c_void_p(0)
+        check(lib.hb_exchange_create(self.device, self.rank, self.world, self.slice_capacity, self.max_k,
+                                     ctypes.byref(self._h)))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib.hb_exchange_destroy(self._h)
+            self._h.value = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def handle(self) -> bytes:
+        """64-byte CUDA IPC handle of this rank's window, to be all-gathered by the host side."""
+        import ctypes
+
+        buf = ctypes.create_string_buffer(_capi.HB_EXCHANGE_HANDLE_BYTES)
+        check(lib.hb_exchange_handle(self._h, buf, _capi.HB_EXCHANGE_HANDLE_BYTES))
+        return buf.raw
+
+    def connect(self, handles) -> None:
+        """handles: the `world` handles in rank order (bytes each)."""
+        blob = b"".join(handles)
+        if len(blob) != self.world * _capi.HB_EXCHANGE_HANDLE_BYTES:
+            raise ValueError(f"expected {self.world} handles of {_capi.HB_EXCHANGE_HANDLE_BYTES} bytes")
+        check(lib.hb_exchange_connect(self._h, blob, self.world))
+
+    @staticmethod
+    def connect_local(exchanges) -> None:
+        """Wire exchanges created in this process (one per simulated rank, same device) together."""
+        import ctypes
+
+        arr = (ctypes.c_void_p * len(exchanges))(*[x._h.value for x in exchanges])
+        for x in exchanges:
+            check(lib.hb_exchange_connect_local(x._h, arr, len(exchanges)))
+
+    def search_scatter(self, bank: "MemoryBank", q: torch.Tensor, qsplit, k: int = 30, k_prime: int = 64,
+                       idx_offset: int = 0, return_qnorm: bool = True):
+        """K2 + K2b with the output rows of queries [qsplit[p], qsplit[p+1]) stored into rank p's
+        window.  Returns the (Q,) query norms (or None)."""
+        import ctypes
+
+        q = _require_cuda(q, "q", torch.float32)
+        if q.dim() != 2 or q.shape[1] != bank.d:
+            raise ValueError(f"queries must be (Q, {bank.d}), got {tuple(q.shape)}")
+        if len(qsplit) != self.world + 1:
+            raise ValueError(f"qsplit needs world+1 = {self.world + 1} entries")
+        Q = q.shape[0]
+        qn = torch.empty((Q,), dtype=torch.float32, device=q.device) if return_qnorm else None
+        arr = (ctypes.c_int64 * (self.world + 1))(*[int(v) for v in qsplit])
+        check(lib.hb_search_scatter(bank._h, self._h, ptr(q), Q, int(k), int(k_prime), int(idx_offset), arr,
+                                    ptr(qn), stream_ptr(q.device)))
+        self._k = int(k)
+        return qn
+
+    def merge(self):
+        """(scores fp32 (rows, k), idx int64 (rows, k)) of this rank's slice of the last scatter."""
+        rows = int(lib.hb_exchange_slice_rows(self._h))
+        dev = torch.device("cuda", self.device)
+        out_s = torch.empty((rows, self._k), dtype=torch.float32, device=dev)
+        out_i = torch.empty((rows, self._k), dtype=torch.int64, device=dev)
+        check(lib.hb_exchange_merge(self._h, ptr(out_s), ptr(out_i), stream_ptr(dev)))
+        return out_s, out_i
+
+
 def merge_topk(shard_scores: torch.Tensor, shard_idx: torch.Tensor):
     """K3: (G, Q, k) gathered per-shard results -> (Q, k) global top-k."""
     shard_scores = _require_cuda(shard_scores, "shard_scores", torch.float32)

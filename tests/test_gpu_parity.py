@@ -313,6 +313,57 @@ def test_merge_topk_equals_oracle_and_unsharded_search():
     whole.close()
 
 
+def test_fused_exchange_equals_allgather_merge_and_oracle():
+    """K3x on one GPU: G simulated ranks wired by pointer (hb_exchange_connect_local) run the same
+    kernels a multi-process run does — K2b scatters each query's shard top-k into the owner's
+    window, the merge kernel waits on the step flags.  Bit-identical to all-gather + K3 and to the
+    oracle's IndexShards merge; several steps alternate the two window buffers; one slice is empty."""
+    g = torch.Generator().manual_seed(9)
+    N, d, G, k = 23017, 64, 4, 30
+    rows = torch.randn((N, d), generator=g)
+    bounds = [N * r // G for r in range(G + 1)]
+    shards = [bank_from_rows(rows[bounds[r]:bounds[r + 1]].to(DEV)) for r in range(G)]
+    xs = [ops.ShardExchange(r, G, 200, k, 0) for r in range(G)]
+    ops.ShardExchange.connect_local(xs)
+    for step, qsplit in enumerate([[0, 100, 100, 231, 300], [0, 75, 150, 225, 300], [0, 200, 200, 200, 257]]):
+        Q = qsplit[-1]
+        q = (torch.randn((Q, d), generator=g) * 2).to(DEV)
+        ss, si = [], []
+        for r in range(G):
+            s, i, qn0 = shards[r].search(q, k, 64, idx_offset=bounds[r])
+            ss.append(s), si.append(i)
+        ms, mi = ops.merge_topk(torch.stack(ss), torch.stack(si))
+        oi, od = O.merge_shards(torch.stack(si).cpu().numpy(), torch.stack(ss).cpu().numpy(), k)
+        for r in range(G):
+            qn = xs[r].search_scatter(shards[r], q, qsplit, k, 64, idx_offset=bounds[r])
+            assert torch.equal(qn, qn0)
+        for r in range(G):
+            fs, fi = xs[r].merge()
+            a, b = qsplit[r], qsplit[r + 1]
+            assert fs.shape == (b - a, k)
+            assert torch.equal(fi, mi[a:b]) and torch.equal(fs, ms[a:b]), (step, r)
+            np.testing.assert_array_equal(fi.cpu().numpy(), oi[a:b])
+            np.testing.assert_array_equal(fs.cpu().numpy(), od[a:b])
+    with pytest.raises(ValueError, match="window capacity"):
+        xs[0].search_scatter(shards[0], torch.zeros((300, d), device=DEV), [0, 300, 300, 300, 300], k, 64)
+    with pytest.raises(RuntimeError, match="no scatter to merge"):
+        xs[0].merge()
+    for o in xs + shards:
+        o.close()
+
+
+def test_exchange_world1_is_plain_search():
+    g = torch.Generator().manual_seed(10)
+    rows, q = torch.randn((5000, 64), generator=g).to(DEV), torch.randn((130, 64), generator=g).to(DEV)
+    bank = bank_from_rows(rows)
+    s0, i0, qn0 = bank.search(q, 30, 64)
+    x = ops.ShardExchange(0, 1, 130, 30, 0)
+    qn = x.search_scatter(bank, q, [0, 130], 30, 64)
+    s, i = x.merge()
+    assert torch.equal(s, s0) and torch.equal(i, i0) and torch.equal(qn, qn0)
+    x.close(), bank.close()
+
+
 # ------------------------------------------------------------------ K4: label transfer, upsample + argmax
 def test_label_transfer_matches_reference_golden(case):
     cfg, g, data = case

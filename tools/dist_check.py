@@ -1,5 +1,6 @@
 """Run under torchrun (one rank per GPU): the row-sharded engine must reproduce the reference's
-golden result (tests/golden) — per-shard search, NCCL all-gather, K3 merge, replicated label table,
+golden result (tests/golden) — per-shard search, shard exchange (fused peer-memory exchange and
+the NCCL all-gather + K3 merge path, which must agree bit for bit), replicated label table,
 all-reduced confusion matrix."""
 import json
 import os
@@ -25,16 +26,26 @@ report = {}
 for name in ("voc_tiny", "ade_tiny"):
     cfg, g = load_golden(name)
     data = SyntheticSegmentationData(**cfg)
-    fe = FeatureExtractorSimple(data.model, data.ftr_extr_fn, data.S, data.d)
-    ev = HbirdEvaluation(fe, data.train_dataloader(), num_classes=data.C, n_neighbours=30, device=f"cuda:{local}",
-                         nn_method="b200", dataset_size=data.get_train_dataset_size())
-    miou = ev.evaluate(data.val_dataloader(), data.S, ignore_index=data.ignore_index)
-    conf = ev.last_confusion
-    rows = ev.shard_counts
-    good = abs(miou - float(g["miou"])) <= 5e-4 and conf.sum() == g["conf"].sum() and \
-        np.abs(conf - g["conf"]).sum() <= 2e-4 * conf.sum() and sum(rows) == g["feature_memory"].shape[0] and len(rows) == world
-    report[name] = {"miou": miou, "ref": float(g["miou"]), "shard_rows": rows, "ok": bool(good)}
-    ok = ok and good
+    confs = {}
+    for mode in ("p2p", "nccl"):
+        fe = FeatureExtractorSimple(data.model, data.ftr_extr_fn, data.S, data.d)
+        ev = HbirdEvaluation(fe, data.train_dataloader(), num_classes=data.C, n_neighbours=30,
+                             device=f"cuda:{local}", nn_method="b200", nn_params={"exchange": mode},
+                             dataset_size=data.get_train_dataset_size())
+        miou = ev.evaluate(data.val_dataloader(), data.S, ignore_index=data.ignore_index)
+        conf = ev.last_confusion
+        confs[mode] = conf
+        rows = ev.shard_counts
+        fused = getattr(ev, "_xchg", None) is not None
+        good = abs(miou - float(g["miou"])) <= 5e-4 and conf.sum() == g["conf"].sum() and \
+            np.abs(conf - g["conf"]).sum() <= 2e-4 * conf.sum() and sum(rows) == g["feature_memory"].shape[0] and \
+            len(rows) == world and fused == (mode == "p2p")
+        report[f"{name}_{mode}"] = {"miou": miou, "ref": float(g["miou"]), "shard_rows": rows,
+                                    "fused_exchange": fused, "ok": bool(good)}
+        ok = ok and good
+    same = bool((confs["p2p"] == confs["nccl"]).all())
+    report[f"{name}_paths_identical"] = same
+    ok = ok and same
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
