@@ -7,27 +7,50 @@
 namespace hb {
 
 constexpr int kPackWarps = 8;
+constexpr int kPackPrefetch = 256;  // mask pixels per patch prefetched into registers (16x16)
 
 // One warp per bank row.
 //   LABEL_MODE 0: histogram from the uint8 mask (B, S*ps, S*ps)
 //   LABEL_MODE 1: histogram recovered from fp32 soft labels (n, C)
 template <int LABEL_MODE>
-__global__ void __launch_bounds__(kPackWarps * 32)
+__global__ void __launch_bounds__(kPackWarps * 32, 4)
 pack_rows_kernel(const float* __restrict__ feats, const uint8_t* __restrict__ mask,
                  const float* __restrict__ soft, const int32_t* __restrict__ sel, int64_t n,
                  int d, int dpad, int C, int S, int ps, int pp, int normalise, int l2,
                  __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32,
                  uint16_t* __restrict__ out_hist) {
-  extern __shared__ uint32_t s_hist[];  // kPackWarps * C
+  extern __shared__ uint32_t s_hist[];  // kPackWarps * C, then kPackPrefetch pixel offsets
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t* hist = s_hist + warp * C;
   const int d4 = d >> 2;  // d % 4 == 0 is enforced on the host
   const int W = S * ps;  // pp = pixels per patch (ps*ps when a mask is given; the bank's value otherwise)
+  // offset of pixel t of a patch inside the mask, tabulated once per block (no per-pixel division)
+  uint32_t* pix_off = s_hist + kPackWarps * C;
+  if (LABEL_MODE == 0) {
+    for (int t = threadIdx.x; t < kPackPrefetch && t < pp; t += blockDim.x) pix_off[t] = (t / ps) * W + (t % ps);
+    __syncthreads();
+  }
 
   for (int64_t row = static_cast<int64_t>(blockIdx.x) * kPackWarps + warp; row < n;
        row += static_cast<int64_t>(gridDim.x) * kPackWarps) {
     const int64_t src = sel ? static_cast<int64_t>(sel[row]) : row;
     const float4* in4 = reinterpret_cast<const float4*>(feats + src * d);
+
+    // ---- label record, part 1: issue the mask loads of the first kPackPrefetch pixels now so
+    // that their latency overlaps the feature pass ----
+    int cls_pre[kPackPrefetch / 32];
+    const uint8_t* mrow = nullptr;
+    if (LABEL_MODE == 0) {
+      const int S2 = S * S;
+      const int b = static_cast<int>(src / S2), p = static_cast<int>(src % S2);
+      const int py = p / S, px = p % S;
+      mrow = mask + (static_cast<int64_t>(b) * W + py * ps) * W + px * ps;
+#pragma unroll
+      for (int u = 0; u < kPackPrefetch / 32; ++u) {
+        const int t = u * 32 + lane;
+        cls_pre[u] = t < pp ? static_cast<int>(__ldg(mrow + pix_off[t])) : -1;
+      }
+    }
 
     // ---- features: ||f||_2, then f / ||f||_2 (true division, no epsilon) ----
     float ss = 0.f;
@@ -73,18 +96,21 @@ pack_rows_kernel(const float* __restrict__ feats, const uint8_t* __restrict__ ma
     if (LABEL_MODE == 0) {
       for (int c = lane; c < C; c += 32) hist[c] = 0;
       __syncwarp();
-      const int S2 = S * S;
-      const int b = static_cast<int>(src / S2), p = static_cast<int>(src % S2);
-      const int py = p / S, px = p % S;
-      const uint8_t* mrow = mask + (static_cast<int64_t>(b) * W + py * ps) * W + px * ps;
-      for (int t0 = 0; t0 < pp; t0 += 32) {
+#pragma unroll
+      for (int u = 0; u < kPackPrefetch / 32; ++u) {
+        if (u * 32 < pp) {
+          const int cls = cls_pre[u];
+          // warp-aggregate equal classes, one shared-memory add per distinct class
+          const unsigned peers = __match_any_sync(0xffffffffu, cls);
+          if (cls >= 0 && cls < C && lane == (__ffs(peers) - 1)) hist[cls] += __popc(peers);
+          __syncwarp();
+        }
+      }
+      for (int t0 = kPackPrefetch; t0 < pp; t0 += 32) {  // patches larger than 16x16
         const int t = t0 + lane;
-        const bool valid = t < pp;
-        int cls = -1;
-        if (valid) cls = mrow[(t / ps) * W + (t % ps)];
-        // warp-aggregate equal classes, one shared-memory add per distinct class
+        const int cls = t < pp ? static_cast<int>(mrow[(t / ps) * W + (t % ps)]) : -1;
         const unsigned peers = __match_any_sync(0xffffffffu, cls);
-        if (valid && cls < C && lane == (__ffs(peers) - 1)) hist[cls] += __popc(peers);
+        if (cls >= 0 && cls < C && lane == (__ffs(peers) - 1)) hist[cls] += __popc(peers);
         __syncwarp();
       }
       for (int c = lane; c < C; c += 32) out_hist[row * C + c] = static_cast<uint16_t>(hist[c]);
@@ -208,7 +234,7 @@ static int launch_pack(Bank* b, const float* feats, const uint8_t* mask, const f
   int64_t blocks = ceil_div64(n, kPackWarps);
   const int64_t max_blocks = static_cast<int64_t>(b->num_sms) * 8;
   if (blocks > max_blocks) blocks = max_blocks;
-  const size_t smem = sizeof(uint32_t) * kPackWarps * b->C;
+  const size_t smem = sizeof(uint32_t) * (kPackWarps * b->C + kPackPrefetch);
   __nv_bfloat16* ob = b->feat_bf16 + row0 * b->dpad;
   float* of = b->feat_f32 ? b->feat_f32 + row0 * b->d : nullptr;
   uint16_t* oh = b->label_hist + row0 * b->C;

@@ -74,7 +74,9 @@ def test_decode_mask_all_byte_values_exact():
         np.testing.assert_array_equal(got, O.decode_mask(y, remap).astype(np.uint8))
 
 
-@pytest.mark.parametrize("C,n,ignore", [(21, 1_000_003, 255), (151, 2_000_017, 0), (3, 7, 255), (6, 12288, None), (200, 65536, 255)])
+# the last two sizes are large enough for the 64-pixels-per-thread variant of the kernel
+@pytest.mark.parametrize("C,n,ignore", [(21, 1_000_003, 255), (151, 2_000_017, 0), (3, 7, 255), (6, 12288, None), (200, 65536, 255),
+                                        (21, 20_000_033, 255), (151, 10_000_019, 0)])
 def test_confusion_bit_exact_vs_oracle(C, n, ignore):
     rng = np.random.default_rng(C + n)
     gt = rng.integers(0, min(C + 4, 256), size=n).astype(np.uint8)
