@@ -194,7 +194,7 @@ int hb_search_scatter(hb_bank_t* bank, hb_exchange_t* xchg, const float* q_dev, 
                       float* out_qnorm_dev, void* stream);
 /* Outputs: fp32 / int64 (rows, k) for this rank's slice of the last scatter, sorted descending,
  * global indices; rows = hb_exchange_slice_rows().  A peer that never arrives makes the kernel
- * trap after 60 s instead of hanging the GPU. */
+ * trap after 10 min instead of hanging the GPU. */
 int hb_exchange_merge(hb_exchange_t* xchg, float* out_scores_dev, int64_t* out_idx_dev, void* stream);
 int64_t hb_exchange_slice_rows(const hb_exchange_t* xchg);
 

@@ -320,7 +320,7 @@ int merge_window_launch(const Exchange* x, uint32_t step, int64_t rows, int k, f
   // at least one CTA even for an empty slice: the wait keeps the ranks within one step of each
   // other, which is what makes two window buffers enough
   const unsigned blocks = static_cast<unsigned>(rows > 0 ? ceil_div64(rows, 4) : 1);
-  const unsigned long long timeout_ns = 60ull * 1000000000ull;
+  const unsigned long long timeout_ns = 600ull * 1000000000ull;  // hang protection only
   const int64_t stride = static_cast<int64_t>(x->slot_elems());
 #define HB_MERGE_WIN(R)                                                                         \
   merge_window_kernel<R><<<blocks, 128, 0, st>>>(ss, si, flags, step, x->world, stride, rows, k, \

@@ -608,3 +608,59 @@ def test_full_size_recall_vs_exact_fp32(big_bank):
         rel = ((s - ref.values).abs() / ref.values.abs()).max().item()
         assert rel <= 1e-3
     big_bank.configure_search(cta_group=0)
+
+
+# ------------------------------------------------------------------ BASELINE configs[2] size: 10.24 M x 768
+def test_cfg3_size_recall_and_self_retrieval():
+    """The full cfg3 bank (10,240,000 x 768: 15.7 GB bf16 + 31.5 GB fp32 in HBM).  The CPU oracle
+    cannot run at this size, so the checks are: recall@30 / scores against an
+    exact fp32 torch matmul (TF32 off) on a query subsample, and self-retrieval of scaled bank rows
+    over a full batch of 21,904 queries."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 80 << 30:
+        pytest.skip("needs 80 GB of free HBM")
+    N, d, slab = 10_240_000, 768, 1_024_000
+    g = torch.Generator(device=DEV).manual_seed(21)
+    bank = ops.MemoryBank(d, 1, 1, N, 0, True)
+    one = torch.ones((slab, 1), device=DEV)
+    for a in range(0, N, slab):
+        bank.append_soft(torch.randn((slab, d), generator=g, device=DEV), one, normalise=True)
+    bank.finalize()
+    assert bank.rows == N
+
+    # (1) exact fp32 reference on 256 random queries, slab by slab
+    q = torch.randn((256, d), generator=g, device=DEV) * 3
+    torch.backends.cuda.matmul.allow_tf32 = False
+    best_s = torch.full((256, 30), -float("inf"), device=DEV)
+    best_i = torch.full((256, 30), -1, dtype=torch.int64, device=DEV)
+    for a in range(0, N, slab):
+        f, _ = bank.export(a, slab, labels=False)
+        t = (q @ f.T).topk(30, dim=1)
+        cs, ci = torch.cat([best_s, t.values], 1), torch.cat([best_i, t.indices + a], 1)
+        o = cs.topk(30, dim=1)
+        best_s, best_i = o.values, ci.gather(1, o.indices)
+        del f, t
+    s, i, _ = bank.search(q, 30, 64)
+    hit = (i.unsqueeze(2) == best_i.unsqueeze(1)).any(2).float().mean().item()
+    assert hit >= 0.999
+    assert ((s - best_s).abs() / best_s.abs()).max().item() <= 1e-3
+
+    # (2) one full batch (16 images x 1369 patches) of scaled bank rows
+    Q = 21904
+    pick = torch.randint(0, N, (Q,), generator=g, device=DEV)
+    scale = torch.rand((Q, 1), generator=g, device=DEV) * 5 + 0.5
+    qq = torch.empty((Q, d), device=DEV)
+    for a in range(0, N, slab):  # gather the picked rows slab by slab
+        m = (pick >= a) & (pick < a + slab)
+        if bool(m.any()):
+            f, _ = bank.export(a, slab, labels=False)
+            qq[m] = f[pick[m] - a]
+            del f
+    qq *= scale
+    s2, i2, _ = bank.search(qq, 30, 64)
+    assert bool((i2[:, 0] == pick).all())
+    assert torch.allclose(s2[:, 0], scale[:, 0], rtol=1e-5)
+    assert bool((s2[:, :-1] >= s2[:, 1:]).all())
+    bank.close()
+    del bank
+    torch.cuda.empty_cache()
