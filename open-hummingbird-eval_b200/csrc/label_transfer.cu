@@ -13,11 +13,10 @@ constexpr int kMaxK = 128;
 
 // One warp per query.
 __global__ void __launch_bounds__(256)
-label_transfer_kernel(const uint16_t* __restrict__ table, int64_t table_rows, int C, float inv_unused,
+label_transfer_kernel(const uint16_t* __restrict__ table, int64_t table_rows, int C,
                       int pp, const float* __restrict__ scores, const int64_t* __restrict__ idx,
                       const float* __restrict__ qnorm, int64_t Q, int k, float beta,
                       float* __restrict__ out) {
-  (void)inv_unused;
   __shared__ float s_w[8][kMaxK];
   __shared__ int64_t s_i[8][kMaxK];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -124,7 +123,7 @@ int hb_label_transfer(const uint16_t* label_table_dev, int64_t table_rows, int C
   HB_REQUIRE(label_table_dev && scores_dev && idx_dev && qnorm_dev && out_label_hat_dev, "hb_label_transfer: NULL pointer");
   const unsigned blocks = static_cast<unsigned>(hb::ceil_div64(Q, 8));
   hb::label_transfer_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      label_table_dev, table_rows, C, 0.f, patch_pixels, scores_dev, idx_dev, qnorm_dev, Q, k, beta, out_label_hat_dev);
+      label_table_dev, table_rows, C, patch_pixels, scores_dev, idx_dev, qnorm_dev, Q, k, beta, out_label_hat_dev);
   HB_CHECK_CUDA(cudaGetLastError());
   return HB_OK;
 }

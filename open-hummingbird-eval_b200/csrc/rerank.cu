@@ -30,8 +30,6 @@ __device__ __forceinline__ void warp_bitonic_sort(uint64_t (&a)[R], int lane) {
         }
       } else {
         // partner lives in this lane, register slot r ^ (j/32)
-        constexpr int dummy = 0;
-        (void)dummy;
         const int jr = j >> 5;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -194,10 +192,9 @@ rerank_kernel(const float* __restrict__ q, const float* __restrict__ bank_f32,
   }
 }
 
-int rerank_launch(const Bank* b, const float* q, const float* qnorm_ws, int64_t Q, int k, int kp,
+int rerank_launch(const Bank* b, const float* q, int64_t Q, int k, int kp,
                   int n_chunks, int64_t q_pad, const uint64_t* cand, int64_t idx_offset,
                   float* out_scores, int64_t* out_idx, const Scatter* sc, cudaStream_t st) {
-  (void)qnorm_ws;
   const unsigned blocks = static_cast<unsigned>(ceil_div64(Q, 4));
   const Scatter scatter = sc ? *sc : Scatter();
 #define HB_RERANK(R)                                                                              \

@@ -597,7 +597,7 @@ static int dispatch_search(const Bank* b, int cg, int kp, const CUtensorMap& tma
   return HB_ERR_INVALID;
 }
 
-int rerank_launch(const Bank* b, const float* q, const float* qnorm_ws, int64_t Q, int k, int kp,
+int rerank_launch(const Bank* b, const float* q, int64_t Q, int k, int kp,
                   int n_chunks, int64_t q_pad, const uint64_t* cand, int64_t idx_offset,
                   float* out_scores, int64_t* out_idx, const Scatter* sc, cudaStream_t st);  // rerank.cu
 
@@ -690,7 +690,7 @@ int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_t idx_o
   b->last_launches++;
   if (out_scores == nullptr && sc == nullptr) return HB_OK;  // dump-only call
 
-  rc = rerank_launch(b, q, qnorm, Q, k, kp, plan.n_chunks, q_pad, cand, idx_offset, out_scores, out_idx, sc, st);
+  rc = rerank_launch(b, q, Q, k, kp, plan.n_chunks, q_pad, cand, idx_offset, out_scores, out_idx, sc, st);
   if (rc != HB_OK) return rc;
   b->last_launches++;
   return HB_OK;

@@ -202,7 +202,7 @@ class HbirdEvaluation:
     def _create_nn(self, n_neighbours: int = 30, nn_method: str = "b200", **kwargs) -> None:
         """hbird_eval.py:267-281, through the registry."""
         if nn_method == "b200":
-            kw = {k: v for k, v in kwargs.items() if k not in ("k_prime", "keep_f32", "gpu_ids")}
+            kw = {k: v for k, v in kwargs.items() if k not in ("k_prime", "keep_f32", "gpu_ids", "exchange")}
             measure = str(kw.pop("distance_measure", "dot_product")).lower()
             if measure not in ("dot_product", "l2", "euclidean"):
                 raise ValueError(f"Unsupported distance measure: {measure}")  # search_faiss.py:48

@@ -422,6 +422,22 @@ def test_engine_end_to_end_matches_reference(case):
     np.testing.assert_array_equal(ev.label_memory.numpy(), g["label_memory"])
 
 
+def test_engine_nn_params_follow_reference_semantics():
+    """nn_params reach the backend as ctor kwargs (hbird_eval.py:267-281).  distance_measure="l2" on
+    the engine's unit-norm bank selects the same neighbours as the inner product (the reference
+    discards the distances, :628), k_prime=128 is the strict mode, unknown measures raise."""
+    cfg, g = load_golden("voc_tiny")
+    data = SyntheticSegmentationData(**cfg)
+    base = run_engine(data).evaluate(data.val_dataloader(), data.S, ignore_index=data.ignore_index)
+    for params in ({"distance_measure": "l2"}, {"k_prime": 128}, {"k_prime": 32, "exchange": "nccl"}):
+        m = run_engine(data, nn_params=params).evaluate(data.val_dataloader(), data.S, ignore_index=data.ignore_index)
+        assert abs(m - base) <= 1e-6 and abs(m - float(g["miou"])) <= 5e-4, params
+    with pytest.raises(ValueError, match="Unsupported distance measure"):
+        run_engine(data, nn_params={"distance_measure": "cosine"})
+    with pytest.raises(ValueError, match="k_prime"):
+        run_engine(data, nn_params={"k_prime": 48})
+
+
 @pytest.mark.parametrize("name", CASES)
 def test_engine_bounded_memory_matches_reference(name):
     cfg, g = load_golden(name + "_bounded")
