@@ -428,6 +428,27 @@ def main():
     d2h = conf_host.numel() * 8
     e2e_value = world * Q / (ms_e2e * 1e-3)
 
+    # ---- the reference's literal plugin call (search_faiss.py:83-90): pageable host queries in,
+    # host (indices, distances) out, every copy synchronous -- what a third party using the ABC gets
+    plugin = None
+    if world == 1:
+        import time
+
+        from hbird_b200 import NearestNeighborSearchB200
+
+        nn = NearestNeighborSearchB200(None, n_neighbors=K_NEIGH, bank=bank, k_prime=K_PRIME, gpu_ids=[device.index])
+        q_host = [q.cpu() for q, _ in ring[:2]]
+        nn.find_nearest_neighbors(q_host[0])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n_calls = max(3, min(10, args.steps))
+        for i in range(n_calls):
+            idx_np, dist_np = nn.find_nearest_neighbors(q_host[i % 2])
+        dt = (time.perf_counter() - t0) / n_calls
+        plugin = {"value": Q / dt, "unit": "patch-queries/s", "ms_per_call": dt * 1e3, "calls": n_calls,
+                  "call": "NearestNeighborSearchB200.find_nearest_neighbors(q_cpu) -> (indices, distances) ndarrays",
+                  "h2d_bytes_per_call": Q * w["d"] * 4, "d2h_bytes_per_call": int(idx_np.nbytes + dist_np.nbytes)}
+
     # ---- row-sharded bank: per-shard search -> NCCL all-gather -> merge kernel (strong scaling)
     sharded = None
     if world > 1 and not args.no_sharded:
@@ -508,6 +529,7 @@ def main():
             "parity": parity,
             "e2e": {"value": e2e_value, "unit": "patch-queries/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "plugin_call": plugin,
             "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step,
             "clocks": clocks,

@@ -123,7 +123,7 @@ def connect_shard_exchange(slice_capacity: int, max_k: int, device: torch.device
     rank, world = dist_info(group)
     xchg, ok = None, True
     try:
-        xchg = ops.ShardExchange(rank, world, slice_capacity, max_k, device.index)
+        xchg = ops.ShardExchange(rank, world, slice_capacity, max_k, device.index or 0)
         handle = xchg.handle()
     except RuntimeError:
         ok, handle = False, bytes(64)

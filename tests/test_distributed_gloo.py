@@ -52,6 +52,17 @@ def _worker(rank, world, port, out_dir):
         conf = torch.full((C, C), rank + 1, dtype=torch.int64)
         dist.all_reduce(conf, op=dist.ReduceOp.SUM)
         assert int(conf[0, 0]) == sum(range(1, world + 1))
+        # plumbing of the fused shard exchange: handles travel as fixed-size byte strings, every rank
+        # takes the same p2p-or-NCCL decision, and the query split matches the image split
+        blobs = hdist.all_gather_bytes(bytes([rank]) * 64, torch.device("cpu"))
+        assert blobs == [bytes([r]) * 64 for r in range(world)]
+        assert hdist.all_ranks_ok(True, torch.device("cpu")) is True
+        assert hdist.all_ranks_ok(rank != 1, torch.device("cpu")) is False
+        qs = hdist.query_split(7, 196, world)
+        assert qs[0] == 0 and qs[-1] == 7 * 196 and len(qs) == world + 1
+        assert (qs[rank], qs[rank + 1]) == tuple(196 * v for v in hdist.split_range(7, world, rank))
+        # no CUDA device here: window creation fails on every rank and all ranks fall back together
+        assert hdist.connect_shard_exchange(100, 30, torch.device("cpu")) is None
         b0, b1 = hdist.split_range(7, world, rank)
         open(os.path.join(out_dir, f"ok{rank}"), "w").write(f"{b0},{b1}")
     finally:
@@ -71,3 +82,7 @@ def test_single_process_helpers():
     s, i = torch.zeros(4, 3), torch.zeros(4, 3, dtype=torch.int64)
     gs, gi = hdist.all_gather_topk(s, i)
     assert gs.shape == (1, 4, 3) and gi.shape == (1, 4, 3)
+    assert hdist.query_split(16, 1369, 8) == [2 * 1369 * r for r in range(9)]
+    assert hdist.query_split(3, 10, 4) == [0, 0, 10, 20, 30]  # fewer images than ranks: empty slices
+    assert hdist.all_gather_bytes(b"x" * 64, torch.device("cpu")) == [b"x" * 64]
+    assert hdist.all_ranks_ok(False, torch.device("cpu")) is False
