@@ -71,3 +71,22 @@ def test_no_cpu_fallback_without_gpu():
         NearestNeighborSearchB200(torch.zeros(4, 64))
     with pytest.raises(RuntimeError):
         HbirdEvaluation(torch.nn.Identity(), [], 3, device="cpu")
+
+
+def test_exchange_argument_checks_are_host_only():
+    """hb_exchange_* validate their arguments before touching the device: bad arguments give
+    HB_ERR_INVALID (ValueError) even on a CPU box; a valid request without a GPU fails loudly."""
+    h = ctypes.c_void_p(0)
+    lib = _capi.lib
+    assert lib.hb_exchange_create(0, 2, 2, 100, 30, ctypes.byref(h)) == _capi.HB_ERR_INVALID  # rank >= world
+    assert "rank" in _capi.last_error()
+    assert lib.hb_exchange_create(0, 0, 99, 100, 30, ctypes.byref(h)) == _capi.HB_ERR_INVALID  # world > 16
+    assert lib.hb_exchange_create(0, 0, 2, 0, 30, ctypes.byref(h)) == _capi.HB_ERR_INVALID     # no capacity
+    assert lib.hb_exchange_create(0, 0, 2, 100, 500, ctypes.byref(h)) == _capi.HB_ERR_INVALID  # k > 128
+    assert h.value is None
+    assert lib.hb_exchange_destroy(None) == 0
+    assert lib.hb_exchange_slice_rows(None) == -1
+    assert lib.hb_exchange_merge(None, None, None, None) == _capi.HB_ERR_INVALID
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            ops.ShardExchange(0, 2, 100, 30, 0)
