@@ -57,12 +57,12 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   return v;
 }
 
-template <int R>
+template <int R, bool L2>
 __device__ __forceinline__ void
 rerank_query(const float* __restrict__ q, const float* __restrict__ bank_f32,
              const __nv_bfloat16* __restrict__ bank_bf16, const uint64_t* __restrict__ cand,
              int n_chunks, int64_t q_pad, int64_t Q, int d, int dpad, int k, int64_t idx_offset,
-             int l2, float* __restrict__ out_scores, int64_t* __restrict__ out_idx, const Scatter& sc) {
+             float* __restrict__ out_scores, int64_t* __restrict__ out_idx, const Scatter& sc) {
   constexpr int KP = 32 * R;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t qi = static_cast<int64_t>(blockIdx.x) * 4 + warp;
@@ -109,7 +109,7 @@ rerank_query(const float* __restrict__ q, const float* __restrict__ bank_f32,
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const float4 m = __ldg(reinterpret_cast<const float4*>(bank_f32 + static_cast<int64_t>(rows[u]) * d) + i);
-            if (l2) {
+            if (L2) {
               const float a = qv.x - m.x, b2 = qv.y - m.y, c = qv.z - m.z, e = qv.w - m.w;
               acc[u] -= a * a + b2 * b2 + c * c + e * e;  // -||q-x||^2: larger is nearer
             } else {
@@ -125,7 +125,7 @@ rerank_query(const float* __restrict__ q, const float* __restrict__ bank_f32,
             const uint2 pk = __ldg(reinterpret_cast<const uint2*>(bank_bf16 + static_cast<int64_t>(rows[u]) * dpad) + i);
             const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&pk.x);
             const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&pk.y);
-            if (l2) {
+            if (L2) {
               const float a = qv.x - __low2float(lo), b2 = qv.y - __high2float(lo);
               const float c = qv.z - __low2float(hi), e = qv.w - __high2float(hi);
               acc[u] -= a * a + b2 * b2 + c * c + e * e;
@@ -161,21 +161,21 @@ rerank_query(const float* __restrict__ q, const float* __restrict__ bank_f32,
       const bool ok = exact[r] != 0ull;
       // L2 banks report squared distances, ascending (GpuIndexFlatL2, search_faiss.py:45-46,89)
       const float v = ok ? key_score(exact[r]) : -INFINITY;
-      os[e] = l2 ? -v : v;
+      os[e] = L2 ? -v : v;
       oi[e] = ok ? static_cast<int64_t>(key_row(exact[r])) + idx_offset : -1;
     }
   }
 }
 
-template <int R>
+template <int R, bool L2>
 __global__ void __launch_bounds__(128)
 rerank_kernel(const float* __restrict__ q, const float* __restrict__ bank_f32,
               const __nv_bfloat16* __restrict__ bank_bf16, const uint64_t* __restrict__ cand,
               int n_chunks, int64_t q_pad, int64_t Q, int d, int dpad, int k, int64_t idx_offset,
-              int l2, float* __restrict__ out_scores, int64_t* __restrict__ out_idx,
+              float* __restrict__ out_scores, int64_t* __restrict__ out_idx,
               const __grid_constant__ Scatter sc) {
-  rerank_query<R>(q, bank_f32, bank_bf16, cand, n_chunks, q_pad, Q, d, dpad, k, idx_offset, l2,
-                  out_scores, out_idx, sc);
+  rerank_query<R, L2>(q, bank_f32, bank_bf16, cand, n_chunks, q_pad, Q, d, dpad, k, idx_offset,
+                      out_scores, out_idx, sc);
   if (sc.world) {
     // Fused exchange: every thread's peer stores are ordered before the CTA counts itself done;
     // the last CTA of the grid then raises this rank's arrival flag on every peer.
@@ -198,9 +198,14 @@ int rerank_launch(const Bank* b, const float* q, int64_t Q, int k, int kp,
   const unsigned blocks = static_cast<unsigned>(ceil_div64(Q, 4));
   const Scatter scatter = sc ? *sc : Scatter();
 #define HB_RERANK(R)                                                                              \
-  rerank_kernel<R><<<blocks, 128, 0, st>>>(q, b->feat_f32, b->feat_bf16, cand, n_chunks, q_pad, Q, \
-                                           b->d, b->dpad, k, idx_offset, \
-                                           (b->flags & HB_BANK_L2) ? 1 : 0, out_scores, out_idx, scatter)
+  do {                                                                                            \
+    if (b->flags & HB_BANK_L2)                                                                    \
+      rerank_kernel<R, true><<<blocks, 128, 0, st>>>(q, b->feat_f32, b->feat_bf16, cand, n_chunks, q_pad, Q, \
+                                                     b->d, b->dpad, k, idx_offset, out_scores, out_idx, scatter); \
+    else                                                                                          \
+      rerank_kernel<R, false><<<blocks, 128, 0, st>>>(q, b->feat_f32, b->feat_bf16, cand, n_chunks, q_pad, Q, \
+                                                      b->d, b->dpad, k, idx_offset, out_scores, out_idx, scatter); \
+  } while (0)
   if (kp == 32) HB_RERANK(1);
   else if (kp == 64) HB_RERANK(2);
   else if (kp == 128) HB_RERANK(4);
