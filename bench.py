@@ -487,6 +487,7 @@ def main():
         if xchg is not None:
             torch.cuda.synchronize()
             dist.barrier()
+            hdist.close_shard_exchange(xchg)
         shard_bank.close()
 
     # ---- CPU baseline beside it (rank 0, N = 1 only)

@@ -187,6 +187,10 @@ int hb_exchange_destroy(hb_exchange_t* xchg);
 int hb_exchange_handle(hb_exchange_t* xchg, void* handle_out, int handle_bytes);
 int hb_exchange_connect(hb_exchange_t* xchg, const void* handles, int n_handles);
 int hb_exchange_connect_local(hb_exchange_t* xchg, hb_exchange_t* const* peers, int n_peers);
+/* Orderly teardown across processes: every rank disconnects (unmaps its peers' windows), the host
+ * side runs a barrier, then every rank destroys (frees its own window).  hb_exchange_destroy alone
+ * disconnects first, which is enough when the peers are already gone. */
+int hb_exchange_disconnect(hb_exchange_t* xchg);
 /* qsplit_host: world+1 ascending int64 on the HOST, qsplit[0] = 0, qsplit[world] = Q.
  * out_qnorm_dev: optional fp32 (Q,) query norms, as hb_search. */
 int hb_search_scatter(hb_bank_t* bank, hb_exchange_t* xchg, const float* q_dev, int64_t Q, int k,

@@ -64,13 +64,26 @@ int hb_exchange_create(int device, int rank, int world, int64_t slice_capacity, 
   return HB_OK;
 }
 
-int hb_exchange_destroy(hb_exchange_t* xchg) {
+int hb_exchange_disconnect(hb_exchange_t* xchg) {
   if (!xchg) return HB_OK;
   Exchange* x = reinterpret_cast<Exchange*>(xchg);
   cudaSetDevice(x->device);
   cudaDeviceSynchronize();
-  for (int p = 0; p < x->world; ++p)
-    if (p != x->rank && x->ipc_opened[p] && x->window[p]) cudaIpcCloseMemHandle(x->window[p]);
+  for (int p = 0; p < x->world; ++p) {
+    if (p == x->rank) continue;
+    if (x->ipc_opened[p] && x->window[p]) cudaIpcCloseMemHandle(x->window[p]);
+    x->ipc_opened[p] = false;
+    x->window[p] = nullptr;
+  }
+  (void)cudaGetLastError();
+  x->connected = x->world == 1;
+  return HB_OK;
+}
+
+int hb_exchange_destroy(hb_exchange_t* xchg) {
+  if (!xchg) return HB_OK;
+  Exchange* x = reinterpret_cast<Exchange*>(xchg);
+  hb_exchange_disconnect(xchg);
   if (x->window[x->rank]) cudaFree(x->window[x->rank]);
   if (x->done_ctas) cudaFree(x->done_ctas);
   (void)cudaGetLastError();

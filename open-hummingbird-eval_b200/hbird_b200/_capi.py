@@ -55,6 +55,7 @@ _SIGNATURES = [
     ("hb_exchange_handle", c_int, [c_void_p, c_void_p, c_int]),
     ("hb_exchange_connect", c_int, [c_void_p, c_void_p, c_int]),
     ("hb_exchange_connect_local", c_int, [c_void_p, POINTER(c_void_p), c_int]),
+    ("hb_exchange_disconnect", c_int, [c_void_p]),
     ("hb_search_scatter", c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int64, POINTER(c_int64), c_void_p, c_void_p]),
     ("hb_exchange_merge", c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     ("hb_exchange_slice_rows", c_int64, [c_void_p]),

@@ -140,6 +140,17 @@ def connect_shard_exchange(slice_capacity: int, max_k: int, device: torch.device
     return xchg
 
 
+def close_shard_exchange(xchg, group=None) -> None:
+    """Orderly teardown: unmap peers everywhere, barrier, then free the own window."""
+    if xchg is None:
+        return
+    xchg.disconnect()
+    _, world = dist_info(group)
+    if world > 1:
+        dist.barrier(group=group)
+    xchg.close()
+
+
 def split_range(n: int, world: int, rank: int) -> Tuple[int, int]:
     """The slice of a batch (images or queries) a rank post-processes after the merge."""
     return shard_bounds(n, world, rank)

@@ -217,6 +217,11 @@ class ShardExchange:
         except Exception:
             pass
 
+    def disconnect(self) -> None:
+        """Unmap the peers' windows (first half of an orderly multi-process teardown)."""
+        if self._h.value:
+            check(lib.hb_exchange_disconnect(self._h))
+
     def handle(self) -> bytes:
         """64-byte CUDA IPC handle of this rank's window, to be all-gathered by the host side."""
         import ctypes
