@@ -263,6 +263,15 @@ class HbirdEvaluation:
                 self._xchg_failed = True
         return self._xchg
 
+    def close(self) -> None:
+        """Release the HBM bank and, collectively on all ranks, the shard-exchange windows."""
+        for x in getattr(self, "_retired_xchg", []) + [getattr(self, "_xchg", None)]:
+            hdist.close_shard_exchange(x)
+        self._retired_xchg, self._xchg = [], None
+        if self.bank is not None:
+            self.bank.close()
+            self.bank = None
+
     @torch.no_grad()
     def evaluate(self, val_loader, eval_spatial_resolution: int, return_knn_details: bool = False,
                  ignore_index: int = 255):

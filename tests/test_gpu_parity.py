@@ -428,7 +428,10 @@ def test_engine_nn_params_follow_reference_semantics():
     discards the distances, :628), k_prime=128 is the strict mode, unknown measures raise."""
     cfg, g = load_golden("voc_tiny")
     data = SyntheticSegmentationData(**cfg)
-    base = run_engine(data).evaluate(data.val_dataloader(), data.S, ignore_index=data.ignore_index)
+    ev = run_engine(data)
+    base = ev.evaluate(data.val_dataloader(), data.S, ignore_index=data.ignore_index)
+    ev.close()
+    assert ev.bank is None
     for params in ({"distance_measure": "l2"}, {"k_prime": 128}, {"k_prime": 32, "exchange": "nccl"}):
         m = run_engine(data, nn_params=params).evaluate(data.val_dataloader(), data.S, ignore_index=data.ignore_index)
         assert abs(m - base) <= 1e-6 and abs(m - float(g["miou"])) <= 5e-4, params

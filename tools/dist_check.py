@@ -43,6 +43,7 @@ for name in ("voc_tiny", "ade_tiny"):
         report[f"{name}_{mode}"] = {"miou": miou, "ref": float(g["miou"]), "shard_rows": rows,
                                     "fused_exchange": fused, "ok": bool(good)}
         ok = ok and good
+        ev.close()
     same = bool((confs["p2p"] == confs["nccl"]).all())
     report[f"{name}_paths_identical"] = same
     ok = ok and same
