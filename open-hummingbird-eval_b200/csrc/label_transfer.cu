@@ -43,18 +43,22 @@ label_transfer_kernel(const uint16_t* __restrict__ table, int64_t table_rows, in
     sum += e;
   }
   sum = warp_sum(sum);
+  // softmax weights; a missing neighbour (id < 0) keeps weight 0 and reads row 0, so the gather
+  // loop below has no branch and its loads can be issued ahead of the arithmetic
+  for (int j = lane; j < k; j += 32) {
+    const bool ok = s_i[warp][j] >= 0;
+    s_w[warp][j] = ok ? s_w[warp][j] / sum : 0.f;
+    if (!ok) s_i[warp][j] = 0;
+  }
   __syncwarp();
   const float fpp = static_cast<float>(pp);
   for (int c = lane; c < C; c += 32) {
     float acc = 0.f;
-#pragma unroll 6
+#pragma unroll 10
     for (int j = 0; j < k; ++j) {
-      const int64_t id = s_i[warp][j];
-      if (id >= 0) {
-        // soft label = histogram / pixels-per-patch (one_hot(...).mean(3), hbird_eval.py:319-320)
-        const float lab = static_cast<float>(__ldg(table + id * C + c)) / fpp;
-        acc += (s_w[warp][j] / sum) * lab;
-      }
+      // soft label = histogram / pixels-per-patch (one_hot(...).mean(3), hbird_eval.py:319-320)
+      const float lab = static_cast<float>(__ldg(table + s_i[warp][j] * C + c)) / fpp;
+      acc += s_w[warp][j] * lab;
     }
     out[qi * C + c] = acc;
   }
