@@ -154,38 +154,85 @@ class HbirdEvaluation:
         return ops.sample_patches(mask, S, ps, num_classes, uniform, K)
 
     def _save_memory(self) -> None:
-        """hbird_eval.py:371-378 — same on-disk format: fp32 (N,d) and (N,C) tensors."""
+        """hbird_eval.py:371-378 — same on-disk format: fp32 (N,d) and (N,C) tensors.  With a sharded
+        bank rank 0 collects the shards (in global row order) and writes the single pair of files."""
         if self.f_mem_p is None and self.l_mem_p is None:
             return
-        f, l = self.bank.export(features=self.f_mem_p is not None, labels=self.l_mem_p is not None)
-        if self.f_mem_p is not None:
-            torch.save(f.cpu(), self.f_mem_p)
-        if self.l_mem_p is not None:
-            torch.save(l.cpu(), self.l_mem_p)
+        want_f, want_l = self.f_mem_p is not None, self.l_mem_p is not None
+        if self.world == 1:
+            f, l = self.bank.export(features=want_f, labels=want_l)
+            f, l = (f.cpu() if want_f else None), (l.cpu() if want_l else None)
+        else:
+            f, l = self._collect_memory_on_rank0(want_f, want_l)
+        if self.rank == 0:
+            if want_f:
+                torch.save(f, self.f_mem_p)
+            if want_l:
+                torch.save(l, self.l_mem_p)
+        if self.world > 1:
+            torch.distributed.barrier()
+
+    def _collect_memory_on_rank0(self, want_f: bool, want_l: bool, slab: int = 1 << 18):
+        """Stream every shard to rank 0 in slabs (point-to-point over NCCL); rank 0 returns the CPU
+        tensors (total_rows, d) / (total_rows, C) in global row order, the others (None, None)."""
+        import torch.distributed as dist
+
+        d, C = self.bank.d, self.num_classes
+        fs, ls = [], []
+        for r, n in enumerate(self.shard_counts):
+            for a in range(0, n, slab):
+                m = min(slab, n - a)
+                if self.rank == r:
+                    f, l = self.bank.export(a, m, features=want_f, labels=want_l)
+                    if r != 0:
+                        if want_f:
+                            dist.send(f, dst=0)
+                        if want_l:
+                            dist.send(l, dst=0)
+                elif self.rank == 0:
+                    f = torch.empty((m, d), dtype=torch.float32, device=self.device) if want_f else None
+                    l = torch.empty((m, C), dtype=torch.float32, device=self.device) if want_l else None
+                    if want_f:
+                        dist.recv(f, src=r)
+                    if want_l:
+                        dist.recv(l, src=r)
+                if self.rank == 0:
+                    if want_f:
+                        fs.append(f.cpu())
+                    if want_l:
+                        ls.append(l.cpu())
+        if self.rank != 0:
+            return None, None
+        return (torch.cat(fs) if want_f else None), (torch.cat(ls) if want_l else None)
 
     def load_memory(self) -> bool:
         """hbird_eval.py:380-400 — reload the tensors written by _save_memory (fp32 (N, d) unit rows and
-        (N, C) soft labels) and rebuild the HBM bank and the search backend from them."""
+        (N, C) soft labels) and rebuild the HBM bank and the search backend from them.  With
+        world_size > 1 every rank takes its contiguous row range of the files (a row-sharded bank)."""
         import os
 
         if not (self.f_mem_p and self.l_mem_p and os.path.isfile(self.f_mem_p) and os.path.isfile(self.l_mem_p)):
             logger.warning("Memory files not found or paths not provided; skipping load.")
             return False
-        if self.world > 1:
-            raise NotImplementedError("load_memory rebuilds an unsharded bank; run it on one GPU")
-        f = torch.load(self.f_mem_p).to(torch.float32)
-        l = torch.load(self.l_mem_p).to(torch.float32)
+        f = torch.load(self.f_mem_p, mmap=True)
+        l = torch.load(self.l_mem_p, mmap=True)
+        if f.shape[0] != l.shape[0]:
+            raise ValueError(f"feature memory has {f.shape[0]} rows, label memory {l.shape[0]}")
+        a, b = hdist.shard_bounds(f.shape[0], self.world, self.rank)
         pp = self.bank.patch_pixels
-        new_bank = ops.MemoryBank(f.shape[1], l.shape[1], pp, max(1, f.shape[0]), self.device.index, self.keep_f32)
+        new_bank = ops.MemoryBank(f.shape[1], l.shape[1], pp, max(1, b - a), self.device.index, self.keep_f32)
         step = 1 << 20
-        for a in range(0, f.shape[0], step):
-            new_bank.append_soft(f[a:a + step].to(self.device).contiguous(), l[a:a + step].to(self.device).contiguous(),
-                                 normalise=False)
+        for s0 in range(a, b, step):
+            s1 = min(b, s0 + step)
+            new_bank.append_soft(f[s0:s1].to(self.device, dtype=torch.float32).contiguous(),
+                                 l[s0:s1].to(self.device, dtype=torch.float32).contiguous(), normalise=False)
         new_bank.finalize()
         self.bank.close()
         self.bank = new_bank
-        self.shard_counts, self.idx_offset, self.total_rows = [new_bank.rows], 0, new_bank.rows
-        self.label_table = new_bank.label_table()
+        counts = hdist.gather_counts(new_bank.rows, self.device)
+        self.shard_counts, self.total_rows = counts, sum(counts)
+        self.idx_offset = hdist.offsets_from_counts(counts)[self.rank]
+        self.label_table = hdist.all_gather_rows(new_bank.label_table(), counts)
         self.__dict__.pop("_export_cache", None)
         self._create_nn(self.n_neighbours, nn_method=self.nn_method, **self.nn_params)
         return True

@@ -44,6 +44,30 @@ for name in ("voc_tiny", "ade_tiny"):
                                     "fused_exchange": fused, "ok": bool(good)}
         ok = ok and good
         ev.close()
+    # memory files with a sharded bank: rank 0 writes ONE (N, d) / (N, C) pair (hbird_eval.py:371-378);
+    # reloading re-shards it by contiguous row ranges and must reproduce the evaluation
+    tmp = f"/tmp/hb_dist_check_{os.environ.get('MASTER_PORT', '0')}_{name}"
+    if rank == 0:
+        os.makedirs(tmp, exist_ok=True)
+    dist.barrier()
+    fe = FeatureExtractorSimple(data.model, data.ftr_extr_fn, data.S, data.d)
+    ev = HbirdEvaluation(fe, data.train_dataloader(), num_classes=data.C, n_neighbours=30, device=f"cuda:{local}",
+                         nn_method="b200", dataset_size=data.get_train_dataset_size(),
+                         f_mem_p=os.path.join(tmp, "f.pt"), l_mem_p=os.path.join(tmp, "l.pt"))
+    saved_f, saved_l = torch.load(os.path.join(tmp, "f.pt")).numpy(), torch.load(os.path.join(tmp, "l.pt")).numpy()
+    order_s = np.lexsort(np.concatenate([saved_f, saved_l], 1).T[::-1])
+    order_g = np.lexsort(np.concatenate([g["feature_memory"], g["label_memory"]], 1).T[::-1])
+    files_ok = saved_f.shape == g["feature_memory"].shape and \
+        np.abs(saved_f[order_s] - g["feature_memory"][order_g]).max() <= 2e-7 and \
+        np.array_equal(saved_l[order_s], g["label_memory"][order_g])
+    reloaded = ev.load_memory()
+    miou2 = ev.evaluate(data.val_dataloader(), data.S, ignore_index=data.ignore_index)
+    reload_ok = bool(reloaded) and sum(ev.shard_counts) == g["feature_memory"].shape[0] and \
+        abs(miou2 - float(g["miou"])) <= 5e-4
+    report[f"{name}_save_load"] = {"files_ok": bool(files_ok), "reload_ok": bool(reload_ok), "miou": miou2,
+                                   "shard_rows": ev.shard_counts}
+    ok = ok and bool(files_ok) and reload_ok
+    ev.close()
     same = bool((confs["p2p"] == confs["nccl"]).all())
     report[f"{name}_paths_identical"] = same
     ok = ok and same
