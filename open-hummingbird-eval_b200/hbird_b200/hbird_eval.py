@@ -336,16 +336,19 @@ class HbirdEvaluation:
             gt = ops.decode_mask(y.to(self.device, dtype=torch.float32).contiguous(), False).view(B, h, w)
             scores, idx, qn, b0, b1 = self._search(feats.view(B * N, d), B)
             # each rank post-processes its image slice of the batch
+            label_hat = None
             if b1 > b0:
                 label_hat = ops.label_transfer(self.label_table, self.bank.patch_pixels, scores, idx, qn, BETA)
                 pred = ops.upsample_argmax(label_hat, b1 - b0, S, h, w)
                 metric.update(gt[b0:b1], pred)
-                if return_knn_details:
-                    kf, kl = self._gather_details(idx)
-                    k = self.n_neighbours
-                    knns.append(kf.view(b1 - b0, N, k, -1).cpu())
-                    knns_labels.append(kl.view(b1 - b0, N, k, -1).cpu())
-                    knns_ca.append(label_hat.view(b1 - b0, N, -1).cpu())
+            if return_knn_details:
+                k = self.n_neighbours
+                if label_hat is None:
+                    label_hat = torch.empty((0, C), dtype=torch.float32, device=self.device)
+                kf, kl, lh = self._gather_details(idx, label_hat, B, N)
+                knns.append(kf.view(-1, N, k, d).cpu())
+                knns_labels.append(kl.view(-1, N, k, C).cpu())
+                knns_ca.append(lh.view(-1, N, C).cpu())
         jac, tp, fp, fn, _, _ = metric.compute(is_global_zero=True, sync_distributed=self.world > 1,
                                                return_reordered=False)
         self.last_confusion = metric.confusion_matrix()
@@ -354,16 +357,29 @@ class HbirdEvaluation:
                          "knns_ca_labels": torch.cat(knns_ca)}
         return jac
 
-    def _gather_details(self, idx: torch.Tensor):
-        """return_knn_details support (hbird_eval.py:229-232,255-262): neighbour features / soft
-        labels gathered from the exported fp32 bank (single-GPU banks only)."""
+    def _gather_details(self, idx: torch.Tensor, label_hat: torch.Tensor, n_images: int, per_img: int):
+        """return_knn_details support (hbird_eval.py:229-232,255-262): neighbour features, neighbour
+        soft labels and label_hat for the WHOLE batch, as the reference returns them.  With a sharded
+        bank every rank contributes the feature rows it owns (one all-reduce of the (Q, k, d) tensor:
+        exactly one rank holds each row, the others add zeros) and the slices of idx / label_hat are
+        all-gathered; the soft labels come from the replicated label table."""
         if self.world > 1:
-            raise NotImplementedError("return_knn_details is supported for an unsharded bank")
+            counts = [hdist.split_range(n_images, self.world, r) for r in range(self.world)]
+            counts = [(b - a) * per_img for a, b in counts]
+            idx = hdist.all_gather_rows(idx, counts)
+            label_hat = hdist.all_gather_rows(label_hat, counts)
         if not hasattr(self, "_export_cache"):
-            self._export_cache = self.bank.export()
-        f, l = self._export_cache
-        flat = idx.reshape(-1).clamp_min(0)
-        return f.index_select(0, flat), l.index_select(0, flat)
+            self._export_cache = self.bank.export(labels=False)[0]
+        f = self._export_cache
+        flat = idx.reshape(-1)
+        local = flat - self.idx_offset
+        mine = (local >= 0) & (local < self.bank.rows)
+        kf = f.index_select(0, local.clamp(0, self.bank.rows - 1)) * mine.unsqueeze(1).to(f.dtype)
+        if self.world > 1:
+            torch.distributed.all_reduce(kf)
+        table = torch.as_tensor(self.label_table, device=self.device)
+        kl = table.index_select(0, flat.clamp_min(0)).to(torch.float32) / float(self.bank.patch_pixels)
+        return kf, kl, label_hat
 
 
 def hbird_evaluation(model, d_model: int, patch_size: int, dataset_name, data_dir: str, batch_size: int = 64,

@@ -32,16 +32,24 @@ for name in ("voc_tiny", "ade_tiny"):
         ev = HbirdEvaluation(fe, data.train_dataloader(), num_classes=data.C, n_neighbours=30,
                              device=f"cuda:{local}", nn_method="b200", nn_params={"exchange": mode},
                              dataset_size=data.get_train_dataset_size())
-        miou = ev.evaluate(data.val_dataloader(), data.S, ignore_index=data.ignore_index)
+        miou, det = ev.evaluate(data.val_dataloader(), data.S, return_knn_details=True, ignore_index=data.ignore_index)
         conf = ev.last_confusion
         confs[mode] = conf
+        # details cover the whole val set on every rank, as the reference returns them; global row ids
+        # are ordered rank-major here, so compare the gathered neighbour FEATURES and labels, not ids
+        ref_knn_f = g["feature_memory"][g["knn_idx"]].reshape(det["knns"].shape)
+        ref_knn_l = g["label_memory"][g["knn_idx"]].reshape(det["knns_labels"].shape)
+        same_f = (np.abs(det["knns"].numpy() - ref_knn_f).max(-1) <= 1e-6).mean()
+        same_l = (np.abs(det["knns_labels"].numpy() - ref_knn_l).max(-1) <= 1e-6).mean()
+        details_ok = same_f >= 0.999 and same_l >= 0.999 and \
+            np.abs(det["knns_ca_labels"].numpy() - g["label_hat"]).max() <= 2e-5
         rows = ev.shard_counts
         fused = getattr(ev, "_xchg", None) is not None
         good = abs(miou - float(g["miou"])) <= 5e-4 and conf.sum() == g["conf"].sum() and \
             np.abs(conf - g["conf"]).sum() <= 2e-4 * conf.sum() and sum(rows) == g["feature_memory"].shape[0] and \
-            len(rows) == world and fused == (mode == "p2p")
+            len(rows) == world and fused == (mode == "p2p") and bool(details_ok)
         report[f"{name}_{mode}"] = {"miou": miou, "ref": float(g["miou"]), "shard_rows": rows,
-                                    "fused_exchange": fused, "ok": bool(good)}
+                                    "fused_exchange": fused, "details_ok": bool(details_ok), "ok": bool(good)}
         ok = ok and good
         ev.close()
     # memory files with a sharded bank: rank 0 writes ONE (N, d) / (N, C) pair (hbird_eval.py:371-378);
