@@ -193,6 +193,31 @@ def kats():
     return out
 
 
+def matrix_kats():
+    """PredsmIoU of the reference on random pixel streams with rectangular class counts and every
+    matching mode (incl. precision_based), stored as confusion matrix + results."""
+    from hbird.utils.eval_metrics import PredsmIoU
+
+    rng = np.random.default_rng(7)
+    out = []
+    for (P, G, n, ignore) in ((8, 5, 5000, 255), (5, 8, 5000, 255), (21, 21, 20000, 255), (12, 12, 3000, 0)):
+        gt = rng.integers(0, G, size=n)
+        # predictions correlated with gt through a random relabelling, plus noise and out-of-range ids
+        relabel = rng.integers(0, P, size=G)
+        pred = np.where(rng.random(n) < 0.7, relabel[gt], rng.integers(0, P + 1, size=n))
+        if ignore == 255:
+            gt = np.where(rng.random(n) < 0.03, 255, gt)
+        for mode in ("hungarian", "many_to_one", "many_to_one_precision", "linear_probe"):
+            m = PredsmIoU(P, G, device=torch.device("cpu"), ignore_index=ignore)
+            m.update(torch.from_numpy(gt), torch.from_numpy(pred))
+            miou, tp, fp, fn, _, bg = m.compute(True, many_to_one=mode.startswith("many_to_one"),
+                                                precision_based=mode.endswith("precision"),
+                                                linear_probe=mode == "linear_probe", return_reordered=False)
+            out.append(dict(P=P, G=G, ignore=ignore, mode=mode, conf=m._conf_mat.tolist(), miou=miou,
+                            tp=tp, fp=fp, fn=fn, bg=bg))
+    return out
+
+
 def plugin_fixture():
     """The reference plugin class itself (hbird/nn/search_faiss.py:6-90) on an UN-normalised bank,
     for both distance measures: pins the (indices, distances) order and the L2 convention
@@ -217,9 +242,15 @@ if __name__ == "__main__":
     sys.path.insert(0, REF)
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(1)  # deterministic summation order in the fixtures
+    if "--kats-only" in sys.argv:
+        with open(os.path.join(GOLD, "ref_kats_matrix.json"), "w") as f:
+            json.dump(matrix_kats(), f)
+        sys.exit(0)
     np.savez_compressed(os.path.join(GOLD, "ref_plugin_metrics.npz"), **plugin_fixture())
     if "--plugin-only" in sys.argv:
         sys.exit(0)
+    with open(os.path.join(GOLD, "ref_kats_matrix.json"), "w") as f:
+        json.dump(matrix_kats(), f)
     for name, cfg in CONFIGS.items():
         res = run_reference(cfg, faiss)
         np.savez_compressed(os.path.join(GOLD, f"ref_{name}.npz"), cfg=json.dumps(cfg), **res)

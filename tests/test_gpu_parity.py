@@ -92,6 +92,29 @@ def test_confusion_bit_exact_vs_oracle(C, n, ignore):
     np.testing.assert_array_equal(conf.cpu().numpy(), ref)
 
 
+def test_predsmiou_rectangular_classes_and_modes_vs_oracle():
+    """PredsmIoU (K5 + host math) with num_pred != num_gt, int64 inputs with out-of-range ids, all
+    matching modes — against the oracle restatement of eval_metrics.py:73-288."""
+    from hbird_b200 import PredsmIoU
+
+    rng = np.random.default_rng(12)
+    for P, G, ignore in ((8, 5, 255), (5, 8, 255), (12, 12, 0)):
+        n = 100_003
+        gt = rng.integers(0, G, size=n)
+        pred = np.where(rng.random(n) < 0.6, rng.integers(0, P, size=G)[gt], rng.integers(-1, P + 2, size=n))
+        gt = np.where(rng.random(n) < 0.03, 255, gt)
+        m = PredsmIoU(P, G, device=DEV, ignore_index=ignore)
+        half = n // 2
+        m.update(torch.from_numpy(gt[:half]), torch.from_numpy(pred[:half]))         # CPU int64 in
+        m.update(torch.from_numpy(gt[half:]).to(DEV), torch.from_numpy(pred[half:]).to(DEV))
+        conf = O.confusion_matrix(gt, pred, G, P, ignore)
+        np.testing.assert_array_equal(m.confusion_matrix(), conf)
+        for kw in (dict(), dict(many_to_one=True), dict(many_to_one=True, precision_based=True), dict(linear_probe=True)):
+            miou, tp, fp, fn, _, bg = m.compute(True, return_reordered=False, **kw)
+            omiou, otp, ofp, ofn, obg = O.miou_from_confusion(conf, **kw)
+            assert miou == pytest.approx(omiou, abs=1e-12) and (tp, fp, fn) == (otp, ofp, ofn) and bg == pytest.approx(obg)
+
+
 def test_confusion_matches_reference_golden(case):
     cfg, g, data = case
     conf = torch.zeros((data.C, data.C), dtype=torch.int64, device=DEV)

@@ -100,3 +100,22 @@ def test_parse_nn_params_follows_reference_cli_coercion():
     with pytest.raises(ValueError, match="KEY=VALUE"):
         parse_nn_params(["novalue"])
     assert {"b200", "faiss", "scann"} <= set(nn_method_choices())
+
+
+def test_metric_math_rectangular_and_precision_modes_match_reference():
+    """tests/golden/ref_kats_matrix.json: the reference's PredsmIoU on random pixel streams with
+    num_pred != num_gt, ignore_index 255 / 0 and all four matching modes (eval_metrics.py:112-288).
+    Both the product's host math and the oracle must reproduce it."""
+    kats = json.load(open(os.path.join(GOLDEN, "ref_kats_matrix.json")))
+    assert len(kats) == 16
+    for k in kats:
+        conf = np.array(k["conf"], dtype=np.int64)
+        assert conf.shape == (k["G"], k["P"])
+        kw = dict(many_to_one=k["mode"].startswith("many_to_one"), precision_based=k["mode"].endswith("precision"),
+                  linear_probe=k["mode"] == "linear_probe")
+        miou, tp, fp, fn, _, bg = miou_from_confusion(conf, **kw)
+        assert miou == pytest.approx(k["miou"], abs=1e-12), (k["P"], k["G"], k["mode"])
+        assert (tp, fp, fn) == (k["tp"], k["fp"], k["fn"]) and bg == pytest.approx(k["bg"])
+        omiou, otp, ofp, ofn, obg = O.miou_from_confusion(conf, **kw)
+        assert omiou == pytest.approx(k["miou"], abs=1e-12) and (otp, ofp, ofn) == (k["tp"], k["fp"], k["fn"])
+        assert obg == pytest.approx(k["bg"])
