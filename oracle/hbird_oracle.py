@@ -114,8 +114,8 @@ def _topk_rows(s: np.ndarray, kk: int) -> Tuple[np.ndarray, np.ndarray]:
     return np.take_along_axis(part, order, axis=1), np.take_along_axis(ps, order, axis=1)
 
 
-def search_exact_ip(q: np.ndarray, bank: np.ndarray, k: int, block: int = 4096,
-                    threads: Optional[int] = None) -> Tuple[np.ndarray, np.ndarray]:
+def search_exact_ip(q: np.ndarray, bank: np.ndarray, k: int, block: Optional[int] = None,
+                    threads: Optional[int] = None, scratch_bytes: float = 6e9) -> Tuple[np.ndarray, np.ndarray]:
     """hbird/nn/search_faiss.py:39-41,83-90 — GpuIndexFlatIP.search: exact top-k by inner product
     of raw queries with the unit-norm bank, descending; faiss pads with (-inf, -1) when N < k.
     Returns (indices int64 (Q, k), distances fp32 (Q, k)) — indices first, as the plugin does.
@@ -131,10 +131,15 @@ def search_exact_ip(q: np.ndarray, bank: np.ndarray, k: int, block: int = 4096,
     idx = np.full((Q, k), -1, dtype=np.int64)
     dist = np.full((Q, k), -np.inf, dtype=F32)
     threads = threads or os.cpu_count() or 1
+    if block is None:
+        # a block of B query rows costs ~16 B per (row, bank row): fp32 scores, their negation and the
+        # int64 argpartition output; keep that within `scratch_bytes` of host memory (48 rows at
+        # N = 10.24 M, 366 at N = 1.024 M) so that the baseline cannot exhaust the host
+        block = int(max(8, min(4096, scratch_bytes / (16.0 * max(N, 1)))))
     for a in range(0, Q, block):
         s = q[a:a + block] @ bank.T
         rows = s.shape[0]
-        nsplit = max(1, min(threads, rows // 8))
+        nsplit = max(1, min(threads, rows // 2))
         if nsplit == 1:
             i, d = _topk_rows(s, kk)
             idx[a:a + rows, :kk], dist[a:a + rows, :kk] = i, d
