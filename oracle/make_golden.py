@@ -11,7 +11,12 @@ inner-product flat index.  Everything else (_create_memory, _sample_features,
 _find_nearest_key_to_query, _cross_attention, interpolate/argmax, PredsmIoU) is the reference's own
 code, executed verbatim on the CPU.
 
-    python oracle/make_golden.py            # writes tests/golden/ref_*.npz and ref_kats.json
+    python oracle/make_golden.py                # all fixtures under tests/golden/:
+                                                #   ref_{voc,ade}_tiny[_bounded].npz  whole-path runs of HbirdEvaluation
+                                                #   ref_plugin_metrics.npz            NearestNeighborSearchFaiss, IP and L2
+                                                #   ref_kats.json, ref_kats_matrix.json  PredsmIoU known answers
+    python oracle/make_golden.py --plugin-only  # only ref_plugin_metrics.npz
+    python oracle/make_golden.py --kats-only    # only ref_kats_matrix.json
 """
 import json
 import os
