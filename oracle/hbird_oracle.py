@@ -12,7 +12,8 @@ IndexFlatIP) and committed under `tests/golden/`; `tests/test_oracle_golden.py` 
 function below against those fixtures and against the PredsmIoU known-answer vectors.
 
 Each function cites the reference lines it restates (paths relative to the reference root).
-Arithmetic is float32 wherever the reference's is.
+Arithmetic is float32 wherever the reference's is.  `hbird_oracle.c` (loaded by `c_oracle.py`) is an
+independent plain-C twin of the byte/integer steps, held to the same fixtures.
 """
 from __future__ import annotations
 

@@ -1,0 +1,80 @@
+"""The plain-C oracle (oracle/hbird_oracle.c, built with gcc) against the golden fixtures of the
+unmodified reference and against the numpy oracle.  Integer / byte work must agree bit for bit;
+the scalar fp32 search and label transfer within summation-order tolerance.  CPU only."""
+import numpy as np
+import pytest
+
+from helpers import batches_np, load_golden, recall
+from hbird_b200.data import SyntheticSegmentationData
+from oracle import c_oracle as C
+from oracle import hbird_oracle as O
+
+CASES = ["voc_tiny", "ade_tiny"]
+
+
+@pytest.fixture(params=CASES)
+def case(request):
+    cfg, g = load_golden(request.param)
+    return cfg, g, SyntheticSegmentationData(**cfg)
+
+
+def test_decode_mask_every_byte_value():
+    y = (np.arange(256, dtype=np.float32) / np.float32(255)).astype(np.float32)
+    for remap in (False, True):
+        np.testing.assert_array_equal(C.decode_mask(y, remap), O.decode_mask(y, remap).astype(np.uint8))
+
+
+def test_soft_labels_and_eval_masks_match_reference(case):
+    cfg, g, data = case
+    hists = []
+    for _, y in batches_np(data, data.train_dataloader()):
+        mask = C.decode_mask(y, True).reshape(y.shape[0], y.shape[-2], y.shape[-1])
+        hists.append(C.patch_histogram(mask, data.S, data.ps, data.C))
+    hist = np.concatenate(hists)
+    # the reference's label_memory is one_hot(...).mean(3) = counts / ps^2, exact in fp32
+    np.testing.assert_array_equal(hist.astype(np.float32) / np.float32(data.ps * data.ps), g["label_memory"])
+    gt = np.concatenate([C.decode_mask(y, False) for _, y in batches_np(data, data.val_dataloader())])
+    np.testing.assert_array_equal(gt, g["gt"])
+
+
+def test_confusion_matches_reference_and_numpy_oracle(case):
+    cfg, g, data = case
+    conf = C.confusion(g["gt"], g["pred"], data.C, data.C, data.ignore_index)
+    np.testing.assert_array_equal(conf, g["conf"])
+    rng = np.random.default_rng(3)
+    gt = rng.integers(0, 256, size=100_003).astype(np.uint8)
+    pred = rng.integers(0, 12, size=100_003).astype(np.uint8)
+    for G, P, ign in ((9, 7, 255), (7, 9, 0), (12, 12, None)):
+        np.testing.assert_array_equal(C.confusion(gt, pred, G, P, ign), O.confusion_matrix(gt, pred, G, P, ign))
+
+
+def test_upsample_argmax_matches_reference_bit_for_bit(case):
+    """Fed the reference's own label_hat, the C bilinear + argmax reproduces the reference's
+    prediction maps exactly (same fp32 operation order as ATen's upsample_bilinear2d)."""
+    cfg, g, data = case
+    H = data.S * data.ps
+    n_img = g["pred"].shape[0]
+    pred = C.upsample_argmax(g["label_hat"].reshape(n_img, data.S * data.S, data.C), n_img, data.S, H, H)
+    np.testing.assert_array_equal(pred, g["pred"].reshape(n_img, H, H))
+    np.testing.assert_array_equal(pred.reshape(n_img, 1, H, H), O.predict_map(g["label_hat"].reshape(n_img, data.S * data.S, data.C), data.S, H, H))
+
+
+def test_search_and_label_transfer_match_reference(case):
+    cfg, g, data = case
+    q = np.concatenate([f.reshape(-1, f.shape[-1]) for f, _ in batches_np(data, data.val_dataloader())])
+    idx, dist = C.search_ip(q, g["feature_memory"], 30)
+    np.testing.assert_allclose(dist, g["knn_dist"], rtol=5e-6, atol=2e-6)
+    assert recall(idx, g["knn_idx"]) >= 0.9995 and (np.diff(dist, axis=1) <= 0).all()
+    lh = C.label_transfer(q, g["feature_memory"], g["label_memory"], g["knn_idx"])
+    np.testing.assert_allclose(lh, g["label_hat"].reshape(lh.shape), rtol=0, atol=2e-5)
+
+
+def test_search_pads_and_orders_ties_like_faiss():
+    bank = np.eye(4, 8, dtype=np.float32)
+    bank = np.concatenate([bank, bank[:1]])  # row 4 duplicates row 0: a tie
+    idx, dist = C.search_ip(np.ones((1, 8), np.float32) * np.array([[1, 0, 0, 0, 0, 0, 0, 0]], np.float32), bank, 7)
+    assert idx[0, 0] == 0 and idx[0, 1] == 4  # equal scores: the smaller index first
+    assert (idx[0, 5:] == -1).all() and np.isneginf(dist[0, 5:]).all()
+    oi, od = O.search_exact_ip(np.array([[1, 0, 0, 0, 0, 0, 0, 0]], np.float32), bank, 7)
+    np.testing.assert_array_equal(idx, oi)
+    np.testing.assert_array_equal(dist, od)
