@@ -78,3 +78,16 @@ def test_search_pads_and_orders_ties_like_faiss():
     oi, od = O.search_exact_ip(np.array([[1, 0, 0, 0, 0, 0, 0, 0]], np.float32), bank, 7)
     np.testing.assert_array_equal(idx, oi)
     np.testing.assert_array_equal(dist, od)
+
+
+@pytest.mark.parametrize("S,ps,n_cls", [(14, 16, 21), (37, 14, 21), (5, 7, 151), (3, 10, 2), (1, 8, 4)])
+def test_upsample_argmax_c_equals_numpy_on_random_label_maps(S, ps, n_cls):
+    """The two restatements of ATen's align_corners=False bilinear + argmax agree pixel for pixel at the
+    BASELINE geometries (S=14/ps=16, S=37/ps=14) and at degenerate ones (S=1)."""
+    rng = np.random.default_rng(S * 100 + ps)
+    B, H = 2, S * ps
+    lh = rng.random((B, S * S, n_cls)).astype(np.float32)
+    lh[0, :, 0] = lh[0, :, 1]  # exact ties between two classes: the first maximum must win in both
+    got = C.upsample_argmax(lh, B, S, H, H)
+    ref = O.predict_map(lh, S, H, H).reshape(B, H, H)
+    np.testing.assert_array_equal(got, ref)
