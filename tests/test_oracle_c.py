@@ -91,3 +91,41 @@ def test_upsample_argmax_c_equals_numpy_on_random_label_maps(S, ps, n_cls):
     got = C.upsample_argmax(lh, B, S, H, H)
     ref = O.predict_map(lh, S, H, H).reshape(B, H, H)
     np.testing.assert_array_equal(got, ref)
+
+
+@pytest.mark.parametrize("S,ps,n_cls", [(14, 16, 21), (37, 14, 21), (8, 7, 9)])
+def test_upsample_argmax_oracles_equal_aten_interpolate(S, ps, n_cls):
+    """Ground truth for A9 is ATen itself (hbird_eval.py:235-243): permute -> F.interpolate(bilinear,
+    align_corners=False) -> argmax, run here on the CPU.  Both oracles must reproduce it exactly."""
+    import torch
+    import torch.nn.functional as F
+
+    rng = np.random.default_rng(7 * S + ps)
+    B, H = 2, S * ps
+    lh = rng.random((B, S * S, n_cls)).astype(np.float32)
+    x = torch.from_numpy(lh).view(B, S, S, n_cls).permute(0, 3, 1, 2)
+    aten = F.interpolate(x, size=(H, H), mode="bilinear").argmax(dim=1).numpy().astype(np.uint8)
+    np.testing.assert_array_equal(C.upsample_argmax(lh, B, S, H, H), aten)
+    np.testing.assert_array_equal(O.predict_map(lh, S, H, H).reshape(B, H, H), aten)
+
+
+def test_decode_and_soft_labels_equal_the_torch_ops_the_reference_runs():
+    """(y*255).long() with y = id/255 as the loader delivers it (image_transformations.py:39-49) and
+    one_hot(...).float().mean(3) over patch pixels (hbird_eval.py:319-320), computed with torch on the
+    CPU, against both oracles."""
+    import torch
+    import torch.nn.functional as F
+
+    ids = torch.arange(256, dtype=torch.float32)
+    y = ids / 255
+    want = (y * 255).long().numpy()
+    np.testing.assert_array_equal(C.decode_mask(y.numpy(), False), want.astype(np.uint8))
+    np.testing.assert_array_equal(O.decode_mask(y.numpy(), False), want)
+    rng = np.random.default_rng(5)
+    B, S, ps, n_cls = 2, 5, 7, 11
+    mask = rng.integers(0, n_cls, size=(B, S * ps, S * ps)).astype(np.uint8)
+    pg = torch.from_numpy(mask.astype(np.int64)).view(B, S, ps, S, ps).permute(0, 1, 3, 2, 4).reshape(B, S, S, ps * ps)
+    soft = F.one_hot(pg, n_cls).float().mean(3).reshape(B * S * S, n_cls).numpy()
+    hist = C.patch_histogram(mask, S, ps, n_cls)
+    np.testing.assert_array_equal(hist.astype(np.float32) / np.float32(ps * ps), soft)
+    np.testing.assert_array_equal(O.soft_labels(pg.numpy(), n_cls).reshape(B * S * S, n_cls), soft)
