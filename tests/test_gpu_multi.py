@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs at least 2 GPUs")
 def test_sharded_engine_matches_reference_golden():
-    n = min(torch.cuda.device_count(), 4)
+    n = 2  # the golden miniatures have 2-3 training batches: every rank must own at least one
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
            "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tools", "dist_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
