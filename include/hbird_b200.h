@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define HB_ABI_VERSION 1
+#define HB_ABI_VERSION 2
 
 typedef enum hb_status {
   HB_OK = 0,
@@ -113,13 +113,51 @@ int hb_bank_export(const hb_bank_t* bank, int64_t row0, int64_t n, float* feats_
  * i.e. GpuIndexFlatIP.search: exact top-k by inner product of the raw (un-normalised)
  * queries against the unit-norm bank rows, sorted by descending score.
  * q_dev: fp32 (Q, d).  k <= k_prime, k_prime in {32, 64, 128}: the tcgen05 bf16 pass keeps
- * k_prime candidates per query, the fp32 pass re-scores them exactly and keeps k.
+ * candidates per query, the fp32 pass re-scores them exactly and keeps k.
  * out_scores_dev fp32 (Q, k); out_idx_dev int64 (Q, k) = row index + idx_offset (the
  * shard's first global row); out_qnorm_dev fp32 (Q,) = ||q||_2 or NULL.  If the bank
- * holds fewer than k rows the tail is (-inf, -1), as faiss pads. */
+ * holds fewer than k rows the tail is (-inf, -1), as faiss pads.
+ *
+ * What the bf16 pass guarantees (csrc/search.cu).  A query's bank rows are scanned by L >= 4
+ * candidate lists of k_prime/2 entries each (two per bank chunk, at least two chunks; which of
+ * a chunk's two lists sees a given 32-row group changes pseudo-randomly from tile to tile).
+ * A list drops a row only (a) below its own (k_prime/2)-th best score or (b) below a shared
+ * threshold x for which k_prime rows scoring >= x are known to exist (2 lists holding k_prime/2
+ * each, or 4 lists holding k_prime/4 each).  Hence:
+ *   - the query's best k_prime/2 rows by bf16 score are ALWAYS among the candidates;
+ *   - a row ranked r <= k_prime is missing only if k_prime/2 better rows share its list; for
+ *     rows spread over the lists independently of their score that is P[Bin(r-1, 1/L) >=
+ *     k_prime/2]: for k_prime = 64, L = 4: 6e-10 at r = 48 and 1e-5 at r = 64; L >= 6: < 1e-9;
+ *   - banks of at most 16384 rows always run with k_prime = 128 lists (64 entries each).
+ * The fp32 top-k is a subset of the bf16 top-k_prime only statistically (bf16 rounding moves a
+ * row by a few ranks; SURVEY.md H1 measured the fp32 top-30 inside the bf16 top-64 always and
+ * inside the bf16 top-30 for 99.6 % of the neighbours).  Callers that need the bf16 top-64
+ * strictly (k up to 64, or adversarial row placement) pass k_prime = 128. */
 int hb_search(hb_bank_t* bank, const float* q_dev, int64_t Q, int k, int k_prime,
               int64_t idx_offset, float* out_scores_dev, int64_t* out_idx_dev,
               float* out_qnorm_dev, void* stream);
+
+/* K2 + K2b with K4a fused into the re-rank warp: as hb_search, and the warp that holds a query's k
+ * exact neighbours also writes label_hat[q] (see hb_label_transfer) — the neighbour list is never
+ * re-read from HBM.  label_table_dev: uint16 (table_rows, C) indexed by row + idx_offset (NULL =
+ * the bank's own table, table_rows ignored); out_scores_dev / out_idx_dev may both be NULL when
+ * only label_hat is wanted; out_label_hat_dev fp32 (Q, C).  Inner-product banks only. */
+int hb_search_transfer(hb_bank_t* bank, const uint16_t* label_table_dev, int64_t table_rows,
+                       const float* q_dev, int64_t Q, int k, int k_prime, int64_t idx_offset,
+                       float beta, float* out_scores_dev, int64_t* out_idx_dev,
+                       float* out_qnorm_dev, float* out_label_hat_dev, void* stream);
+
+/* One validation batch through the whole path in 4 launches (query prep, K2, K2b+K4a, fused tail):
+ * replaces hbird_eval.py:217-252 for a bank that is not row-sharded.  q_dev fp32 (B*S*S, d) raw
+ * features; y_dev fp32 (B, H, W) = class id / 255 (loader contract, :219); label_hat_dev fp32
+ * (B*S*S, C) scratch that holds label_hat on return; conf_dev int64 (C, C) accumulated in place;
+ * out_pred_dev uint8 (B, H, W) or NULL; out_scores_dev / out_idx_dev (B*S*S, k) or both NULL.
+ * Capturable in a CUDA graph once the bank's scratch has been sized by a first call. */
+int hb_eval_step(hb_bank_t* bank, const uint16_t* label_table_dev, int64_t table_rows,
+                 const float* q_dev, int B, int S, int H, int W, const float* y_dev, int k,
+                 int k_prime, int64_t idx_offset, float beta, int ignore_index,
+                 float* label_hat_dev, int64_t* conf_dev, uint8_t* out_pred_dev,
+                 float* out_scores_dev, int64_t* out_idx_dev, void* stream);
 
 /* Tuning/diagnostics for hb_search: cta_group (1 or 2; 0 = library default),
  * max_chunks (bank split per query block; 0 = auto). */
@@ -165,6 +203,15 @@ int hb_merge_topk(const float* shard_scores_dev, const int64_t* shard_idx_dev, i
                   int64_t Q, int k, float* out_scores_dev, int64_t* out_idx_dev,
                   void* stream);
 
+/* K3 with K4a fused (see hb_search_transfer): qnorm_dev fp32 (Q,), out_label_hat_dev fp32 (Q, C);
+ * out_scores_dev / out_idx_dev may both be NULL.  Inner-product results only (the merge keeps the
+ * largest scores). */
+int hb_merge_topk_transfer(const float* shard_scores_dev, const int64_t* shard_idx_dev, int G,
+                           int64_t Q, int k, const uint16_t* label_table_dev, int64_t table_rows,
+                           int C, int patch_pixels, const float* qnorm_dev, float beta,
+                           float* out_scores_dev, int64_t* out_idx_dev,
+                           float* out_label_hat_dev, void* stream);
+
 /* ---- K3x: fused shard exchange over NVLink peer memory -------------------------------------
  * The B200 form of faiss.IndexShards' search (search_faiss.py:53-63,89) for one process per GPU:
  * every rank searches all Q queries against its row shard; rank p post-processes the queries
@@ -200,6 +247,13 @@ int hb_search_scatter(hb_bank_t* bank, hb_exchange_t* xchg, const float* q_dev, 
  * global indices; rows = hb_exchange_slice_rows().  A peer that never arrives makes the kernel
  * trap after 10 min instead of hanging the GPU. */
 int hb_exchange_merge(hb_exchange_t* xchg, float* out_scores_dev, int64_t* out_idx_dev, void* stream);
+/* hb_exchange_merge with K4a fused into the merging warp: qnorm_slice_dev fp32 (rows,) are the norms
+ * of this rank's query slice, out_label_hat_dev fp32 (rows, C); out_scores_dev / out_idx_dev may
+ * both be NULL.  Counts as the one merge of the last scatter. */
+int hb_exchange_merge_transfer(hb_exchange_t* xchg, const uint16_t* label_table_dev, int64_t table_rows,
+                               int C, int patch_pixels, const float* qnorm_slice_dev, float beta,
+                               float* out_scores_dev, int64_t* out_idx_dev,
+                               float* out_label_hat_dev, void* stream);
 int64_t hb_exchange_slice_rows(const hb_exchange_t* xchg);
 
 /* ---- K4: label transfer ------------------------------------------------------------------
@@ -218,6 +272,18 @@ int hb_label_transfer(const uint16_t* label_table_dev, int64_t table_rows, int C
  * (first maximum wins).  out_pred_dev uint8 (B, H, W). */
 int hb_upsample_argmax(const float* label_hat_dev, int B, int S, int C, int H, int W,
                        uint8_t* out_pred_dev, void* stream);
+
+/* Fused tail — replaces hbird_eval.py:219 (mask decode), :235-243 (upsample + argmax) and
+ * PredsmIoU.update (eval_metrics.py:73-109) in one pass over the output pixels: per (image, band of
+ * rows) the label_hat cells are staged in shared memory, every pixel is interpolated with torch's
+ * arithmetic, its argmax is scored against the ground truth in a shared-memory histogram, and
+ * neither the decoded mask nor the prediction map has to be written.  Ground truth: y_dev fp32
+ * (B, H, W) = id/255, or gt_dev uint8 (B, H, W) already decoded (y_dev wins; both NULL only with
+ * conf_dev NULL).  conf_dev int64 (C, C) accumulated in place or NULL; out_pred_dev uint8
+ * (B, H, W) or NULL. */
+int hb_predict_score(const float* label_hat_dev, int B, int S, int C, int H, int W,
+                     const float* y_dev, const uint8_t* gt_dev, int ignore_index,
+                     int64_t* conf_dev, uint8_t* out_pred_dev, void* stream);
 
 /* ---- K5: scoring --------------------------------------------------------------------------
  * Replaces the loader-contract decode `(y*255).long()` (hbird_eval.py:219,309-310):

@@ -17,18 +17,31 @@ void set_error(const char* fmt, ...) {
 }
 void clear_error() { g_err[0] = 0; }
 
-int ensure_workspace(Bank* b, size_t bytes) {
+int ensure_workspace(Bank* b, size_t bytes, cudaStream_t st) {
   if (bytes <= b->ws_bytes) return HB_OK;
+  // Stream-ordered growth: the old block is released after the work already queued on `st` (the
+  // only stream a bank is driven from, include/hbird_b200.h) and nothing synchronises the device.
   if (b->ws) {
-    HB_CHECK_CUDA(cudaDeviceSynchronize());
-    HB_CHECK_CUDA(cudaFree(b->ws));
+    HB_CHECK_CUDA(cudaFreeAsync(b->ws, st));
     b->ws = nullptr;
     b->ws_bytes = 0;
   }
   size_t want = bytes + bytes / 4;
-  HB_CHECK_CUDA(cudaMalloc(&b->ws, want));
+  HB_CHECK_CUDA(cudaMallocAsync(&b->ws, want, st));
   b->ws_bytes = want;
   return HB_OK;
+}
+
+int device_sm_count() {
+  static int cached[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,

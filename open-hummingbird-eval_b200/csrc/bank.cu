@@ -295,7 +295,7 @@ int hb_bank_destroy(hb_bank_t* bank) {
   if (!bank) return HB_OK;
   Bank* b = reinterpret_cast<Bank*>(bank);
   cudaSetDevice(b->device);
-  cudaDeviceSynchronize();
+  // cudaFree itself waits for queued work that still uses a block; no explicit device sync
   if (b->feat_bf16) cudaFree(b->feat_bf16);
   if (b->feat_f32) cudaFree(b->feat_f32);
   if (b->label_hist) cudaFree(b->label_hist);

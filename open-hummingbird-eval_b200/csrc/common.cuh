@@ -84,6 +84,18 @@ struct Scatter {
   unsigned int* done_ctas = nullptr; // local counter of finished CTAs
 };
 
+// Optional fused label transfer (K4a) at the end of K2b / K3 / K3x: when `table` is set, the warp
+// that holds a query's final neighbour list also writes label_hat[q] (C floats).
+struct LabelOut {
+  const uint16_t* table = nullptr;  // (table_rows, C) class histograms, indexed by GLOBAL bank row
+  int64_t table_rows = 0;
+  int C = 0;
+  int pp = 1;                       // pixels per patch: soft label = histogram / pp
+  float beta = 0.02f;
+  const float* qnorm = nullptr;     // ||q||_2, indexed like the kernel's query index
+  float* out = nullptr;             // (queries, C)
+};
+
 // One rank's end of the exchange: a cudaMalloc'ed window other ranks map through CUDA IPC.
 //   window = [flags: kMaxPeers x u32, padded to 256 B]
 //            2 x [scores: world x cap x kmax f32][idx: world x cap x kmax i64]
@@ -106,7 +118,24 @@ struct Exchange {
   size_t buffer_bytes() const { return (sizeof(float) + sizeof(int64_t)) * slot_elems() * world; }
 };
 
-int ensure_workspace(Bank* b, size_t bytes);
+int ensure_workspace(Bank* b, size_t bytes, cudaStream_t st);
+// SM count of the current device (cached per device id).
+int device_sm_count();
+// Fused tail (label_transfer.cu): decode + upsample + argmax + confusion.  HB_ERR_UNSUPPORTED (no
+// message) when C is too large for the shared-memory histogram.
+int predict_score_launch(const float* label_hat, int B, int S, int C, int H, int W, const float* y,
+                         const uint8_t* gt, int ignore_index, int64_t* conf, uint8_t* pred, cudaStream_t st);
+// K2 + K2b (search.cu): bf16 tcgen05 pass + exact fp32 re-rank.  Outputs are optional: out_scores /
+// out_idx (local top-k), sc (scatter into the owner ranks' exchange windows), lo (fused label
+// transfer; lo->qnorm is filled in by the callee), dump (validation: raw score matrix only).
+int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_t idx_offset,
+                float* out_scores, int64_t* out_idx, float* out_qnorm, float* dump, int cg_override,
+                cudaStream_t st, const Scatter* sc, const LabelOut* lo);
+int rerank_launch(const Bank* b, const float* q, int64_t Q, int k, int kp, int n_chunks,
+                  int64_t q_pad, const uint64_t* cand, int64_t idx_offset, float* out_scores,
+                  int64_t* out_idx, const Scatter* sc, const LabelOut* lo, cudaStream_t st);  // rerank.cu
+int merge_window_launch(const Exchange* x, uint32_t step, int64_t rows, int k, float* out_scores,
+                        int64_t* out_idx, const LabelOut* lo, cudaStream_t st);  // rerank.cu
 // Encode a 2-D bf16 row-major (rows, cols_pad) tensor map with a (64 x box_rows) box and
 // 128-byte swizzle.  Resolved through cudaGetDriverEntryPoint: no link-time libcuda.
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, int64_t rows, int cols_pad,

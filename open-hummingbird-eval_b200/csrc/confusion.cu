@@ -129,7 +129,8 @@ int hb_decode_mask(const float* y_dev, int64_t n, int remap_255_to_0, uint8_t* o
   if (n == 0) return HB_OK;
   HB_REQUIRE(y_dev && out_dev, "hb_decode_mask: NULL pointer");
   int64_t blocks = hb::ceil_div64(n, 256 * 8);
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  const int64_t cap = static_cast<int64_t>(hb::device_sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
   hb::decode_mask_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(y_dev, n, remap_255_to_0, out_dev);
   HB_CHECK_CUDA(cudaGetLastError());
   return HB_OK;
@@ -148,13 +149,14 @@ int hb_confusion_accumulate(const uint8_t* gt_dev, const uint8_t* pred_dev, int6
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   unsigned long long* conf = reinterpret_cast<unsigned long long*>(conf_dev);
   // 64 pixels per thread once there is enough work to fill the GPU that way, 16 otherwise
-  const bool wide = n >= static_cast<int64_t>(148) * per_sm * hb::kConfThreads * 64;
+  const int sms = hb::device_sm_count();
+  const bool wide = n >= static_cast<int64_t>(sms) * per_sm * hb::kConfThreads * 64;
   auto kernel = wide ? hb::confusion_kernel<4> : hb::confusion_kernel<1>;
   if (smem > 48 * 1024)
     HB_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   const int64_t chunk = static_cast<int64_t>(hb::kConfThreads) * hb::kConfPixPerThread * (wide ? 4 : 1);
   int64_t blocks = hb::ceil_div64(n, chunk);
-  if (blocks > 148 * per_sm) blocks = 148 * per_sm;
+  if (blocks > static_cast<int64_t>(sms) * per_sm) blocks = static_cast<int64_t>(sms) * per_sm;
   kernel<<<static_cast<unsigned>(blocks), hb::kConfThreads, smem, st>>>(gt_dev, pred_dev, n, C_gt, C_pred,
                                                                          ignore_index, conf);
   HB_CHECK_CUDA(cudaGetLastError());

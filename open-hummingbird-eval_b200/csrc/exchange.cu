@@ -14,16 +14,6 @@
 
 #include "common.cuh"
 
-namespace hb {
-
-int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_t idx_offset,
-                float* out_scores, int64_t* out_idx, float* out_qnorm, float* dump, int cg_override,
-                cudaStream_t st, const Scatter* sc);  // search.cu
-int merge_window_launch(const Exchange* x, uint32_t step, int64_t rows, int k, float* out_scores,
-                        int64_t* out_idx, cudaStream_t st);  // rerank.cu
-
-}  // namespace hb
-
 using hb::Bank;
 using hb::Exchange;
 
@@ -162,6 +152,8 @@ int hb_search_scatter(hb_bank_t* bank, hb_exchange_t* xchg, const float* q_dev, 
   HB_REQUIRE(k_prime == 32 || k_prime == 64 || k_prime == 128, "hb_search_scatter: k_prime=%d not in {32, 64, 128}", k_prime);
   HB_REQUIRE(q_dev && qsplit_host, "hb_search_scatter: NULL pointer");
   HB_REQUIRE(b->rows >= 1, "hb_search_scatter: the bank shard is empty");
+  // the cross-shard merge keeps the LARGEST scores; squared-L2 results are ascending distances
+  HB_REQUIRE((b->flags & HB_BANK_L2) == 0, "hb_search_scatter: squared-L2 banks cannot be row-sharded (inner-product metric only)");
   HB_REQUIRE(qsplit_host[0] == 0 && qsplit_host[x->world] == Q, "hb_search_scatter: qsplit must run from 0 to Q");
   for (int p = 0; p < x->world; ++p) {
     const int64_t n = qsplit_host[p + 1] - qsplit_host[p];
@@ -169,12 +161,14 @@ int hb_search_scatter(hb_bank_t* bank, hb_exchange_t* xchg, const float* q_dev, 
   }
   HB_CHECK_CUDA(cudaSetDevice(b->device));
 
-  x->step += 1;
-  const int parity = static_cast<int>(x->step & 1u);
+  // the step counter advances only once the launches are in the stream: a call that fails before
+  // that leaves this end of the exchange as it was
+  const uint32_t step = x->step + 1;
+  const int parity = static_cast<int>(step & 1u);
   hb::Scatter sc;
   sc.world = x->world;
   sc.rank = x->rank;
-  sc.step = x->step;
+  sc.step = step;
   sc.done_ctas = x->done_ctas;
   for (int p = 0; p <= x->world; ++p) sc.qsplit[p] = qsplit_host[p];
   for (int p = 0; p < x->world; ++p) {
@@ -183,10 +177,13 @@ int hb_search_scatter(hb_bank_t* bank, hb_exchange_t* xchg, const float* q_dev, 
     sc.idx[p] = reinterpret_cast<int64_t*>(win + x->idx_off(parity)) + x->slot_elems() * x->rank;
     sc.flag[p] = reinterpret_cast<uint32_t*>(win) + x->rank;
   }
+  const int rc = hb::search_impl(b, q_dev, Q, k, k_prime, idx_offset, nullptr, nullptr, out_qnorm_dev, nullptr, 0,
+                                 static_cast<cudaStream_t>(stream), &sc, nullptr);
+  if (rc != HB_OK) return rc;
+  x->step = step;
   x->last_rows = qsplit_host[x->rank + 1] - qsplit_host[x->rank];
   x->last_k = k;
-  return hb::search_impl(b, q_dev, Q, k, k_prime, idx_offset, nullptr, nullptr, out_qnorm_dev, nullptr, 0,
-                         static_cast<cudaStream_t>(stream), &sc);
+  return HB_OK;
 }
 
 int hb_exchange_merge(hb_exchange_t* xchg, float* out_scores_dev, int64_t* out_idx_dev, void* stream) {
@@ -200,8 +197,36 @@ int hb_exchange_merge(hb_exchange_t* xchg, float* out_scores_dev, int64_t* out_i
   HB_CHECK_CUDA(cudaSetDevice(x->device));
   const int k = x->last_k;
   x->last_k = 0;  // one merge per scatter
-  return hb::merge_window_launch(x, x->step, x->last_rows, k, out_scores_dev, out_idx_dev,
+  return hb::merge_window_launch(x, x->step, x->last_rows, k, out_scores_dev, out_idx_dev, nullptr,
                                  static_cast<cudaStream_t>(stream));
+}
+
+int hb_exchange_merge_transfer(hb_exchange_t* xchg, const uint16_t* label_table_dev, int64_t table_rows, int C,
+                               int patch_pixels, const float* qnorm_slice_dev, float beta,
+                               float* out_scores_dev, int64_t* out_idx_dev, float* out_label_hat_dev,
+                               void* stream) {
+  HB_REQUIRE(xchg != nullptr, "hb_exchange_merge_transfer: exchange is NULL");
+  Exchange* x = reinterpret_cast<Exchange*>(xchg);
+  if (x->step == 0 || x->last_k == 0) {
+    hb::set_error("hb_exchange_merge_transfer: no scatter to merge (call hb_search_scatter first)");
+    return HB_ERR_STATE;
+  }
+  HB_REQUIRE(C >= 1 && C <= 256 && patch_pixels >= 1 && beta > 0.f, "hb_exchange_merge_transfer: bad C/patch_pixels/beta");
+  HB_REQUIRE((out_scores_dev == nullptr) == (out_idx_dev == nullptr), "hb_exchange_merge_transfer: give both or neither of out_scores/out_idx");
+  HB_REQUIRE(x->last_rows == 0 || (label_table_dev && qnorm_slice_dev && out_label_hat_dev), "hb_exchange_merge_transfer: NULL pointer");
+  HB_CHECK_CUDA(cudaSetDevice(x->device));
+  hb::LabelOut lo;
+  lo.table = label_table_dev;
+  lo.table_rows = table_rows;
+  lo.C = C;
+  lo.pp = patch_pixels;
+  lo.beta = beta;
+  lo.qnorm = qnorm_slice_dev;
+  lo.out = out_label_hat_dev;
+  const int k = x->last_k;
+  x->last_k = 0;  // one merge per scatter
+  return hb::merge_window_launch(x, x->step, x->last_rows, k, out_scores_dev, out_idx_dev,
+                                 x->last_rows > 0 ? &lo : nullptr, static_cast<cudaStream_t>(stream));
 }
 
 int64_t hb_exchange_slice_rows(const hb_exchange_t* xchg) {

@@ -106,6 +106,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_
   }
 }
 
+// ---- shared memory ------------------------------------------------------------------
+// 32-bit store through a shared-window address (no register pairing, so a value that lives in a
+// tcgen05.ld destination register can be stored without a copy).
+__device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+// x + y as a volatile instruction: stays where it is written (inside a predicated region)
+// instead of being hoisted and computed speculatively.
+__device__ __forceinline__ uint32_t add_volatile(uint32_t x, uint32_t y) {
+  uint32_t r;
+  asm volatile("add.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(y));
+  return r;
+}
+
 // ---- TMA ---------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");

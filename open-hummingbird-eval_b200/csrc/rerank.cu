@@ -57,12 +57,69 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   return v;
 }
 
+// K4a fused into the kernels that produce a query's final neighbour list (K2b when the bank is not
+// sharded, the merge kernels K3 / K3x when it is): the warp that holds the k (score, row) pairs in
+// its lanes turns them into label_hat[q] = sum_j softmax_j(cos_j / beta) * soft_label[row_j]
+// (hbird_eval.py:575-609,632-636) without the list ever being re-read from HBM.  cos_j =
+// score_j / ||q|| because bank rows are unit norm; soft label = uint16 histogram / pixels per
+// patch.  Same arithmetic, in the same order, as the stand-alone label_transfer_kernel.
+// Element e = r*32 + lane of the list is (sc[r], id[r]); id < 0 = no neighbour.
+template <int R>
+__device__ __forceinline__ void
+label_transfer_lanes(const LabelOut& lo, int64_t qi, int64_t out_row, int k, const float (&sc)[R],
+                     const int64_t (&id)[R], float* s_w, int64_t* s_i) {
+  const int lane = threadIdx.x & 31;
+  // F.normalize clamps the norm at eps = 1e-12 (hbird_eval.py:594)
+  const float qn = fmaxf(lo.qnorm[qi], 1e-12f);
+  float logit[R];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int e = r * 32 + lane;
+    const bool ok = e < k && id[r] >= 0 && id[r] < lo.table_rows;
+    logit[r] = ok ? (sc[r] / qn) / lo.beta : -INFINITY;
+    mx = fmaxf(mx, logit[r]);
+  }
+  mx = warp_max(mx);
+  float ex[R];
+  float sum = 0.f;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    ex[r] = (logit[r] == -INFINITY) ? 0.f : expf(logit[r] - mx);
+    sum += ex[r];
+  }
+  sum = warp_sum(sum);
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int e = r * 32 + lane;
+    if (e < k) {
+      const bool ok = logit[r] != -INFINITY;
+      s_w[e] = ok ? ex[r] / sum : 0.f;  // a missing neighbour keeps weight 0 and reads row 0
+      s_i[e] = ok ? id[r] : 0;
+    }
+  }
+  __syncwarp();
+  const float fpp = static_cast<float>(lo.pp);
+  const int C = lo.C;
+  for (int c = lane; c < C; c += 32) {
+    float acc = 0.f;
+#pragma unroll 10
+    for (int j = 0; j < k; ++j) {
+      const float lab = static_cast<float>(__ldg(lo.table + s_i[j] * C + c)) / fpp;
+      acc += s_w[j] * lab;
+    }
+    lo.out[out_row * C + c] = acc;
+  }
+  __syncwarp();
+}
+
 template <int R, bool L2>
 __device__ __forceinline__ void
 rerank_query(const float* __restrict__ q, const float* __restrict__ bank_f32,
              const __nv_bfloat16* __restrict__ bank_bf16, const uint64_t* __restrict__ cand,
              int n_chunks, int64_t q_pad, int64_t Q, int d, int dpad, int k, int64_t idx_offset,
-             float* __restrict__ out_scores, int64_t* __restrict__ out_idx, const Scatter& sc) {
+             float* __restrict__ out_scores, int64_t* __restrict__ out_idx, const Scatter& sc,
+             const LabelOut& lo, float* s_w, int64_t* s_i) {
   constexpr int KP = 32 * R;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t qi = static_cast<int64_t>(blockIdx.x) * 4 + warp;
@@ -145,8 +202,8 @@ rerank_query(const float* __restrict__ q, const float* __restrict__ bank_f32,
   warp_bitonic_sort<R, true>(exact, lane);
 
   // ---- emit the top-k: locally, or into the window of the rank that owns this query ----
-  float* os = out_scores + qi * k;
-  int64_t* oi = out_idx + qi * k;
+  float* os = out_scores ? out_scores + qi * k : nullptr;
+  int64_t* oi = out_idx ? out_idx + qi * k : nullptr;
   if (sc.world) {
     int p = 0;
     while (p + 1 < sc.world && qi >= sc.qsplit[p + 1]) ++p;
@@ -154,17 +211,22 @@ rerank_query(const float* __restrict__ q, const float* __restrict__ bank_f32,
     os = sc.scores[p] + row * k;  // peer memory (NVLink) unless p == rank
     oi = sc.idx[p] + row * k;
   }
+  float fs[R];
+  int64_t fi[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int e = r * 32 + lane;
-    if (e < k) {
-      const bool ok = exact[r] != 0ull;
-      // L2 banks report squared distances, ascending (GpuIndexFlatL2, search_faiss.py:45-46,89)
-      const float v = ok ? key_score(exact[r]) : -INFINITY;
-      os[e] = L2 ? -v : v;
-      oi[e] = ok ? static_cast<int64_t>(key_row(exact[r])) + idx_offset : -1;
+    const bool ok = exact[r] != 0ull;
+    // L2 banks report squared distances, ascending (GpuIndexFlatL2, search_faiss.py:45-46,89)
+    const float v = ok ? key_score(exact[r]) : -INFINITY;
+    fs[r] = L2 ? -v : v;
+    fi[r] = ok ? static_cast<int64_t>(key_row(exact[r])) + idx_offset : -1;
+    if (e < k && os != nullptr) {
+      os[e] = fs[r];
+      oi[e] = fi[r];
     }
   }
+  if (!L2 && lo.table != nullptr) label_transfer_lanes<R>(lo, qi, qi, k, fs, fi, s_w, s_i);
 }
 
 template <int R, bool L2>
@@ -173,9 +235,11 @@ rerank_kernel(const float* __restrict__ q, const float* __restrict__ bank_f32,
               const __nv_bfloat16* __restrict__ bank_bf16, const uint64_t* __restrict__ cand,
               int n_chunks, int64_t q_pad, int64_t Q, int d, int dpad, int k, int64_t idx_offset,
               float* __restrict__ out_scores, int64_t* __restrict__ out_idx,
-              const __grid_constant__ Scatter sc) {
+              const __grid_constant__ Scatter sc, const LabelOut lo) {
+  __shared__ float s_w[4][32 * R];
+  __shared__ int64_t s_i[4][32 * R];
   rerank_query<R, L2>(q, bank_f32, bank_bf16, cand, n_chunks, q_pad, Q, d, dpad, k, idx_offset,
-                      out_scores, out_idx, sc);
+                      out_scores, out_idx, sc, lo, s_w[threadIdx.x >> 5], s_i[threadIdx.x >> 5]);
   if (sc.world) {
     // Fused exchange: every thread's peer stores are ordered before the CTA counts itself done;
     // the last CTA of the grid then raises this rank's arrival flag on every peer.
@@ -194,17 +258,19 @@ rerank_kernel(const float* __restrict__ q, const float* __restrict__ bank_f32,
 
 int rerank_launch(const Bank* b, const float* q, int64_t Q, int k, int kp,
                   int n_chunks, int64_t q_pad, const uint64_t* cand, int64_t idx_offset,
-                  float* out_scores, int64_t* out_idx, const Scatter* sc, cudaStream_t st) {
+                  float* out_scores, int64_t* out_idx, const Scatter* sc, const LabelOut* lo,
+                  cudaStream_t st) {
   const unsigned blocks = static_cast<unsigned>(ceil_div64(Q, 4));
   const Scatter scatter = sc ? *sc : Scatter();
+  const LabelOut label = lo ? *lo : LabelOut();
 #define HB_RERANK(R)                                                                              \
   do {                                                                                            \
     if (b->flags & HB_BANK_L2)                                                                    \
       rerank_kernel<R, true><<<blocks, 128, 0, st>>>(q, b->feat_f32, b->feat_bf16, cand, n_chunks, q_pad, Q, \
-                                                     b->d, b->dpad, k, idx_offset, out_scores, out_idx, scatter); \
+                                                     b->d, b->dpad, k, idx_offset, out_scores, out_idx, scatter, label); \
     else                                                                                          \
       rerank_kernel<R, false><<<blocks, 128, 0, st>>>(q, b->feat_f32, b->feat_bf16, cand, n_chunks, q_pad, Q, \
-                                                      b->d, b->dpad, k, idx_offset, out_scores, out_idx, scatter); \
+                                                      b->d, b->dpad, k, idx_offset, out_scores, out_idx, scatter, label); \
   } while (0)
   if (kp == 32) HB_RERANK(1);
   else if (kp == 64) HB_RERANK(2);
@@ -223,7 +289,8 @@ int rerank_launch(const Bank* b, const float* q, int64_t Q, int k, int kp,
 template <int R>
 __device__ __forceinline__ void
 merge_query(const float* ss, const int64_t* si, int G, int64_t slot_stride, int64_t qi, int k,
-            float* __restrict__ out_scores, int64_t* __restrict__ out_idx) {
+            float* __restrict__ out_scores, int64_t* __restrict__ out_idx, const LabelOut& lo,
+            float* s_w, int64_t* s_i) {
   // keys here carry a 64-bit index, so sort (ordered score, then index) pairs held as two words
   const int lane = threadIdx.x & 31;
   // candidate slots: position in the gathered (G, k) list, encoded as g*k + j in the low word
@@ -251,33 +318,40 @@ merge_query(const float* ss, const int64_t* si, int G, int64_t slot_stride, int6
     for (int r = 0; r < R; ++r) top[r] = top[r] > nxt[r] ? top[r] : nxt[r];
     warp_bitonic_sort<R, true>(top, lane);
   }
+  float fs[R];
+  int64_t fi[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int e = r * 32 + lane;
+    fs[r] = -INFINITY;
+    fi[r] = -1;
     if (e < k) {
-      const bool ok = top[r] != 0ull;
-      int64_t id = -1;
-      float s = -INFINITY;
-      if (ok) {
+      if (top[r] != 0ull) {
         const uint32_t pos = key_row(top[r]);
         const int g = pos / k, j = pos % k;
         const int64_t off = static_cast<int64_t>(g) * slot_stride + qi * k + j;
-        id = __ldcg(si + off);
-        s = __ldcg(ss + off);
+        fi[r] = __ldcg(si + off);
+        fs[r] = __ldcg(ss + off);
       }
-      out_scores[qi * k + e] = s;
-      out_idx[qi * k + e] = id;
+      if (out_scores != nullptr) {
+        out_scores[qi * k + e] = fs[r];
+        out_idx[qi * k + e] = fi[r];
+      }
     }
   }
+  if (lo.table != nullptr) label_transfer_lanes<R>(lo, qi, qi, k, fs, fi, s_w, s_i);
 }
 
 template <int R>
 __global__ void __launch_bounds__(128)
 merge_topk_kernel(const float* __restrict__ ss, const int64_t* __restrict__ si, int G, int64_t Q,
-                  int k, float* __restrict__ out_scores, int64_t* __restrict__ out_idx) {
+                  int k, float* __restrict__ out_scores, int64_t* __restrict__ out_idx,
+                  const LabelOut lo) {
+  __shared__ float s_w[4][32 * R];
+  __shared__ int64_t s_i[4][32 * R];
   const int64_t qi = static_cast<int64_t>(blockIdx.x) * 4 + (threadIdx.x >> 5);
   if (qi >= Q) return;
-  merge_query<R>(ss, si, G, Q * k, qi, k, out_scores, out_idx);
+  merge_query<R>(ss, si, G, Q * k, qi, k, out_scores, out_idx, lo, s_w[threadIdx.x >> 5], s_i[threadIdx.x >> 5]);
 }
 
 // K3x: the receiving half of the fused exchange.  Waits until every source rank has published
@@ -289,7 +363,9 @@ __global__ void __launch_bounds__(128)
 merge_window_kernel(const float* ss, const int64_t* si, const uint32_t* flags, uint32_t step, int G,
                     int64_t slot_stride, int64_t rows, int k, unsigned long long timeout_ns,
                     unsigned int* timeout_flag, float* __restrict__ out_scores,
-                    int64_t* __restrict__ out_idx) {
+                    int64_t* __restrict__ out_idx, const LabelOut lo) {
+  __shared__ float s_w[4][32 * R];
+  __shared__ int64_t s_i[4][32 * R];
   if (threadIdx.x < G) {
     unsigned long long t0 = 0;
     // flags count exchanges; a peer may already be one step ahead (its data for that step went
@@ -309,11 +385,12 @@ merge_window_kernel(const float* ss, const int64_t* si, const uint32_t* flags, u
   __syncthreads();
   const int64_t qi = static_cast<int64_t>(blockIdx.x) * 4 + (threadIdx.x >> 5);
   if (qi >= rows) return;
-  merge_query<R>(ss, si, G, slot_stride, qi, k, out_scores, out_idx);
+  merge_query<R>(ss, si, G, slot_stride, qi, k, out_scores, out_idx, lo, s_w[threadIdx.x >> 5], s_i[threadIdx.x >> 5]);
 }
 
 int merge_window_launch(const Exchange* x, uint32_t step, int64_t rows, int k, float* out_scores,
-                        int64_t* out_idx, cudaStream_t st) {
+                        int64_t* out_idx, const LabelOut* lo, cudaStream_t st) {
+  const LabelOut label = lo ? *lo : LabelOut();
   const uint8_t* win = x->window[x->rank];
   const int parity = static_cast<int>(step & 1u);
   const float* ss = reinterpret_cast<const float*>(win + x->scores_off(parity));
@@ -326,7 +403,7 @@ int merge_window_launch(const Exchange* x, uint32_t step, int64_t rows, int k, f
   const int64_t stride = static_cast<int64_t>(x->slot_elems());
 #define HB_MERGE_WIN(R)                                                                         \
   merge_window_kernel<R><<<blocks, 128, 0, st>>>(ss, si, flags, step, x->world, stride, rows, k, \
-                                                 timeout_ns, x->timeout_flag, out_scores, out_idx)
+                                                 timeout_ns, x->timeout_flag, out_scores, out_idx, label)
   if (k <= 32) HB_MERGE_WIN(1);
   else if (k <= 64) HB_MERGE_WIN(2);
   else HB_MERGE_WIN(4);
@@ -337,6 +414,17 @@ int merge_window_launch(const Exchange* x, uint32_t step, int64_t rows, int k, f
 
 }  // namespace hb
 
+static int merge_topk_impl(const float* shard_scores_dev, const int64_t* shard_idx_dev, int G, int64_t Q, int k,
+                           float* out_scores_dev, int64_t* out_idx_dev, const hb::LabelOut& lo, void* stream) {
+  const unsigned blocks = static_cast<unsigned>(hb::ceil_div64(Q, 4));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (k <= 32) hb::merge_topk_kernel<1><<<blocks, 128, 0, st>>>(shard_scores_dev, shard_idx_dev, G, Q, k, out_scores_dev, out_idx_dev, lo);
+  else if (k <= 64) hb::merge_topk_kernel<2><<<blocks, 128, 0, st>>>(shard_scores_dev, shard_idx_dev, G, Q, k, out_scores_dev, out_idx_dev, lo);
+  else hb::merge_topk_kernel<4><<<blocks, 128, 0, st>>>(shard_scores_dev, shard_idx_dev, G, Q, k, out_scores_dev, out_idx_dev, lo);
+  HB_CHECK_CUDA(cudaGetLastError());
+  return HB_OK;
+}
+
 extern "C" int hb_merge_topk(const float* shard_scores_dev, const int64_t* shard_idx_dev, int G,
                              int64_t Q, int k, float* out_scores_dev, int64_t* out_idx_dev,
                              void* stream) {
@@ -345,11 +433,29 @@ extern "C" int hb_merge_topk(const float* shard_scores_dev, const int64_t* shard
   HB_REQUIRE(Q >= 0, "hb_merge_topk: Q < 0");
   if (Q == 0) return HB_OK;
   HB_REQUIRE(shard_scores_dev && shard_idx_dev && out_scores_dev && out_idx_dev, "hb_merge_topk: NULL pointer");
-  const unsigned blocks = static_cast<unsigned>(hb::ceil_div64(Q, 4));
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (k <= 32) hb::merge_topk_kernel<1><<<blocks, 128, 0, st>>>(shard_scores_dev, shard_idx_dev, G, Q, k, out_scores_dev, out_idx_dev);
-  else if (k <= 64) hb::merge_topk_kernel<2><<<blocks, 128, 0, st>>>(shard_scores_dev, shard_idx_dev, G, Q, k, out_scores_dev, out_idx_dev);
-  else hb::merge_topk_kernel<4><<<blocks, 128, 0, st>>>(shard_scores_dev, shard_idx_dev, G, Q, k, out_scores_dev, out_idx_dev);
-  HB_CHECK_CUDA(cudaGetLastError());
-  return HB_OK;
+  return merge_topk_impl(shard_scores_dev, shard_idx_dev, G, Q, k, out_scores_dev, out_idx_dev, hb::LabelOut(), stream);
+}
+
+extern "C" int hb_merge_topk_transfer(const float* shard_scores_dev, const int64_t* shard_idx_dev, int G,
+                                      int64_t Q, int k, const uint16_t* label_table_dev, int64_t table_rows,
+                                      int C, int patch_pixels, const float* qnorm_dev, float beta,
+                                      float* out_scores_dev, int64_t* out_idx_dev,
+                                      float* out_label_hat_dev, void* stream) {
+  HB_REQUIRE(G >= 1 && G <= 1024, "hb_merge_topk_transfer: G=%d not in [1, 1024]", G);
+  HB_REQUIRE(k >= 1 && k <= 128, "hb_merge_topk_transfer: k=%d not in [1, 128]", k);
+  HB_REQUIRE(C >= 1 && C <= 256 && patch_pixels >= 1 && beta > 0.f, "hb_merge_topk_transfer: bad C/patch_pixels/beta");
+  HB_REQUIRE(Q >= 0, "hb_merge_topk_transfer: Q < 0");
+  if (Q == 0) return HB_OK;
+  HB_REQUIRE(shard_scores_dev && shard_idx_dev && label_table_dev && qnorm_dev && out_label_hat_dev,
+             "hb_merge_topk_transfer: NULL pointer");
+  HB_REQUIRE((out_scores_dev == nullptr) == (out_idx_dev == nullptr), "hb_merge_topk_transfer: give both or neither of out_scores/out_idx");
+  hb::LabelOut lo;
+  lo.table = label_table_dev;
+  lo.table_rows = table_rows;
+  lo.C = C;
+  lo.pp = patch_pixels;
+  lo.beta = beta;
+  lo.qnorm = qnorm_dev;
+  lo.out = out_label_hat_dev;
+  return merge_topk_impl(shard_scores_dev, shard_idx_dev, G, Q, k, out_scores_dev, out_idx_dev, lo, stream);
 }

@@ -53,6 +53,9 @@ constexpr int kTmemCols = 512;
 // then hit in the 126 MB L2 by everyone else.
 constexpr int kPaceTiles = 32;
 constexpr int kPaceLag = 2;
+constexpr int64_t kSmallBankRows = 16384;  // banks up to this size always run with k' = 128 lists
+constexpr int kBoardPeriod = 8;  // tiles between two reads of the threshold board (power of two)
+constexpr int kBoardDense = 24;  // ... after the first kBoardDense tiles of a work item, which read it every tile
 
 struct SearchParams {
   int64_t n_rows;      // valid bank rows
@@ -62,7 +65,8 @@ struct SearchParams {
   int n_chunks;        // bank chunks per query block
   int n_tiles;         // ceil(n_rows / 256)
   uint64_t* cand;      // (n_chunks, n_qblocks*128*CG, KP) candidate keys
-  uint32_t* tau_seed;  // (n_qblocks*128*CG) per-query shared threshold, ordered-float bits (0 = none yet)
+  uint32_t* board;     // (2, 2*n_chunks, q_pad) published list statistics, ordered-float bits (0 = none yet):
+                       // plane 0 = every list's KL-th best, plane 1 = its (KL/2)-th best (see the epilogue)
   float* dump;         // optional (n_queries, n_rows) raw scores (validation only)
   unsigned long long* stats;  // optional (CTAs, 8 warps, 8) cycle counters (instrumented build only)
   int prefetch_tiles;  // > 0: L2-prefetch bank tiles this many tiles ahead (split over the CTAs)
@@ -313,12 +317,14 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
     }
   } else if (warp < kEpiWarps) {
     // =========================== epilogue: fused top-k' ===========================
-    constexpr int KL = KP / 2;                    // list length per (row, column half)
+    constexpr int KL = KP / 2;                    // list length per (row, column set)
     constexpr int QC = kQueueCap;
+    constexpr uint32_t kQStride = kEpiThreads * 8;  // bytes between consecutive queue entries of a thread
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
-    const int half = warp >> 2;                   // column set: 32-column chunks half, half+2, half+4, half+6
+    const int half = warp >> 2;                   // which of the two per-row lists this thread keeps
     const int row_in_tile = quarter * 32 + lane;  // query row owned by this thread
-    uint2* queue = reinterpret_cast<uint2*>(smem + L::kRingBytes) + threadIdx.x;  // entry j at [j*kEpiThreads]
+    const uint2* queue = reinterpret_cast<const uint2*>(smem + L::kRingBytes) + threadIdx.x;  // entry j at [j*kEpiThreads]
+    const uint32_t queue_addr = smem_base + L::kRingBytes + threadIdx.x * 8u;
     uint32_t* rows = reinterpret_cast<uint32_t*>(smem + L::kRingBytes + L::kQueueBytes) + threadIdx.x;
     const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const uint32_t tempty_leader0 = (CG == 2) ? ptx::mapa(tempty_bar(0), 0) : tempty_bar(0);
@@ -334,6 +340,8 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         if (CG == 2) ptx::mbar_arrive_cluster(bar); else ptx::mbar_arrive_local(bar);
       }
     };
+    const int64_t q_pad = static_cast<int64_t>(p.n_qblocks) * BM * CG;
+    const int n_slots = 2 * p.n_chunks;
     for (int item = cluster_id; item < total_items; item += n_clusters) {
       const int qb = item % p.n_qblocks, chunk = item / p.n_qblocks;
       const int t0 = chunk_tile_begin(p.n_tiles, p.n_chunks, chunk);
@@ -345,35 +353,73 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         ls[j] = -INFINITY;
         rows[j * kEpiThreads] = 0xffffffffu;  // "no candidate"
       }
-      int cnt = 0;  // queued, not yet folded
+      uint32_t qtop = queue_addr;  // shared-memory address of this thread's next free queue entry
       long long st_wait = 0, st_load = 0, st_slow = 0, st_fold = 0, st_nfold = 0, st_nslow = 0, st_tiles = 0, t_a = 0;
-      // Live threshold sharing: every list that scans bank rows for this query (2 column halves x
-      // n_chunks chunks, on different CTAs, possibly at the same time) publishes its current
-      // k'/2-th best score with a global atomicMax and re-reads the maximum once per tile.  A
-      // published value has k'/2 better candidates behind it, so nothing below it can be among the
-      // query's best k'/2: lists stay exact for those, and the start-up transient of each list
-      // is paid once, jointly.
-      uint32_t* seed_ptr = p.tau_seed + q_row;
-      float seed = -INFINITY;
-      float tau = -INFINITY;
-      uint32_t seed_bits = __ldcg(seed_ptr);
+      // Threshold sharing through the board.  Every list that scans bank rows for this query (2 per
+      // chunk, chunks on different CTAs, at the same time or one after the other) publishes two
+      // statistics after each fold: its KL-th best score (plane 0) and its (KL/2)-th best (plane 1).
+      // If two lists each hold KL scores >= x, or four lists each hold KL/2 scores >= x, then the
+      // bank holds 2*KL = k' rows scoring >= x, so a row below x is not among the query's best k'.
+      // x = max(2nd largest of plane 0, 4th largest of plane 1) over a window of up to 8 lists is
+      // therefore a threshold every list may prune with.  Together with a list's own KL-th best:
+      // a row of the query's bf16 top-k' is dropped only if KL better rows share its list.
+      const int slot = 2 * chunk + half;
+      int w0 = 2 * chunk - 4;
+      if (w0 > n_slots - 8) w0 = n_slots - 8;
+      if (w0 < 0) w0 = 0;
+      const int w1 = (w0 + 8 < n_slots) ? w0 + 8 : n_slots;
+      auto board_bound = [&]() -> float {
+        const uint32_t* brd = p.board + static_cast<int64_t>(w0) * q_pad + q_row;
+        const int64_t plane = static_cast<int64_t>(n_slots) * q_pad;
+        uint32_t x[8], y[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+          const bool in = w0 + s < w1;  // warp-uniform; a slot must not be counted twice
+          x[s] = in ? __ldcg(brd + s * q_pad) : 0u;
+          y[s] = in ? __ldcg(brd + plane + s * q_pad) : 0u;
+        }
+        uint32_t f1 = 0, f2 = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+          f2 = max(f2, min(f1, x[s]));
+          f1 = max(f1, x[s]);
+          const uint32_t a = min(h1, y[s]);
+          h1 = max(h1, y[s]);
+          const uint32_t b = min(h2, a);
+          h2 = max(h2, a);
+          const uint32_t c = min(h3, b);
+          h3 = max(h3, b);
+          h4 = max(h4, c);
+        }
+        const uint32_t bound = max(f2, h4);
+        return bound ? ordered_to_f32(bound) : -INFINITY;
+      };
+      auto publish = [&]() {
+        uint32_t* pub = p.board + static_cast<int64_t>(slot) * q_pad + q_row;
+        __stcg(pub, f32_to_ordered(ls[KL - 1]));
+        __stcg(pub + static_cast<int64_t>(n_slots) * q_pad, f32_to_ordered(ls[KL / 2 - 1]));
+      };
+      float shared_tau = -INFINITY;  // best bound read from the board so far
+      float tau = -INFINITY;         // max(shared_tau, own KL-th best)
       for (int tile = t0; tile < t1; ++tile) {
+        // every tile while the lists of this query are young (their statistics move fast and short
+        // chunks are over before a sparse schedule pays), every kBoardPeriod tiles afterwards
+        if ((tile - t0 < kBoardDense || ((tile - t0) & (kBoardPeriod - 1)) == 0) && MODE != 3 && MODE != 4) {
+          shared_tau = fmaxf(shared_tau, board_bound());
+          tau = fmaxf(tau, shared_tau);
+        }
         if (MODE == 2) t_a = clock64();
         ptx::mbar_wait(tfull_bar(abuf), aphase, 4);
         ptx::tc_fence_after();
         if (MODE == 2) { st_wait += clock64() - t_a; ++st_tiles; }
-        // software-pipelined refresh of the shared threshold: the value loaded during the previous
-        // tile is applied now and the next load is issued, so its L2 latency is never waited on
-        if (((tile - t0) & 7) == 0) {
-          if (seed_bits) seed = fmaxf(seed, ordered_to_f32(seed_bits));
-          tau = fmaxf(tau, seed);
-          seed_bits = __ldcg(seed_ptr);
-        }
         const int64_t col_base = static_cast<int64_t>(tile) * BN;
         const int64_t rem = p.n_rows - col_base;
         const int nvalid = rem >= BN ? BN : static_cast<int>(rem);  // valid columns of this tile (>= 1)
         const uint32_t tacc = tmem_lane + static_cast<uint32_t>(abuf * BN);
-        const int c_first = half * kChunk;
+        // the two lists of a row take alternate 32-column chunks of a tile, and which list takes the
+        // even ones changes pseudo-randomly from tile to tile: bank rows with a regular stride (the
+        // same patch position in consecutive images) do not pile up in one list
+        const int c_first = (half ^ static_cast<int>((static_cast<uint32_t>(tile) * 0x9E3779B1u) >> 31)) * kChunk;
 #pragma unroll 1
         for (int c0 = c_first; c0 < BN; c0 += 2 * kChunk) {  // this warp's interleaved column set
           if (c0 >= nvalid || MODE == 3) break;  // warp-uniform
@@ -388,10 +434,11 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             for (int j = 0; j < kChunk; ++j)
               if (c0 + j < nvalid) p.dump[q_row * p.n_rows + col_base + c0 + j] = __uint_as_float(v[j]);
           }
-          if (c0 + kChunk > nvalid) {  // last, partial tile of the bank: padded rows never win
+          const int nv = nvalid - c0;  // valid columns of this chunk (may exceed kChunk)
+          if (nv < kChunk) {  // last, partial tile of the bank: padded rows never win
 #pragma unroll
             for (int j = 0; j < kChunk; ++j)
-              if (c0 + j >= nvalid) v[j] = 0xff800000u;  // -inf
+              if (j >= nv) v[j] = 0xff800000u;  // -inf
           }
           // fast reject: per-group maxima against tau, one warp-wide OR of the 4-bit result
           float mg[kGroups];
@@ -411,47 +458,45 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             if (last_chunk) release_accumulator();
           } else {
             if (MODE == 2) { t_a = clock64(); ++st_nslow; }
-            // Survivors of a group are appended with independent stores (slot = cnt + rank of the
-            // column among the lane's hits).  If some lane's queue cannot take its hits, the warp
-            // folds first -- that needs the registers v occupies, so the chunk is re-read from TMEM
-            // afterwards (the accumulator is still ours) and appending resumes at that group.
+            // Survivors are appended to the thread's queue with predicated stores through a running
+            // address.  A group adds at most 8 entries per lane; if some lane has fewer than 8 free
+            // the warp folds first -- that needs the registers v occupies, so the chunk is re-read
+            // from TMEM afterwards (the accumulator is still ours) and appending resumes there.
+            const uint32_t code0 = static_cast<uint32_t>(col_base) + static_cast<uint32_t>(c0);
             int resume = 0;
             for (;;) {
               int blocked = -1;
 #pragma unroll
               for (int g = 0; g < kGroups; ++g) {
                 if (blocked < 0 && g >= resume && ((hot >> g) & 1u)) {
-                  uint32_t hm = 0;
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) hm |= (__uint_as_float(v[8 * g + j]) > tau ? 1u : 0u) << j;
-                  const int h = __popc(hm);
-                  if (__any_sync(0xffffffffu, cnt + h > QC)) {
+                  if (__any_sync(0xffffffffu, qtop > queue_addr + (QC - 8) * kQStride)) {
                     blocked = g;
                   } else {
-                    const uint32_t col = static_cast<uint32_t>(col_base + c0 + 8 * g);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                      if ((hm >> j) & 1u)
-                        queue[(cnt + __popc(hm & ((1u << j) - 1u))) * kEpiThreads] = make_uint2(v[8 * g + j], col + j);
+                      if (__uint_as_float(v[8 * g + j]) > tau) {
+                        // the bank row is formed here, under the predicate, and not hoisted to the
+                        // entry of the slow path for all 32 columns (most groups are not hot)
+                        ptx::st_shared_v2(qtop, v[8 * g + j], ptx::add_volatile(code0, static_cast<uint32_t>(8 * g + j)));
+                        qtop += kQStride;
+                      }
                     }
-                    cnt += h;
                   }
                 }
               }
               if (blocked < 0) break;
               if (MODE == 2) ++st_nfold;
-              fold_queue<KL, QC>(ls, rows, queue, cnt);  // v is dead here
-              cnt = 0;
-              const float worst = ls[KL - 1];
-              if (worst > seed) atomicMax(seed_ptr, f32_to_ordered(worst));
-              tau = fmaxf(seed, worst);
+              fold_queue<KL, QC>(ls, rows, queue, static_cast<int>((qtop - queue_addr) / kQStride));  // v is dead here
+              qtop = queue_addr;
+              publish();
+              tau = fmaxf(shared_tau, ls[KL - 1]);
               resume = blocked;
               ptx::tmem_ld_chunk(tacc + c0, v);
               ptx::tmem_ld_wait();
-              if (c0 + kChunk > nvalid) {
+              if (nv < kChunk) {
 #pragma unroll
                 for (int j = 0; j < kChunk; ++j)
-                  if (c0 + j >= nvalid) v[j] = 0xff800000u;
+                  if (j >= nv) v[j] = 0xff800000u;
               }
             }
             if (last_chunk) release_accumulator();
@@ -459,22 +504,24 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
           }
         }
         if (c_first >= nvalid || MODE == 3) release_accumulator();  // nothing was read
-        // routine folds happen here, after the accumulator was released, and only when some lane's
-        // queue is nearly full: a fold costs ~1.5k cycles of this warp, and the MMA of the tile after
-        // next waits for the slowest of all epilogue warps, so folds must be rare
-        if (__any_sync(0xffffffffu, cnt > QC - 4)) {
+        // routine folds happen here, after the accumulator was released, whenever some lane could not
+        // take another full group: a fold costs ~1k cycles of this warp, and the MMA of the tile after
+        // next waits for the slowest of all epilogue warps
+        if (__any_sync(0xffffffffu, qtop > queue_addr + (QC - 8) * kQStride)) {
           if (MODE == 2) { t_a = clock64(); ++st_nfold; }
-          fold_queue<KL, QC>(ls, rows, queue, cnt);
-          cnt = 0;
-          const float worst = ls[KL - 1];
-          if (worst > seed) atomicMax(seed_ptr, f32_to_ordered(worst));
-          tau = fmaxf(seed, worst);
+          fold_queue<KL, QC>(ls, rows, queue, static_cast<int>((qtop - queue_addr) / kQStride));
+          qtop = queue_addr;
+          publish();
+          tau = fmaxf(shared_tau, ls[KL - 1]);
           if (MODE == 2) st_fold += clock64() - t_a;
         }
         abuf ^= 1;
         if (abuf == 0) aphase ^= 1u;
       }
-      if (__any_sync(0xffffffffu, cnt > 0)) fold_queue<KL, QC>(ls, rows, queue, cnt);
+      if (__any_sync(0xffffffffu, qtop > queue_addr)) {
+        fold_queue<KL, QC>(ls, rows, queue, static_cast<int>((qtop - queue_addr) / kQStride));
+        publish();  // lists that start later begin with this one's final statistics
+      }
       if (MODE == 2 && lane == 0) {
         unsigned long long* o = p.stats + (static_cast<size_t>(blockIdx.x) * kEpiWarps + warp) * 8;
         atomicAdd(o + 0, static_cast<unsigned long long>(st_wait));
@@ -485,8 +532,7 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         atomicAdd(o + 5, static_cast<unsigned long long>(st_nfold));
         atomicAdd(o + 6, static_cast<unsigned long long>(st_tiles));
       }
-      // emit this item's candidates (k'/2 per column set; the re-rank kernel merges them)
-      const int64_t q_pad = static_cast<int64_t>(p.n_qblocks) * BM * CG;
+      // emit this item's candidates (k'/2 per list; the re-rank kernel merges them)
       uint64_t* out = p.cand + (static_cast<int64_t>(chunk) * q_pad + q_row) * KP + half * KL;
 #pragma unroll
       for (int j = 0; j < KL; ++j) {
@@ -597,19 +643,18 @@ static int dispatch_search(const Bank* b, int cg, int kp, const CUtensorMap& tma
   return HB_ERR_INVALID;
 }
 
-int rerank_launch(const Bank* b, const float* q, int64_t Q, int k, int kp,
-                  int n_chunks, int64_t q_pad, const uint64_t* cand, int64_t idx_offset,
-                  float* out_scores, int64_t* out_idx, const Scatter* sc, cudaStream_t st);  // rerank.cu
-
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_t idx_offset,
                 float* out_scores, int64_t* out_idx, float* out_qnorm, float* dump, int cg_override,
-                cudaStream_t st, const Scatter* sc) {
+                cudaStream_t st, const Scatter* sc, const LabelOut* lo) {
   // measured on B200 (profiles/): CTA pairs (cta_group::2: half the B-operand shared-memory traffic
   // per SM) win at every bank size and feature dim; cta_group 1 stays selectable
   int cg = cg_override ? cg_override : (b->cfg_cta_group ? b->cfg_cta_group : 2);
   if (b->num_sms < 2) cg = 1;
+  // Small banks have too few tiles to spread a query's best rows over many lists: keep k'/2 = 64
+  // per list there (strict bf16 top-64 per list; the cost is irrelevant at this size).
+  if (b->rows <= kSmallBankRows && kp < 128 && dump == nullptr) kp = 128;
   const SearchPlan plan = plan_search(b->rows, Q, cg, b->num_sms, b->cfg_max_chunks);
   const int64_t q_pad = static_cast<int64_t>(plan.n_qblocks) * BM * cg;
 
@@ -617,7 +662,9 @@ int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_t idx_o
   const size_t off_q = 0;
   const size_t off_norm = align_up(off_q + sizeof(__nv_bfloat16) * static_cast<size_t>(Q) * b->dpad, 256);
   const size_t off_cand = align_up(off_norm + sizeof(float) * static_cast<size_t>(Q), 256);
-  const size_t off_seed = align_up(off_cand + sizeof(uint64_t) * static_cast<size_t>(plan.n_chunks) * q_pad * kp, 256);
+  // threshold board: 2 planes x (2 lists per chunk) x padded queries
+  const size_t off_board = align_up(off_cand + sizeof(uint64_t) * static_cast<size_t>(plan.n_chunks) * q_pad * kp, 256);
+  const size_t board_bytes = sizeof(uint32_t) * 4 * static_cast<size_t>(plan.n_chunks) * q_pad;
   int n_units_used = 1;
   const int variant = dump ? 1 : (b->cfg_ablate ? 2 + b->cfg_ablate : (b->cfg_stats ? 2 : 0));
   int& cached_fit = b->fit_cache[cg - 1][kp == 128 ? 2 : (kp == 64 ? 1 : 0)][variant];
@@ -641,18 +688,18 @@ int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_t idx_o
   }
   const int n_rounds = (plan.n_qblocks * plan.n_chunks + n_units_used - 1) / n_units_used;
   const int pace_groups = (plan.n_tiles / plan.n_chunks + 1) / kPaceTiles + 2;
-  const size_t off_pace = align_up(off_seed + sizeof(uint32_t) * static_cast<size_t>(q_pad), 256);
+  const size_t off_pace = align_up(off_board + board_bytes, 256);
   const size_t total = off_pace + sizeof(uint32_t) * static_cast<size_t>(n_rounds) * pace_groups;
-  int rc = ensure_workspace(b, total);
+  int rc = ensure_workspace(b, total, st);
   if (rc != HB_OK) return rc;
   uint8_t* ws = static_cast<uint8_t*>(b->ws);
   __nv_bfloat16* q_bf16 = reinterpret_cast<__nv_bfloat16*>(ws + off_q);
   float* qnorm = out_qnorm ? out_qnorm : reinterpret_cast<float*>(ws + off_norm);
   uint64_t* cand = reinterpret_cast<uint64_t*>(ws + off_cand);
-  uint32_t* tau_seed = reinterpret_cast<uint32_t*>(ws + off_seed);
+  uint32_t* board = reinterpret_cast<uint32_t*>(ws + off_board);
   uint32_t* pace = reinterpret_cast<uint32_t*>(ws + off_pace);
-  // seeds and pacing counters are contiguous: one memset
-  HB_CHECK_CUDA(cudaMemsetAsync(tau_seed, 0, total - off_seed, st));
+  // board and pacing counters are contiguous: one memset
+  HB_CHECK_CUDA(cudaMemsetAsync(board, 0, total - off_board, st));
 
   b->last_launches = 0;
   int64_t blocks = std::min<int64_t>(ceil_div64(Q, 8), static_cast<int64_t>(b->num_sms) * 8);
@@ -672,7 +719,7 @@ int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_t idx_o
   p.n_chunks = plan.n_chunks;
   p.n_tiles = plan.n_tiles;
   p.cand = cand;
-  p.tau_seed = tau_seed;
+  p.board = board;
   p.pace = b->cfg_pace ? pace : nullptr;
   p.pace_groups = pace_groups;
   p.dump = dump;
@@ -688,9 +735,15 @@ int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_t idx_o
     b->timing_count++;
   }
   b->last_launches++;
-  if (out_scores == nullptr && sc == nullptr) return HB_OK;  // dump-only call
+  if (dump != nullptr) return HB_OK;  // validation call: raw scores only
 
-  rc = rerank_launch(b, q, Q, k, kp, plan.n_chunks, q_pad, cand, idx_offset, out_scores, out_idx, sc, st);
+  LabelOut label;
+  if (lo != nullptr) {
+    label = *lo;
+    label.qnorm = qnorm;
+  }
+  rc = rerank_launch(b, q, Q, k, kp, plan.n_chunks, q_pad, cand, idx_offset, out_scores, out_idx, sc,
+                     lo ? &label : nullptr, st);
   if (rc != HB_OK) return rc;
   b->last_launches++;
   return HB_OK;
@@ -718,7 +771,69 @@ int hb_search(hb_bank_t* bank, const float* q_dev, int64_t Q, int k, int k_prime
   HB_REQUIRE(b->rows >= 1, "hb_search: the bank is empty");
   HB_CHECK_CUDA(cudaSetDevice(b->device));
   return hb::search_impl(b, q_dev, Q, k, k_prime, idx_offset, out_scores_dev, out_idx_dev, out_qnorm_dev,
-                         nullptr, 0, static_cast<cudaStream_t>(stream), nullptr);
+                         nullptr, 0, static_cast<cudaStream_t>(stream), nullptr, nullptr);
+}
+
+static int fill_label_out(const Bank* b, const uint16_t* label_table_dev, int64_t table_rows, float beta,
+                          float* out_label_hat_dev, hb::LabelOut* lo, const char* who) {
+  HB_REQUIRE(out_label_hat_dev != nullptr, "%s: out_label_hat_dev is NULL", who);
+  HB_REQUIRE(beta > 0.f, "%s: beta must be positive", who);
+  HB_REQUIRE((b->flags & HB_BANK_L2) == 0, "%s: label transfer needs an inner-product bank (unit-norm rows)", who);
+  lo->table = label_table_dev ? label_table_dev : b->label_hist;
+  lo->table_rows = label_table_dev ? table_rows : b->rows;
+  HB_REQUIRE(lo->table_rows >= 1, "%s: empty label table", who);
+  lo->C = b->C;
+  lo->pp = b->pp;
+  lo->beta = beta;
+  lo->out = out_label_hat_dev;
+  return HB_OK;
+}
+
+int hb_search_transfer(hb_bank_t* bank, const uint16_t* label_table_dev, int64_t table_rows,
+                       const float* q_dev, int64_t Q, int k, int k_prime, int64_t idx_offset, float beta,
+                       float* out_scores_dev, int64_t* out_idx_dev, float* out_qnorm_dev,
+                       float* out_label_hat_dev, void* stream) {
+  HB_REQUIRE(bank != nullptr, "hb_search_transfer: bank is NULL");
+  Bank* b = reinterpret_cast<Bank*>(bank);
+  if (!b->finalized) {
+    hb::set_error("hb_search_transfer: bank not finalized (call hb_bank_finalize first)");
+    return HB_ERR_STATE;
+  }
+  HB_REQUIRE(Q >= 0 && Q < (int64_t(1) << 31), "hb_search_transfer: Q=%lld out of range", (long long)Q);
+  HB_REQUIRE(k >= 1 && k <= k_prime, "hb_search_transfer: need 1 <= k (%d) <= k_prime (%d)", k, k_prime);
+  HB_REQUIRE(k_prime == 32 || k_prime == 64 || k_prime == 128, "hb_search_transfer: k_prime=%d not in {32, 64, 128}", k_prime);
+  HB_REQUIRE((out_scores_dev == nullptr) == (out_idx_dev == nullptr), "hb_search_transfer: give both or neither of out_scores/out_idx");
+  if (Q == 0) return HB_OK;
+  HB_REQUIRE(q_dev != nullptr, "hb_search_transfer: q_dev is NULL");
+  HB_REQUIRE(b->rows >= 1, "hb_search_transfer: the bank is empty");
+  hb::LabelOut lo;
+  int rc = fill_label_out(b, label_table_dev, table_rows, beta, out_label_hat_dev, &lo, "hb_search_transfer");
+  if (rc != HB_OK) return rc;
+  HB_CHECK_CUDA(cudaSetDevice(b->device));
+  return hb::search_impl(b, q_dev, Q, k, k_prime, idx_offset, out_scores_dev, out_idx_dev, out_qnorm_dev,
+                         nullptr, 0, static_cast<cudaStream_t>(stream), nullptr, &lo);
+}
+
+int hb_eval_step(hb_bank_t* bank, const uint16_t* label_table_dev, int64_t table_rows, const float* q_dev,
+                 int B, int S, int H, int W, const float* y_dev, int k, int k_prime, int64_t idx_offset,
+                 float beta, int ignore_index, float* label_hat_dev, int64_t* conf_dev,
+                 uint8_t* out_pred_dev, float* out_scores_dev, int64_t* out_idx_dev, void* stream) {
+  HB_REQUIRE(bank != nullptr, "hb_eval_step: bank is NULL");
+  HB_REQUIRE(B >= 0 && S >= 1 && H >= 1 && W >= 1, "hb_eval_step: bad shape B=%d S=%d H=%d W=%d", B, S, H, W);
+  if (B == 0) return HB_OK;
+  HB_REQUIRE(y_dev != nullptr && conf_dev != nullptr, "hb_eval_step: y_dev / conf_dev is NULL");
+  const int64_t Q = static_cast<int64_t>(B) * S * S;
+  int rc = hb_search_transfer(bank, label_table_dev, table_rows, q_dev, Q, k, k_prime, idx_offset, beta,
+                              out_scores_dev, out_idx_dev, nullptr, label_hat_dev, stream);
+  if (rc != HB_OK) return rc;
+  Bank* b = reinterpret_cast<Bank*>(bank);
+  rc = hb::predict_score_launch(label_hat_dev, B, S, b->C, H, W, y_dev, nullptr, ignore_index, conf_dev,
+                                out_pred_dev, static_cast<cudaStream_t>(stream));
+  if (rc == HB_ERR_UNSUPPORTED)
+    hb::set_error("hb_eval_step: %d classes exceed the fused tail's shared-memory histogram; use "
+                  "hb_search_transfer + hb_decode_mask + hb_predict_score", b->C);
+  if (rc == HB_OK) b->last_launches++;
+  return rc;
 }
 
 int hb_search_stats(hb_bank_t* bank, unsigned long long* stats_dev) {
@@ -814,7 +929,7 @@ int hb_search_dump_scores(hb_bank_t* bank, const float* q_dev, int64_t Q, float*
   HB_REQUIRE(Q * b->rows <= (int64_t(1) << 28), "hb_search_dump_scores: Q*rows too large for a debug dump");
   HB_CHECK_CUDA(cudaSetDevice(b->device));
   return hb::search_impl(b, q_dev, Q, 1, 64, 0, nullptr, nullptr, nullptr, out_dev, cta_group,
-                         static_cast<cudaStream_t>(stream), nullptr);
+                         static_cast<cudaStream_t>(stream), nullptr, nullptr);
 }
 
 }  // extern "C"

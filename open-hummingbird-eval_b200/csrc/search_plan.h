@@ -40,10 +40,13 @@ inline SearchPlan plan_search(int64_t rows, int64_t Q, int cta_group, int num_sm
   int cap = max_chunks > 0 ? max_chunks : 64;
   if (cap > p.n_tiles) cap = p.n_tiles;
   // Prefer few, long chunks (tighter running thresholds, fewer candidate lists); take more only
-  // when that fills the last wave noticeably better.
-  int best = 1;
+  // when that fills the last wave noticeably better.  At least two chunks (= four candidate lists
+  // per query) unless the caller caps it: the top-k' bound of the search rests on the query's best
+  // rows being spread over several lists (search.cu).
+  int first = (cap >= 2 && max_chunks != 1) ? 2 : 1;
+  int best = first;
   double best_eff = 0.0;
-  for (int c = 1; c <= cap; ++c) {
+  for (int c = first; c <= cap; ++c) {
     const int64_t items = static_cast<int64_t>(p.n_qblocks) * c;
     const int64_t waves = (items + p.n_units - 1) / p.n_units;
     // each item costs ~n_tiles/c tiles; the job takes waves * ceil(n_tiles/c) tile-times

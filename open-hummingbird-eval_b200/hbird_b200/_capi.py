@@ -12,6 +12,9 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_uint, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "lib", "libhbird_b200.so"))
+# Measurement tooling only (tools/gpu_probe.py A/B runs): load another build of the library, e.g. the
+# previous round's, whose export list may be shorter.  The product never sets this.
+_AB_LIB = os.environ.get("HBIRD_B200_AB_LIB")
 
 HB_OK = 0
 HB_ERR_INVALID = -1
@@ -40,6 +43,10 @@ _SIGNATURES = [
     ("hb_bank_label_table", c_void_p, [c_void_p]),
     ("hb_bank_export", c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     ("hb_search", c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    ("hb_search_transfer", c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int64, c_float,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    ("hb_eval_step", c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
+                             c_int64, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     ("hb_search_config", c_int, [c_void_p, c_int, c_int]),
     ("hb_search_tune", c_int, [c_void_p, c_int, c_int]),
     ("hb_search_stats", c_int, [c_void_p, c_void_p]),
@@ -50,6 +57,8 @@ _SIGNATURES = [
     ("hb_plan_search", c_int, [c_int64, c_int64, c_int, c_int, c_int, POINTER(c_int)]),
     ("hb_search_dump_scores", c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p]),
     ("hb_merge_topk", c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    ("hb_merge_topk_transfer", c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_int64, c_int, c_int, c_void_p,
+                                       c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     ("hb_exchange_create", c_int, [c_int, c_int, c_int, c_int64, c_int, POINTER(c_void_p)]),
     ("hb_exchange_destroy", c_int, [c_void_p]),
     ("hb_exchange_handle", c_int, [c_void_p, c_void_p, c_int]),
@@ -58,9 +67,13 @@ _SIGNATURES = [
     ("hb_exchange_disconnect", c_int, [c_void_p]),
     ("hb_search_scatter", c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int64, POINTER(c_int64), c_void_p, c_void_p]),
     ("hb_exchange_merge", c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    ("hb_exchange_merge_transfer", c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p,
+                                           c_void_p, c_void_p]),
     ("hb_exchange_slice_rows", c_int64, [c_void_p]),
     ("hb_label_transfer", c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p]),
     ("hb_upsample_argmax", c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    ("hb_predict_score", c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                 c_void_p]),
     ("hb_decode_mask", c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     ("hb_confusion_accumulate", c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
 ]
@@ -74,8 +87,10 @@ def _load() -> ctypes.CDLL:
             "`python __graft_entry__.py` (or `make -C open-hummingbird-eval_b200/csrc`). "
             "There is no CPU or PyTorch fallback for this path."
         )
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = ctypes.CDLL(_AB_LIB or LIB_PATH)
     for name, restype, argtypes in _SIGNATURES:
+        if _AB_LIB and not hasattr(lib, name):
+            continue
         fn = getattr(lib, name)  # AttributeError if the header and the library drifted apart
         fn.restype = restype
         fn.argtypes = argtypes

@@ -25,6 +25,7 @@ from __future__ import annotations
 import logging
 from typing import Any, Dict, Optional
 
+import numpy as np
 import torch
 
 from . import distributed as hdist
@@ -40,11 +41,25 @@ BETA = 0.02  # cross-attention temperature, hbird_eval.py:576
 
 class HbirdEvaluation:
     """Build the patch memory bank from `train_loader`, then evaluate `val_loader` by kNN label
-    transfer.  Loaders are any iterable of (x fp32 (B,3,H,W), y fp32 = class_id/255 (B,1,H,W))."""
+    transfer.  Loaders are any iterable of (x fp32 (B,3,H,W), y fp32 = class_id/255 (B,1,H,W)).
+
+    Multi-GPU (torch.distributed initialised, one process per GPU) follows the reference's two faiss
+    layouts, selected like there by nn_params["idx_shard"] (search_faiss.py:7,53-74):
+      False (default) — replicas (IndexReplicas): every rank ends up with the whole bank and the
+                        validation batches are dealt round-robin to the ranks; no data-path
+                        collective, one all-reduce of the (C, C) matrix at the end;
+      True            — row shards (IndexShards): rank r keeps the rows it built; every rank searches
+                        every query against its shard, the shard results are exchanged (fused NVLink
+                        exchange or NCCL all-gather + merge) and each rank post-processes its image
+                        slice of the batch.  Features are extracted once: rank r runs the ViT on its
+                        slice of the batch and the queries are all-gathered."""
+
+    _B200_PARAMS = ("k_prime", "keep_f32", "gpu_ids", "exchange", "idx_shard", "use_fp16", "distance_measure",
+                    "cta_group", "max_chunks")
 
     def __init__(self, feature_extractor: torch.nn.Module, train_loader, num_classes: int,
                  n_neighbours: int = 30, augmentation_epoch: int = 1, device: torch.device | str = "cpu",
-                 nn_method: str = "b200", nn_params: Optional[Dict[str, Any]] = None,
+                 nn_method: str = "scann", nn_params: Optional[Dict[str, Any]] = None,
                  memory_size: Optional[int] = None, dataset_size: Optional[int] = None,
                  f_mem_p: Optional[str] = None, l_mem_p: Optional[str] = None) -> None:
         self.nn_params = dict(nn_params or {})
@@ -62,13 +77,27 @@ class HbirdEvaluation:
         self.feature_extractor.eval()
         self.augmentation_epoch = augmentation_epoch
         self.memory_size = memory_size
-        self.n_neighbours = n_neighbours
+        self.n_neighbours = int(n_neighbours)
         self.num_classes = num_classes
         self.f_mem_p, self.l_mem_p = f_mem_p, l_mem_p
         self.num_sampled_features: Optional[int] = None
         self.rank, self.world = hdist.dist_info()
-        self.k_prime = int(self.nn_params.get("k_prime", 64))
-        self.keep_f32 = bool(self.nn_params.get("keep_f32", True))
+        self.idx_shard = bool(self.nn_params.get("idx_shard", False)) and self.world > 1
+        if nn_method == "b200":
+            unknown = sorted(set(self.nn_params) - set(self._B200_PARAMS))
+            if unknown:  # the faiss backend swallows unknown names (search_faiss.py:7); a typo should not be silent
+                raise TypeError(f"nn_params not understood by the b200 backend: {unknown} (known: {sorted(self._B200_PARAMS)})")
+            if not 1 <= self.n_neighbours <= 128:
+                raise ValueError(f"n_neighbours={n_neighbours} outside the b200 backend's range [1, 128]")
+        elif self.world > 1:
+            raise ValueError(f"nn_method={nn_method!r} is a single-process backend; multi-GPU runs need nn_method='b200'")
+        # k' (candidates kept by the bf16 pass): the best k'/2 are strict, see include/hbird_b200.h
+        default_kp = 64 if self.n_neighbours <= 32 else 128
+        self.k_prime = int(self.nn_params.get("k_prime", default_kp))
+        if nn_method == "b200" and self.n_neighbours > self.k_prime // 2:
+            logger.warning("n_neighbours=%d > k_prime/2=%d: neighbours beyond rank %d of the bf16 pass are covered "
+                           "statistically, not strictly", self.n_neighbours, self.k_prime // 2, self.k_prime // 2)
+        self.keep_f32 = bool(self.nn_params.get("keep_f32", not self.nn_params.get("use_fp16", False)))
 
         S = self.feature_extractor.eval_spatial_resolution
         if self.memory_size is not None:
@@ -86,72 +115,123 @@ class HbirdEvaluation:
 
     # ------------------------------------------------------------------ bank construction
     def _capacity_rows(self, loader_len: Optional[int], first_batch: int, S: int) -> int:
-        if self.memory_size is not None:
-            return int(self.memory_size)
+        """Rows this rank can be asked to hold: its share of the loader's batches over ALL
+        augmentation epochs (the batch counter runs on across epochs) times the rows per batch."""
+        per_image = S * S if self.memory_size is None else int(self.num_sampled_features)
         if loader_len is None:
-            raise ValueError("train_loader must define __len__ when memory_size is None")
-        my_batches = (loader_len - self.rank + self.world - 1) // self.world
-        return max(1, my_batches * first_batch * S * S * self.augmentation_epoch)
+            if self.memory_size is None:
+                raise ValueError("train_loader must define __len__ when memory_size is None")
+            return int(self.memory_size)
+        my_batches = (self.augmentation_epoch * loader_len - self.rank + self.world - 1) // self.world
+        cap = max(1, my_batches * first_batch * per_image)
+        return cap if self.memory_size is None else min(cap, int(self.memory_size))
 
     @torch.no_grad()
     def _create_memory(self, train_loader, num_classes: int, eval_spatial_resolution: int) -> int:
-        """hbird_eval.py:283-369.  With world_size > 1 rank r takes batches r, r+W, ... and owns
-        the rows it produces (row-sharded bank)."""
+        """hbird_eval.py:283-369.  With world_size > 1 rank r takes batches r, r+W, ... and builds the
+        rows they produce; with idx_shard it keeps them (row-sharded bank), otherwise the shards are
+        then replicated to every rank."""
         S = eval_spatial_resolution
         d = self.feature_extractor.d_model
         loader_len = len(train_loader) if hasattr(train_loader, "__len__") else None
         step = 0
-        for _ in range(self.augmentation_epoch):
-            for x, y in train_loader:
-                mine = (step % self.world) == self.rank
-                step += 1
-                if not mine:
-                    continue
-                x = x.to(self.device)
-                y = y.to(self.device, dtype=torch.float32)
-                B, _, H, W = x.shape
-                ps = x.shape[-1] // S
-                if H != S * ps or W != S * ps:
-                    raise ValueError(f"input {H}x{W} is not eval_spatial_resolution*patch = {S}*{ps}")
-                feats, _ = self.feature_extractor.forward_features(x)
-                feats = feats.to(torch.float32).contiguous()
-                mask = ops.decode_mask(y.contiguous(), True).view(B, H, W)
-                if self.bank is None:
-                    cap = self._capacity_rows(loader_len, B, S)
-                    self.bank = ops.MemoryBank(d, num_classes, ps * ps, cap, self.device.index, self.keep_f32)
-                    self._ps = ps
-                if self.memory_size is None:
-                    self.bank.append(feats, mask, S, ps)
-                else:
-                    sel = self._sample_patches(mask, S, ps, num_classes)
-                    room = self.bank.capacity - self.bank.rows
-                    if sel.numel() > room:  # the reference's slice assignment would raise here too
-                        raise ValueError("memory_size exhausted before the training set was consumed")
-                    self.bank.append(feats, mask, S, ps, sel)
-        if self.bank is None:
-            raise ValueError("train_loader yielded no batches for this rank")
-        self.bank.finalize()
-        # replicate the label table and fix the global row offset of this shard
+        error: Optional[BaseException] = None
+        try:
+            for _ in range(self.augmentation_epoch):
+                for x, y in train_loader:
+                    mine = (step % self.world) == self.rank
+                    step += 1
+                    if not mine:
+                        continue
+                    x = x.to(self.device)
+                    y = y.to(self.device, dtype=torch.float32)
+                    B, _, H, W = x.shape
+                    ps = x.shape[-1] // S
+                    if H != S * ps or W != S * ps:
+                        raise ValueError(f"input {H}x{W} is not eval_spatial_resolution*patch = {S}*{ps}")
+                    feats, _ = self.feature_extractor.forward_features(x)
+                    feats = feats.to(torch.float32).contiguous()
+                    mask = ops.decode_mask(y.contiguous(), True).view(B, H, W)
+                    if self.bank is None:
+                        cap = self._capacity_rows(loader_len, B, S)
+                        self.bank = ops.MemoryBank(d, num_classes, ps * ps, cap, self.device.index, self.keep_f32)
+                        self._ps = ps
+                    if self.memory_size is None:
+                        self.bank.append(feats, mask, S, ps)
+                    else:
+                        sel = self._sample_patches(mask, S, ps, num_classes)
+                        room = self.bank.capacity - self.bank.rows
+                        if sel.numel() > room:  # the reference's slice assignment would raise here too
+                            raise ValueError("memory_size exhausted before the training set was consumed")
+                        self.bank.append(feats, mask, S, ps, sel)
+            if self.bank is None:
+                raise ValueError("train_loader yielded no batches for this rank")
+            self.bank.finalize()
+        except Exception as e:  # noqa: BLE001 - re-raised below, on every rank
+            error = e
+        # one rank's failure must not leave the others waiting in the collectives below
+        if not hdist.all_ranks_ok(error is None, self.device):
+            if error is not None:
+                raise error
+            raise RuntimeError("memory-bank construction failed on another rank")
         counts = hdist.gather_counts(self.bank.rows, self.device)
+        if self.world > 1 and not self.idx_shard:
+            self._replicate_bank(counts)
+            counts = [self.bank.rows]
+            self.idx_offset = 0
+        else:
+            self.idx_offset = hdist.offsets_from_counts(counts)[self.rank]
         self.shard_counts = counts
-        self.idx_offset = hdist.offsets_from_counts(counts)[self.rank]
         self.total_rows = sum(counts)
-        self.label_table = hdist.all_gather_rows(self.bank.label_table(), counts)
-        logger.info("Memory bank: %d rows on this rank, %d total, d=%d", self.bank.rows, self.total_rows, d)
+        # the label table is indexed by global row: replicated when the bank is sharded
+        self.label_table = hdist.all_gather_rows(self.bank.label_table(), counts) if self.idx_shard \
+            else self.bank.label_table()
+        logger.info("Memory bank: %d rows on this rank, %d total, d=%d (%s)", self.bank.rows, self.total_rows, d,
+                    "row shards" if self.idx_shard else ("replicas" if self.world > 1 else "single GPU"))
         return self.bank.rows
+
+    def _replicate_bank(self, counts, slab: int = 1 << 18) -> None:
+        """Replicas layout (search_faiss.py:65-74): every rank receives every shard's packed rows
+        (slab-wise broadcasts of the fp32 unit rows and soft labels) and re-packs them, so all ranks
+        hold the same bank in the same global row order (rank-major)."""
+        import torch.distributed as dist
+
+        d, C = self.bank.d, self.num_classes
+        full = ops.MemoryBank(d, C, self.bank.patch_pixels, max(1, sum(counts)), self.device.index, self.keep_f32)
+        for r, n in enumerate(counts):
+            for a in range(0, n, slab):
+                m = min(slab, n - a)
+                if self.rank == r:
+                    f, l = self.bank.export(a, m)
+                else:
+                    f = torch.empty((m, d), dtype=torch.float32, device=self.device)
+                    l = torch.empty((m, C), dtype=torch.float32, device=self.device)
+                dist.broadcast(f, src=r)
+                dist.broadcast(l, src=r)
+                full.append_soft(f, l, normalise=False)
+        full.finalize()
+        self.bank.close()
+        self.bank = full
 
     def _sample_patches(self, mask: torch.Tensor, S: int, ps: int, num_classes: int) -> torch.Tensor:
         """Bounded-memory sampler, hbird_eval.py:447-517: per image keep the K patches with the
-        smallest score*U(0,1) (hb_sample_patches).  U is drawn with the CPU generator, one value
-        per patch in image order exactly as the reference does (:497-508; every patch is non-empty
-        once 255 -> 0 is applied), and uploaded, so a seeded run picks the same patches.
+        smallest score*U(0,1) (hb_sample_patches).  U is drawn with the CPU generator in image order
+        exactly as the reference does (:497-508: one value per NON-EMPTY patch, i.e. per patch that
+        holds a label in [0, C); a patch of out-of-range labels only consumes no draw and scores 1e6)
+        and uploaded, so a seeded run picks the same patches.
         Returns int32 flat source rows (b*S*S + patch) on the device, ascending score per image."""
         B = mask.shape[0]
         K = int(self.num_sampled_features)
         if K > S * S:
             raise ValueError(f"memory_size asks for {K} patches per image but an image has only {S * S}")
-        uniform = torch.rand(B * S * S).to(mask.device, non_blocking=True)
-        return ops.sample_patches(mask, S, ps, num_classes, uniform, K)
+        uniform = torch.ones(B * S * S)  # empty patches: 1e6 * 1, as the reference (:494-506)
+        if num_classes >= 256:  # uint8 ids are always < C: every patch is non-empty
+            uniform = torch.rand(B * S * S)
+        else:
+            nonempty = (mask.view(B, S, ps, S, ps) < num_classes).any(dim=4).any(dim=2).reshape(-1).cpu()
+            n = int(nonempty.sum())
+            uniform[nonempty] = torch.rand(n)
+        return ops.sample_patches(mask, S, ps, num_classes, uniform.to(mask.device, non_blocking=True), K)
 
     def _save_memory(self) -> None:
         """hbird_eval.py:371-378 — same on-disk format: fp32 (N,d) and (N,C) tensors.  With a sharded
@@ -159,9 +239,11 @@ class HbirdEvaluation:
         if self.f_mem_p is None and self.l_mem_p is None:
             return
         want_f, want_l = self.f_mem_p is not None, self.l_mem_p is not None
-        if self.world == 1:
-            f, l = self.bank.export(features=want_f, labels=want_l)
-            f, l = (f.cpu() if want_f else None), (l.cpu() if want_l else None)
+        if not self.idx_shard:
+            f = l = None
+            if self.rank == 0:
+                f, l = self.bank.export(features=want_f, labels=want_l)
+                f, l = (f.cpu() if want_f else None), (l.cpu() if want_l else None)
         else:
             f, l = self._collect_memory_on_rank0(want_f, want_l)
         if self.rank == 0:
@@ -207,8 +289,8 @@ class HbirdEvaluation:
 
     def load_memory(self) -> bool:
         """hbird_eval.py:380-400 — reload the tensors written by _save_memory (fp32 (N, d) unit rows and
-        (N, C) soft labels) and rebuild the HBM bank and the search backend from them.  With
-        world_size > 1 every rank takes its contiguous row range of the files (a row-sharded bank)."""
+        (N, C) soft labels) and rebuild the HBM bank and the search backend from them.  With a sharded
+        bank every rank takes its contiguous row range of the files; replicas load all of them."""
         import os
 
         if not (self.f_mem_p and self.l_mem_p and os.path.isfile(self.f_mem_p) and os.path.isfile(self.l_mem_p)):
@@ -218,7 +300,7 @@ class HbirdEvaluation:
         l = torch.load(self.l_mem_p, mmap=True)
         if f.shape[0] != l.shape[0]:
             raise ValueError(f"feature memory has {f.shape[0]} rows, label memory {l.shape[0]}")
-        a, b = hdist.shard_bounds(f.shape[0], self.world, self.rank)
+        a, b = hdist.shard_bounds(f.shape[0], self.world, self.rank) if self.idx_shard else (0, f.shape[0])
         pp = self.bank.patch_pixels
         new_bank = ops.MemoryBank(f.shape[1], l.shape[1], pp, max(1, b - a), self.device.index, self.keep_f32)
         step = 1 << 20
@@ -229,17 +311,22 @@ class HbirdEvaluation:
         new_bank.finalize()
         self.bank.close()
         self.bank = new_bank
-        counts = hdist.gather_counts(new_bank.rows, self.device)
+        if self.idx_shard:
+            counts = hdist.gather_counts(new_bank.rows, self.device)
+            self.idx_offset = hdist.offsets_from_counts(counts)[self.rank]
+            self.label_table = hdist.all_gather_rows(new_bank.label_table(), counts)
+        else:
+            counts, self.idx_offset = [new_bank.rows], 0
+            self.label_table = new_bank.label_table()
         self.shard_counts, self.total_rows = counts, sum(counts)
-        self.idx_offset = hdist.offsets_from_counts(counts)[self.rank]
-        self.label_table = hdist.all_gather_rows(new_bank.label_table(), counts)
         self.__dict__.pop("_export_cache", None)
         self._create_nn(self.n_neighbours, nn_method=self.nn_method, **self.nn_params)
         return True
 
     @property
     def feature_memory(self) -> torch.Tensor:
-        """The reference's feature_memory (N, d) fp32 CPU tensor, materialised on demand."""
+        """The reference's feature_memory (N, d) fp32 CPU tensor, materialised on demand (this
+        rank's rows when the bank is sharded)."""
         return self.bank.export(labels=False)[0].cpu()
 
     @property
@@ -249,8 +336,8 @@ class HbirdEvaluation:
     def _create_nn(self, n_neighbours: int = 30, nn_method: str = "b200", **kwargs) -> None:
         """hbird_eval.py:267-281, through the registry."""
         if nn_method == "b200":
-            kw = {k: v for k, v in kwargs.items() if k not in ("k_prime", "keep_f32", "gpu_ids", "exchange")}
-            measure = str(kw.pop("distance_measure", "dot_product")).lower()
+            kw = {k: v for k, v in kwargs.items() if k in ("cta_group", "max_chunks", "idx_shard", "use_fp16")}
+            measure = str(kwargs.get("distance_measure", "dot_product")).lower()
             if measure not in ("dot_product", "l2", "euclidean"):
                 raise ValueError(f"Unsupported distance measure: {measure}")  # search_faiss.py:48
             # Bank rows are unit-norm (hbird_eval.py:324), so ||q-x||^2 = ||q||^2 + 1 - 2 q.x ranks
@@ -262,32 +349,26 @@ class HbirdEvaluation:
                 idx_offset=self.idx_offset, gpu_ids=[self.device.index], **kw)
         else:
             # legacy / third-party plugins take the reference's CPU feature tensor
+            measure = str(kwargs.get("distance_measure", "dot_product")).lower()
+            if measure != "dot_product":
+                # the reference ignores the backend's distances and re-derives cosines (:594-609); the
+                # ranking of a non-IP backend over unit rows is the same, so only IP is wired here
+                raise ValueError("legacy backends are driven with distance_measure='dot_product' only")
             self.NN_algorithm = create_nn_backend(nn_method, self.feature_memory, n_neighbors=n_neighbours, **kwargs)
 
     # ------------------------------------------------------------------ evaluation
-    def _search(self, q: torch.Tensor, n_images: int):
-        """(scores, global idx, qnorm, b0, b1): neighbours of the queries of images [b0, b1) — the
-        slice of the batch this rank post-processes (all of it when the bank is not sharded)."""
-        per_img = q.shape[0] // n_images
-        b0, b1 = hdist.split_range(n_images, self.world, self.rank)
-        sl = slice(b0 * per_img, b1 * per_img)
-        if self.nn_method != "b200":
-            idx_np, dist_np = self.NN_algorithm.find_nearest_neighbors(q.cpu())
-            idx = torch.as_tensor(idx_np.astype("int64"), device=self.device)
-            scores = torch.as_tensor(dist_np, dtype=torch.float32, device=self.device)
-            qn = torch.linalg.vector_norm(q, dim=1)
-        elif self.world > 1 and self._exchange_for(q.shape[0], n_images) is not None:
-            # fused exchange: K2b scatters over NVLink, the merge kernel waits for every shard
-            qsplit = hdist.query_split(n_images, per_img, self.world)
-            qn = self._xchg.search_scatter(self.bank, q, qsplit, self.n_neighbours, self.k_prime, self.idx_offset)
-            scores, idx = self._xchg.merge()
-            return scores, idx, qn[sl], b0, b1
-        else:
-            scores, idx, qn = self.NN_algorithm.search_device(q, self.n_neighbours)
-        if self.world > 1:
-            gs, gi = hdist.all_gather_topk(scores, idx)
-            scores, idx = ops.merge_topk(gs, gi)
-        return scores[sl], idx[sl], qn[sl], b0, b1
+    def _legacy_neighbours(self, q: torch.Tensor):
+        """faiss / scann / third-party plugin: host round trip as in the reference (:624-629).  The
+        backend's distances are NOT used (they may be approximate or another metric): exact inner
+        products with the bank rows are recomputed on the device, as _cross_attention does."""
+        idx_np, _ = self.NN_algorithm.find_nearest_neighbors(q.cpu())
+        idx = torch.as_tensor(np.asarray(idx_np).astype("int64"), device=self.device)
+        if not hasattr(self, "_export_cache"):
+            self._export_cache = self.bank.export(labels=False)[0]
+        rows = self._export_cache.index_select(0, idx.reshape(-1).clamp_min(0)).view(idx.shape[0], idx.shape[1], -1)
+        scores = torch.einsum("qkd,qd->qk", rows, q)
+        scores = torch.where(idx >= 0, scores, torch.full_like(scores, float("-inf")))
+        return scores, idx, torch.linalg.vector_norm(q, dim=1)
 
     def _exchange_for(self, n_queries: int, n_images: int):
         """The ShardExchange, (re)built when a batch needs a larger window.  Every rank sees the
@@ -319,42 +400,87 @@ class HbirdEvaluation:
             self.bank.close()
             self.bank = None
 
+    def _features(self, x: torch.Tensor) -> torch.Tensor:
+        feats, _ = self.feature_extractor.forward_features(x)
+        return feats.to(torch.float32).contiguous()
+
+    def _sharded_batch(self, x: torch.Tensor, want_neighbours: bool):
+        """Row-sharded bank: (label_hat, scores, idx, b0, b1) for the image slice [b0, b1) of the
+        batch this rank post-processes.  Features are extracted once across the ranks: each rank runs
+        the extractor on its slice and the query rows are all-gathered (every shard must see every
+        query).  Then K2/K2b per shard -> exchange -> merge with the label transfer fused in."""
+        B = x.shape[0]
+        b0, b1 = hdist.split_range(B, self.world, self.rank)
+        img_counts = [hdist.split_range(B, self.world, r) for r in range(self.world)]
+        if b1 > b0:
+            mine = self._features(x[b0:b1].to(self.device))
+            N, d = mine.shape[1], mine.shape[2]
+        else:
+            N, d = self.feature_extractor.eval_spatial_resolution ** 2, self.feature_extractor.d_model
+            mine = torch.empty((0, N, d), dtype=torch.float32, device=self.device)
+        q = hdist.all_gather_rows(mine.view(-1, d), [(e - a) * N for a, e in img_counts])
+        k, kp = self.n_neighbours, self.k_prime
+        pp = self.bank.patch_pixels
+        if self._exchange_for(B * N, B) is not None:
+            qsplit = hdist.query_split(B, N, self.world)
+            qn = self._xchg.search_scatter(self.bank, q, qsplit, k, kp, self.idx_offset)
+            lh, s, i = self._xchg.merge_transfer(self.label_table, pp, qn[b0 * N:b1 * N].contiguous(), BETA, want_neighbours)
+        else:
+            s, i, qn = self.bank.search(q, k, kp, self.idx_offset)
+            gs, gi = hdist.all_gather_topk(s, i)
+            sl = slice(b0 * N, b1 * N)
+            lh, s, i = ops.merge_topk_transfer(gs[:, sl].contiguous(), gi[:, sl].contiguous(), self.label_table, pp,
+                                               qn[sl].contiguous(), BETA, want_neighbours)
+        return lh, s, i, q, b0, b1
+
     @torch.no_grad()
     def evaluate(self, val_loader, eval_spatial_resolution: int, return_knn_details: bool = False,
                  ignore_index: int = 255):
         """hbird_eval.py:184-265.  Returns the mIoU (Python float in [0, 1]) or (mIoU, details)."""
         S = eval_spatial_resolution
         C = self.num_classes
-        metric = PredsmIoU(C, C, device=self.device, ignore_index=ignore_index)
-        knns, knns_labels, knns_ca = [], [], []
-        for x, y in val_loader:
-            x = x.to(self.device)
+        metric = PredsmIoU(C, C, device=self.device, ignore_index=ignore_index, store_reordered_preds=False)
+        conf = metric.confusion_buffer()
+        details = []  # per batch: (batch number, knns, knns_labels, knns_ca_labels) CPU tensors
+        replicas = self.world > 1 and not self.idx_shard
+        for step, (x, y) in enumerate(val_loader):
+            if replicas and step % self.world != self.rank:
+                continue  # replicas: the batches are dealt round-robin, nothing is exchanged
             B, _, h, w = x.shape
-            feats, _ = self.feature_extractor.forward_features(x)
-            feats = feats.to(torch.float32).contiguous()
-            N, d = feats.shape[1], feats.shape[2]
-            gt = ops.decode_mask(y.to(self.device, dtype=torch.float32).contiguous(), False).view(B, h, w)
-            scores, idx, qn, b0, b1 = self._search(feats.view(B * N, d), B)
-            # each rank post-processes its image slice of the batch
-            label_hat = None
-            if b1 > b0:
-                label_hat = ops.label_transfer(self.label_table, self.bank.patch_pixels, scores, idx, qn, BETA)
-                pred = ops.upsample_argmax(label_hat, b1 - b0, S, h, w)
-                metric.update(gt[b0:b1], pred)
+            if self.idx_shard:
+                lh, s, i, q, b0, b1 = self._sharded_batch(x, return_knn_details)
+                if b1 > b0:
+                    ys = y[b0:b1].to(self.device, dtype=torch.float32).contiguous()
+                    ops.predict_score(lh, b1 - b0, S, h, w, conf, y=ys, ignore_index=ignore_index)
+                N, d = q.shape[0] // B, q.shape[1]
+            else:
+                feats = self._features(x.to(self.device))
+                N, d = feats.shape[1], feats.shape[2]
+                q = feats.view(B * N, d)
+                ys = y.to(self.device, dtype=torch.float32).contiguous()
+                if self.nn_method != "b200":
+                    s, i, qn = self._legacy_neighbours(q)
+                    lh = ops.label_transfer(self.label_table, self.bank.patch_pixels, s, i, qn, BETA)
+                    ops.predict_score(lh, B, S, h, w, conf, y=ys, ignore_index=ignore_index)
+                elif return_knn_details:
+                    lh, _, s, i = self.bank.search_transfer(q, self.n_neighbours, self.k_prime, 0, BETA, None, True)
+                    ops.predict_score(lh, B, S, h, w, conf, y=ys, ignore_index=ignore_index)
+                else:  # the whole batch in one call: prep, K2, K2b+K4a, fused tail
+                    self.bank.eval_step(q, ys, S, conf, ignore_index, self.n_neighbours, self.k_prime, BETA)
             if return_knn_details:
                 k = self.n_neighbours
-                if label_hat is None:
-                    label_hat = torch.empty((0, C), dtype=torch.float32, device=self.device)
-                kf, kl, lh = self._gather_details(idx, label_hat, B, N)
-                knns.append(kf.view(-1, N, k, d).cpu())
-                knns_labels.append(kl.view(-1, N, k, C).cpu())
-                knns_ca.append(lh.view(-1, N, C).cpu())
+                kf, kl, lhd = self._gather_details(i, lh, B, N)
+                details.append((step, kf.view(-1, N, k, d).cpu(), kl.view(-1, N, k, C).cpu(), lhd.view(-1, N, C).cpu()))
         jac, tp, fp, fn, _, _ = metric.compute(is_global_zero=True, sync_distributed=self.world > 1,
                                                return_reordered=False)
         self.last_confusion = metric.confusion_matrix()
         if return_knn_details:
-            return jac, {"knns": torch.cat(knns), "knns_labels": torch.cat(knns_labels),
-                         "knns_ca_labels": torch.cat(knns_ca)}
+            if replicas:  # every rank returns the whole validation set, in batch order, as the reference does
+                gathered = [None] * self.world
+                torch.distributed.all_gather_object(gathered, details)
+                details = sorted((t for part in gathered for t in part), key=lambda t: t[0])
+            return jac, {"knns": torch.cat([t[1] for t in details]), "knns_labels": torch.cat([t[2] for t in details]),
+                         "knns_ca_labels": torch.cat([t[3] for t in details])}
         return jac
 
     def _gather_details(self, idx: torch.Tensor, label_hat: torch.Tensor, n_images: int, per_img: int):
@@ -363,7 +489,7 @@ class HbirdEvaluation:
         bank every rank contributes the feature rows it owns (one all-reduce of the (Q, k, d) tensor:
         exactly one rank holds each row, the others add zeros) and the slices of idx / label_hat are
         all-gathered; the soft labels come from the replicated label table."""
-        if self.world > 1:
+        if self.idx_shard:
             counts = [hdist.split_range(n_images, self.world, r) for r in range(self.world)]
             counts = [(b - a) * per_img for a, b in counts]
             idx = hdist.all_gather_rows(idx, counts)
@@ -375,7 +501,7 @@ class HbirdEvaluation:
         local = flat - self.idx_offset
         mine = (local >= 0) & (local < self.bank.rows)
         kf = f.index_select(0, local.clamp(0, self.bank.rows - 1)) * mine.unsqueeze(1).to(f.dtype)
-        if self.world > 1:
+        if self.idx_shard:
             torch.distributed.all_reduce(kf)
         table = torch.as_tensor(self.label_table, device=self.device)
         kl = table.index_select(0, flat.clamp_min(0)).to(torch.float32) / float(self.bank.patch_pixels)
@@ -384,7 +510,7 @@ class HbirdEvaluation:
 
 def hbird_evaluation(model, d_model: int, patch_size: int, dataset_name, data_dir: str, batch_size: int = 64,
                      input_size: int = 224, augmentation_epoch: int = 1, device: str | torch.device = "cpu",
-                     return_knn_details: bool = False, n_neighbours: int = 30, nn_method: str = "b200",
+                     return_knn_details: bool = False, n_neighbours: int = 30, nn_method: str = "scann",
                      nn_params: Optional[Dict[str, Any]] = None, ftr_extr_fn=None,
                      memory_size: Optional[int] = None, num_workers: int = 8, ignore_index: int = 255,
                      train_fs_path: Optional[str] = None, val_fs_path: Optional[str] = None):

@@ -144,6 +144,61 @@ class MemoryBank:
                             ptr(qn), stream_ptr(q.device)))
         return scores, idx, qn
 
+    def search_transfer(self, q: torch.Tensor, k: int = 30, k_prime: int = 64, idx_offset: int = 0,
+                        beta: float = 0.02, label_table: Optional[torch.Tensor] = None, return_neighbours: bool = False):
+        """K2 + K2b with K4a fused into the re-rank warp.  Returns (label_hat fp32 (Q, C), qnorm fp32 (Q,),
+        scores, idx) — scores/idx are None unless return_neighbours.  label_table: int16 (rows, C) indexed by
+        global row (None = this bank's own table)."""
+        q = _require_cuda(q, "q", torch.float32)
+        if q.dim() != 2 or q.shape[1] != self.d:
+            raise ValueError(f"queries must be (Q, {self.d}), got {tuple(q.shape)}")
+        Q = q.shape[0]
+        table_rows = 0
+        if label_table is not None:
+            label_table = _require_cuda(label_table, "label_table", torch.int16)
+            if label_table.dim() != 2 or label_table.shape[1] != self.num_classes:
+                raise ValueError(f"label_table must be (rows, {self.num_classes})")
+            table_rows = label_table.shape[0]
+        lh = torch.empty((Q, self.num_classes), dtype=torch.float32, device=q.device)
+        qn = torch.empty((Q,), dtype=torch.float32, device=q.device)
+        scores = torch.empty((Q, k), dtype=torch.float32, device=q.device) if return_neighbours else None
+        idx = torch.empty((Q, k), dtype=torch.int64, device=q.device) if return_neighbours else None
+        check(lib.hb_search_transfer(self._h, ptr(label_table), table_rows, ptr(q), Q, int(k), int(k_prime),
+                                     int(idx_offset), float(beta), ptr(scores), ptr(idx), ptr(qn), ptr(lh),
+                                     stream_ptr(q.device)))
+        return lh, qn, scores, idx
+
+    def eval_step(self, q: torch.Tensor, y: torch.Tensor, S: int, conf: torch.Tensor, ignore_index: Optional[int],
+                  k: int = 30, k_prime: int = 64, beta: float = 0.02, label_table: Optional[torch.Tensor] = None,
+                  idx_offset: int = 0, label_hat: Optional[torch.Tensor] = None, pred: Optional[torch.Tensor] = None,
+                  scores: Optional[torch.Tensor] = None, idx: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One validation batch in 4 launches (hb_eval_step): q fp32 (B*S*S, d) raw features, y fp32
+        (B, 1, H, W) or (B, H, W) = id/255, conf int64 (C, C) accumulated in place.  Optional
+        pre-allocated outputs (label_hat (B*S*S, C) fp32, pred (B, H, W) uint8, scores/idx (B*S*S, k))
+        make the call allocation-free, i.e. capturable in a CUDA graph.  Returns label_hat."""
+        q = _require_cuda(q, "q", torch.float32)
+        y = _require_cuda(y, "y", torch.float32)
+        conf = _require_cuda(conf, "conf", torch.int64)
+        H, W = int(y.shape[-2]), int(y.shape[-1])
+        B = y.numel() // (H * W)
+        if q.shape != (B * S * S, self.d):
+            raise ValueError(f"queries must be (B*S*S, d) = ({B * S * S}, {self.d}), got {tuple(q.shape)}")
+        if tuple(conf.shape) != (self.num_classes, self.num_classes):
+            raise ValueError(f"conf must be ({self.num_classes}, {self.num_classes})")
+        table_rows = 0
+        if label_table is not None:
+            label_table = _require_cuda(label_table, "label_table", torch.int16)
+            table_rows = label_table.shape[0]
+        if label_hat is None:
+            label_hat = torch.empty((B * S * S, self.num_classes), dtype=torch.float32, device=q.device)
+        if (scores is None) != (idx is None):
+            raise ValueError("give both or neither of scores / idx")
+        ig = -1 if ignore_index is None else int(ignore_index)
+        check(lib.hb_eval_step(self._h, ptr(label_table), table_rows, ptr(q), B, int(S), H, W, ptr(y), int(k),
+                               int(k_prime), int(idx_offset), float(beta), ig, ptr(label_hat), ptr(conf), ptr(pred),
+                               ptr(scores), ptr(idx), stream_ptr(q.device)))
+        return label_hat
+
     def tune_search(self, prefetch_tiles: int = -1, ablate: int = 0) -> None:
         """ablate != 0 is for measurement only (wrong results): 1 = GEMM pipeline alone, 2 = scan only."""
         check(lib.hb_search_tune(self._h, int(prefetch_tiles), int(ablate)))
@@ -265,6 +320,24 @@ class ShardExchange:
         self._k = int(k)
         return qn
 
+    def merge_transfer(self, label_table: torch.Tensor, patch_pixels: int, qnorm_slice: torch.Tensor,
+                       beta: float = 0.02, return_neighbours: bool = False):
+        """K3x with K4a fused into the merging warp: (label_hat (rows, C), scores, idx) of this rank's
+        slice of the last scatter (scores/idx None unless return_neighbours)."""
+        label_table = _require_cuda(label_table, "label_table", torch.int16)
+        qnorm_slice = _require_cuda(qnorm_slice, "qnorm_slice", torch.float32)
+        rows = int(lib.hb_exchange_slice_rows(self._h))
+        if qnorm_slice.numel() != rows:
+            raise ValueError(f"qnorm_slice must hold {rows} norms, got {qnorm_slice.numel()}")
+        trows, C = label_table.shape
+        dev = torch.device("cuda", self.device)
+        lh = torch.empty((rows, C), dtype=torch.float32, device=dev)
+        out_s = torch.empty((rows, self._k), dtype=torch.float32, device=dev) if return_neighbours else None
+        out_i = torch.empty((rows, self._k), dtype=torch.int64, device=dev) if return_neighbours else None
+        check(lib.hb_exchange_merge_transfer(self._h, ptr(label_table), trows, C, int(patch_pixels), ptr(qnorm_slice),
+                                             float(beta), ptr(out_s), ptr(out_i), ptr(lh), stream_ptr(dev)))
+        return lh, out_s, out_i
+
     def merge(self):
         """(scores fp32 (rows, k), idx int64 (rows, k)) of this rank's slice of the last scatter."""
         rows = int(lib.hb_exchange_slice_rows(self._h))
@@ -273,6 +346,58 @@ class ShardExchange:
         out_i = torch.empty((rows, self._k), dtype=torch.int64, device=dev)
         check(lib.hb_exchange_merge(self._h, ptr(out_s), ptr(out_i), stream_ptr(dev)))
         return out_s, out_i
+
+
+def predict_score(label_hat: torch.Tensor, B: int, S: int, H: int, W: int, conf: Optional[torch.Tensor] = None,
+                  y: Optional[torch.Tensor] = None, gt_u8: Optional[torch.Tensor] = None,
+                  ignore_index: Optional[int] = None, return_pred: bool = False) -> Optional[torch.Tensor]:
+    """Fused tail (hb_predict_score): mask decode + bilinear upsample + argmax + confusion update in one
+    pass (hbird_eval.py:219,235-243; eval_metrics.py:73-109).  label_hat fp32 (B*S*S, C); ground truth as
+    y fp32 id/255 (B,1,H,W)/(B,H,W) or gt_u8 uint8 (B,H,W); conf int64 (C, C) accumulated in place.
+    Returns the uint8 (B, H, W) prediction map when return_pred, else None."""
+    label_hat = _require_cuda(label_hat, "label_hat", torch.float32)
+    C = label_hat.shape[-1]
+    if label_hat.numel() != B * S * S * C:
+        raise ValueError("label_hat must hold B*S*S rows")
+    dev = label_hat.device
+    if conf is not None:
+        conf = _require_cuda(conf, "conf", torch.int64)
+        if tuple(conf.shape) != (C, C):
+            raise ValueError(f"conf must be ({C}, {C})")
+        if y is None and gt_u8 is None:
+            raise ValueError("scoring needs y or gt_u8")
+    if y is not None:
+        y = _require_cuda(y, "y", torch.float32)
+        if y.numel() != B * H * W:
+            raise ValueError(f"Shapes must match. Got gt={tuple(y.shape)}, pred={(B, H, W)}")
+    if gt_u8 is not None:
+        gt_u8 = _require_cuda(gt_u8, "gt", torch.uint8)
+        if gt_u8.numel() != B * H * W:
+            raise ValueError(f"Shapes must match. Got gt={tuple(gt_u8.shape)}, pred={(B, H, W)}")
+    pred = torch.empty((B, H, W), dtype=torch.uint8, device=dev) if (return_pred or conf is None) else None
+    ig = -1 if ignore_index is None else int(ignore_index)
+    check(lib.hb_predict_score(ptr(label_hat), B, S, C, H, W, ptr(y), ptr(gt_u8), ig, ptr(conf), ptr(pred),
+                               stream_ptr(dev)))
+    return pred
+
+
+def merge_topk_transfer(shard_scores: torch.Tensor, shard_idx: torch.Tensor, label_table: torch.Tensor,
+                        patch_pixels: int, qnorm: torch.Tensor, beta: float = 0.02, return_neighbours: bool = False):
+    """K3 with K4a fused: (G, Q, k) gathered per-shard results -> label_hat (Q, C) (+ merged (scores, idx))."""
+    shard_scores = _require_cuda(shard_scores, "shard_scores", torch.float32)
+    shard_idx = _require_cuda(shard_idx, "shard_idx", torch.int64)
+    label_table = _require_cuda(label_table, "label_table", torch.int16)
+    qnorm = _require_cuda(qnorm, "qnorm", torch.float32)
+    G, Q, k = shard_scores.shape
+    rows, C = label_table.shape
+    dev = shard_scores.device
+    lh = torch.empty((Q, C), dtype=torch.float32, device=dev)
+    out_s = torch.empty((Q, k), dtype=torch.float32, device=dev) if return_neighbours else None
+    out_i = torch.empty((Q, k), dtype=torch.int64, device=dev) if return_neighbours else None
+    check(lib.hb_merge_topk_transfer(ptr(shard_scores), ptr(shard_idx), G, Q, k, ptr(label_table), rows, C,
+                                     int(patch_pixels), ptr(qnorm), float(beta), ptr(out_s), ptr(out_i), ptr(lh),
+                                     stream_ptr(dev)))
+    return lh, out_s, out_i
 
 
 def merge_topk(shard_scores: torch.Tensor, shard_idx: torch.Tensor):

@@ -163,6 +163,8 @@ def perf(res):
     shapes = [("cfg1", 12544, 102400, 384), ("cfg2", 12544, 1024000, 384),
               ("cfg3_shard8", 21904, 1280000, 768), ("d768_1M", 21904, 1024000, 768)]
     variants = [(1, -1, 0, 64), (2, -1, 0, 64), (1, -1, 2, 64), (2, -1, 2, 64), (2, -1, 1, 64), (2, -1, 0, 32), (2, -1, 0, 128)]
+    if os.environ.get("PROBE_FAST"):
+        variants = [(2, -1, 0, 64), (2, -1, 2, 64), (2, -1, 1, 64)]
     if os.environ.get("PROBE_SHAPES"):
         shapes = [s for s in shapes if s[0] in os.environ["PROBE_SHAPES"].split(",")]
     for (name, Q, N, d) in shapes:
@@ -218,6 +220,6 @@ if __name__ == "__main__":
         res["ok"] = False
         res["error"] = f"{type(e).__name__}: {e}"
     res["seconds"] = time.time() - t0
-    with open(os.path.join(OUT, f"probe_{stage}.json"), "w") as f:
+    with open(os.path.join(OUT, f"probe_{stage}{os.environ.get('PROBE_TAG', '')}.json"), "w") as f:
         json.dump(res, f, indent=1)
     print(json.dumps(res, indent=1))
