@@ -1,22 +1,32 @@
 """bench.py — patch-queries/sec of the dense nearest-neighbour evaluation hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3] [--impl b200|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One "step" = one pass of the hot path over one validation batch of synthetic VOC-shaped input:
-mask decode -> kNN search against the HBM-resident memory bank (tcgen05 GEMM + fused top-k', exact
-fp32 re-rank) -> soft label transfer -> bilinear upsample + argmax -> confusion-matrix update.
-Default workload = BASELINE.json configs[1] ("cfg2": DINO ViT-S/16 224 px, 1,024,000-patch bank,
-d=384, k=30, 64 images = 12,544 patch-queries per step).
+query prep -> kNN search against the HBM-resident memory bank (tcgen05 GEMM + fused top-k', exact
+fp32 re-rank with the label transfer fused in) -> fused tail (mask decode + bilinear upsample +
+argmax + confusion-matrix update); 4 kernel launches.
 
-N > 1: one process per GPU.  Primary number = query-parallel replicas (the reference's default
-faiss.IndexReplicas layout, search_faiss.py:65-74: full bank on every GPU, each rank evaluates its
-own batches, no data-path collective) -> weak scaling.  The row-sharded bank (north star item 3:
-per-shard search -> NCCL all-gather -> k-way merge kernel) is timed in the same run and reported
-under "sharded".
+Default workload = BASELINE.json configs[2], the north-star configuration ("cfg3": DINOv2 ViT-B/14
+518 px, 10,240,000-patch bank, d=768, k=30, 16 images = 21,904 patch-queries per step).
+
+N = 1: the bank lives on one GPU.  N > 1 (one process per GPU): the headline `value` is the
+ROW-SHARDED bank (faiss.IndexShards, search_faiss.py:53-63; N/G rows per GPU, every rank searches
+every query, shard results exchanged by the fused NVLink exchange, each rank post-processes its
+image slice) — strong scaling.  Replicas (faiss.IndexReplicas, :65-74; weak scaling) and the other
+BASELINE configs are reported under `by_workload` in the same line ("q/s vs bank size").
+
+`e2e` = the same metric through the engine's public call with HOST inputs: one
+`HbirdEvaluation.evaluate([batch])` per step (pinned host features and masks in, Python float mIoU
+out; H2D copies, confusion-matrix read-back and Hungarian matching inside the timed region).
+
+`parity` = the timed inputs through the CUDA path against the CPU oracle (recall@30, score error on
+a query sample; mIoU / confusion matrix / pixel agreement on whole images).
 
 `--impl reference` times the CPU oracle port of the reference path (numpy/BLAS on all host cores)
-on a bounded sample of the same workload; under torchrun only rank 0 runs it.
+on a bounded sample of the same workload, with the same synthetic bank generated on the host; it
+does not import the product library.  Under torchrun only rank 0 runs it.
 """
 from __future__ import annotations
 
@@ -35,79 +45,72 @@ for p in (ROOT, os.path.join(ROOT, "open-hummingbird-eval_b200")):
 WORKLOADS = {
     # name: bank rows, d, S, patch px, classes, ignore, images per step
     "cfg1": dict(N=102_400, d=384, S=14, ps=16, C=21, ignore=255, B=64,
-                 desc="DINO ViT-S/16 224px, 102,400-patch bank, d=384, k=30"),
+                 desc="DINO ViT-S/16 224px, 102,400-patch bank, d=384, k=30 (BASELINE configs[0])"),
     "cfg2": dict(N=1_024_000, d=384, S=14, ps=16, C=21, ignore=255, B=64,
                  desc="DINO ViT-S/16 224px, 1,024,000-patch bank, d=384, k=30 (BASELINE configs[1])"),
     "cfg3": dict(N=10_240_000, d=768, S=37, ps=14, C=21, ignore=255, B=16,
                  desc="DINOv2 ViT-B/14 518px, 10,240,000-patch bank, d=768, k=30 (BASELINE configs[2])"),
     "cfg4": dict(N=10_240_000, d=1024, S=37, ps=14, C=151, ignore=0, B=16,
-                 desc="DINOv2 ViT-L/14 518px, ADE20K-shaped, 10,240,000-patch bank, d=1024, k=30"),
+                 desc="DINOv2 ViT-L/14 518px, ADE20K-shaped (150 classes), 10,240,000-patch bank, d=1024, k=30 (BASELINE configs[3])"),
 }
 K_NEIGH, K_PRIME, BETA = 30, 64, 0.02
 RING = 8  # distinct query batches cycled through (with the bank: inputs far larger than the 126 MB L2)
+PATH = ("query prep -> tcgen05 bf16 GEMM + fused top-k' -> fp32 exact re-rank + label transfer -> "
+        "fused tail (decode + upsample + argmax + confusion)")
 
 
 def load_peaks():
     try:
         pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        return float(pk["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+        return {"tf": float(pk["bf16_tflops_sustained"]), "tf_burst": float(pk["bf16_tflops"]), "hbm": float(pk["hbm_gbs"]),
+                "src": "measured (MEASURED_PEAKS.json: bf16_tflops_sustained, hbm_gbs)"}
     except Exception:
-        return 1400.0, "fallback (B200_PROFILING.md sustained)"
+        return {"tf": 1400.0, "tf_burst": 1590.0, "hbm": 6650.0, "src": "fallback (B200_PROFILING.md)"}
 
 
 # ----------------------------------------------------------------------------- synthetic inputs
-def synth_images(w, n_img, gen, device):
-    """(features (n, S*S, d) fp32 raw, masks (n, H, H) uint8) generated on the device: class-prototype
-    features + noise, un-normalised; blocky label maps with ~2 % ignore pixels."""
+def bank_slabs(w, row0, row1, device, slab_rows=1 << 19):
+    """Yield (features (n, S*S, d), bank-side maps (n, H, H) uint8 with 255 -> 0, sel) covering the
+    global bank rows [row0, row1): row r is patch r % S*S of training image r // S*S.  sel = int32
+    slab-local row picks when the slab is not taken whole (shard boundaries inside an image)."""
     import torch
 
-    S, ps, C, d = w["S"], w["ps"], w["C"], w["d"]
-    H = S * ps
-    first = 1 if w["ignore"] == 0 else 0
-    cells = 8
-    coarse = torch.randint(first, C, (n_img, cells, cells), generator=gen, device=device)
-    reps = (H + cells - 1) // cells
-    maps = coarse.repeat_interleave(reps, 1).repeat_interleave(reps, 2)[:, :H, :H]
-    ign = torch.rand((n_img, H, H), generator=gen, device=device) < 0.02
-    maps = torch.where(ign, torch.full_like(maps, w["ignore"]), maps).to(torch.uint8)
-    g0 = torch.Generator(device=device).manual_seed(0)
-    protos = torch.randn((C, d), generator=g0, device=device)
-    centre = maps[:, ps // 2::ps, ps // 2::ps].reshape(n_img, S * S).long().clamp_max(C - 1)
-    feats = protos[centre] + 0.8 * torch.randn((n_img, S * S, d), generator=gen, device=device)
-    feats = feats * (3.7 * torch.exp(0.25 * torch.randn((n_img, S * S, 1), generator=gen, device=device)))
-    return feats.contiguous(), maps.contiguous()
+    import bench_synth as syn
+
+    per_img = w["S"] ** 2
+    protos = syn.prototypes(w, device)
+    step_img = max(1, slab_rows // per_img)
+    img = row0 // per_img
+    while img * per_img < row1:
+        n_img = min(step_img, -(-row1 // per_img) - img)
+        feats, maps = syn.images(w, img, n_img, device, protos, stream=0)
+        maps = torch.where(maps == 255, torch.zeros_like(maps), maps)  # hbird_eval.py:310
+        lo, hi = max(row0, img * per_img), min(row1, (img + n_img) * per_img)
+        sel = None
+        if lo != img * per_img or hi != (img + n_img) * per_img:
+            sel = torch.arange(lo - img * per_img, hi - img * per_img, device=device, dtype=torch.int32)
+        yield feats, maps, sel, hi - lo
+        img += n_img
 
 
-def build_bank(w, rows, device, seed):
-    import torch
-
+def build_bank(w, row0, row1, device, keep_f32=True):
     from hbird_b200 import ops
 
-    S, ps = w["S"], w["ps"]
-    bank = ops.MemoryBank(w["d"], w["C"], ps * ps, rows, device.index, keep_f32=True)
-    gen = torch.Generator(device=device).manual_seed(seed)
-    per_img = S * S
-    slab = max(1, (1 << 19) // per_img)
-    left = rows
-    while left > 0:
-        n_img = min(slab, (left + per_img - 1) // per_img)
-        feats, maps = synth_images(w, n_img, gen, device)
-        maps = torch.where(maps == 255, torch.zeros_like(maps), maps)  # bank side: 255 -> 0
-        take = min(left, n_img * per_img)
-        sel = None if take == n_img * per_img else torch.arange(take, device=device, dtype=torch.int32)
-        bank.append(feats, maps, S, ps, sel)
-        left -= take
+    bank = ops.MemoryBank(w["d"], w["C"], w["ps"] ** 2, row1 - row0, device.index, keep_f32=keep_f32)
+    for feats, maps, sel, _ in bank_slabs(w, row0, row1, device):
+        bank.append(feats, maps, w["S"], w["ps"], sel)
     bank.finalize()
     return bank
 
 
-def make_query_ring(w, device, seed):
-    import torch
+def make_query_ring(w, device, first_batch=0, n=RING):
+    """Validation batches first_batch .. first_batch+n-1: (features (B*S*S, d), y (B, 1, H, H) = id/255)."""
+    import bench_synth as syn
 
-    gen = torch.Generator(device=device).manual_seed(seed)
+    protos = syn.prototypes(w, device)
     ring = []
-    for _ in range(RING):
-        feats, maps = synth_images(w, w["B"], gen, device)
+    for b in range(first_batch, first_batch + n):
+        feats, maps = syn.images(w, b * w["B"], w["B"], device, protos, stream=1)
         y = (maps.float() / 255.0).unsqueeze(1).contiguous()  # loader contract: id/255
         ring.append((feats.view(-1, w["d"]).contiguous(), y))
     return ring
@@ -160,31 +163,27 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------- the hot path
 def run_step(ops, bank, table, w, q, y, conf, shard=None):
-    """One pass: decode -> search -> label transfer -> upsample+argmax -> confusion."""
+    """One pass over one validation batch.  shard = None: the bank is whole on this GPU (4 launches).
+    shard given: row-sharded bank — per-shard search, exchange, merge with the label transfer fused
+    in, fused tail on this rank's image slice (5 launches; `table` is the replicated label table)."""
     B, S, H = w["B"], w["S"], w["S"] * w["ps"]
-    gt = ops.decode_mask(y, False)
-    if shard is not None and shard.get("xchg") is not None:
-        qn = shard["xchg"].search_scatter(bank, q, shard["qsplit"], K_NEIGH, K_PRIME, shard["offset"])
-    else:
-        scores, idx, qn = bank.search(q, K_NEIGH, K_PRIME, 0 if shard is None else shard["offset"])
-    if shard is not None:
-        from hbird_b200 import distributed as hdist
+    if shard is None:
+        bank.eval_step(q, y, S, conf, w["ignore"], K_NEIGH, K_PRIME, BETA)
+        return
+    from hbird_b200 import distributed as hdist
 
-        b0, b1 = hdist.split_range(B, shard["world"], shard["rank"])
-        n = S * S
-        if shard.get("xchg") is not None:  # fused exchange: K2b scatters over NVLink, merge waits
-            scores, idx = shard["xchg"].merge()
-        else:
-            gs, gi = hdist.all_gather_topk(scores, idx)
-            scores, idx = ops.merge_topk(gs, gi)
-            scores, idx = scores[b0 * n:b1 * n], idx[b0 * n:b1 * n]
-        lh = ops.label_transfer(table, w["ps"] ** 2, scores, idx, qn[b0 * n:b1 * n], BETA)
-        pred = ops.upsample_argmax(lh, b1 - b0, S, H, H)
-        ops.confusion_accumulate(conf, gt.view(B, H, H)[b0:b1], pred, w["ignore"])
+    b0, b1 = hdist.split_range(B, shard["world"], shard["rank"])
+    n = S * S
+    if shard.get("xchg") is not None:  # fused exchange: K2b scatters over NVLink, the merge waits
+        qn = shard["xchg"].search_scatter(bank, q, shard["qsplit"], K_NEIGH, K_PRIME, shard["offset"])
+        lh, _, _ = shard["xchg"].merge_transfer(table, w["ps"] ** 2, qn[b0 * n:b1 * n], BETA)
     else:
-        lh = ops.label_transfer(table, w["ps"] ** 2, scores, idx, qn, BETA)
-        pred = ops.upsample_argmax(lh, B, S, H, H)
-        ops.confusion_accumulate(conf, gt.view(B, H, H), pred, w["ignore"])
+        scores, idx, qn = bank.search(q, K_NEIGH, K_PRIME, shard["offset"])
+        gs, gi = hdist.all_gather_topk(scores, idx)
+        lh, _, _ = ops.merge_topk_transfer(gs[:, b0 * n:b1 * n].contiguous(), gi[:, b0 * n:b1 * n].contiguous(), table,
+                                           w["ps"] ** 2, qn[b0 * n:b1 * n].contiguous(), BETA)
+    if b1 > b0:
+        ops.predict_score(lh, b1 - b0, S, H, H, conf, y=y[b0:b1], ignore_index=w["ignore"])
 
 
 def timed_loop(torch, dist, world, fn, steps, warmup):
@@ -210,81 +209,301 @@ def timed_loop(torch, dist, world, fn, steps, warmup):
     return float(ms.item())
 
 
-def cpu_sample_images(w, seconds):
-    """How many images of the workload a ~`seconds` CPU sample holds, assuming ~0.4 TFLOP/s of host
-    GEMM + selection (one image at least, the ring's 8 batches at most)."""
-    per_img = 2.0 * w["S"] ** 2 * w["N"] * w["d"] * 1.6  # flop, with ~60 % on top for the top-k pass
-    return int(max(1, min(w["B"] * RING, seconds * 4e11 / per_img)))
+def measure_workload(torch, dist, ops, w, bank, table, ring, steps, warmup, world, peaks, shard=None, graph=False,
+                     sampler=None):
+    """Device-resident throughput of one workload + the search kernel's share and roofline fraction."""
+    Q = w["B"] * w["S"] ** 2
+    conf = torch.zeros((w["C"], w["C"]), dtype=torch.int64, device=ring[0][0].device)
+
+    def step(i):
+        q, y = ring[i % len(ring)]
+        run_step(ops, bank, table, w, q, y, conf, shard)
+
+    for i in range(warmup):
+        step(i)
+    torch.cuda.synchronize()
+    bank.enable_kernel_timing(True)
+    if sampler is not None:
+        sampler.start()  # clocks are sampled during the timed region only
+    ms = timed_loop(torch, dist, world, step, steps, 0) / steps
+    k2_ms, k2_n = bank.kernel_time_ms()
+    k2b_ms, _ = bank.rerank_time_ms()
+    bank.enable_kernel_timing(False)
+    rows = bank.rows
+    flop = 2.0 * rows * w["d"] * Q  # per GPU: this shard's rows x all queries
+    tf = flop / (k2_ms * 1e-3) / 1e12 if k2_ms > 0 else None
+    out = {"ms_per_step": ms, "search_kernel_ms": k2_ms, "rerank_kernel_ms": k2b_ms, "kernel_launches_timed": k2_n,
+           "search_tflops": tf, "frac": (tf / peaks["tf"]) if tf else None,
+           "kernel_share_of_step": (k2_ms / ms) if ms else None, "flop_per_launch": flop}
+    if graph and shard is None:
+        # the same 4 launches replayed from CUDA graphs (one per ring slot): what a serving loop that
+        # knows its batch shape does; matters where a step is ~1 ms (cfg1)
+        lh = torch.empty((Q, w["C"]), dtype=torch.float32, device=conf.device)
+        graphs = []
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for q, y in ring:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    bank.eval_step(q, y, w["S"], conf, w["ignore"], K_NEIGH, K_PRIME, BETA, label_hat=lh)
+                graphs.append(g)
+        torch.cuda.current_stream().wait_stream(side)
+        out["ms_per_step_cuda_graph"] = timed_loop(torch, dist, world, lambda i: graphs[i % len(graphs)].replay(), steps, warmup) / steps
+    return out, conf
 
 
-def cpu_reference_sample(w, bank, ring, n_img, repeats=1):
-    """The oracle port of the reference path on the host cores, on `n_img` images of the workload's
-    first validation batch against the FULL bank.  Returns (queries/s, seconds, threads)."""
-    import numpy as np
+# ----------------------------------------------------------------------------- CPU oracle legs
+def host_threads():
+    """All host cores for BLAS / OpenMP / torch, whatever the launcher exported (torchrun sets
+    OMP_NUM_THREADS=1).  Call before numpy / torch are imported."""
+    n = os.cpu_count() or 1
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+        os.environ[k] = str(n)
+    return n
 
-    from oracle import hbird_oracle as O
 
-    fm_t, lm_t = bank.export()
-    fm, lm = fm_t.cpu().numpy(), lm_t.cpu().numpy()
-    del fm_t, lm_t
-    S, d = w["S"], w["d"]
-    n_img = min(n_img, w["B"] * len(ring))
-    fl, yl, left = [], [], n_img
-    for q, y in ring:  # images are taken from as many of the ring's batches as needed
-        take = min(left, w["B"])
-        fl.append(q.view(w["B"], S * S, d)[:take].cpu().numpy())
-        yl.append(y[:take].cpu().numpy())
-        left -= take
-        if left == 0:
-            break
-    feats, yy = np.concatenate(fl), np.concatenate(yl)
-    # score blocks of at most ~4 GB of host RAM: (images per block) * S*S * N * 4 B
-    per_block = max(1, min(n_img, int(4e9 // (S * S * fm.shape[0] * 4))))
-    batches = [(feats[i:i + per_block], yy[i:i + per_block]) for i in range(0, n_img, per_block)]
-    threads = os.cpu_count() or 1
+def pin_host_threads(n):
+    import torch
+
+    torch.set_num_threads(n)
+    try:
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=n)
+    except Exception:
+        pass
+    used = n
     try:
         from threadpoolctl import threadpool_info
 
         blas = [t["num_threads"] for t in threadpool_info() if t.get("user_api") == "blas"]
-        threads = max(blas) if blas else threads
+        used = max(blas) if blas else n
     except Exception:
         pass
-    t0 = time.perf_counter()
-    for _ in range(repeats):
-        ref = O.evaluate(fm, lm, batches, w["C"], S, K_NEIGH, w["ignore"], BETA, return_details=True)
-    dt = (time.perf_counter() - t0) / repeats
-    return n_img * S * S / dt, dt, threads, ref
+    return used
 
 
-def parity_vs_oracle(ops, torch, w, bank, table, ring, n_img, ref):
-    """The same n_img images through the CUDA path, compared with what the oracle just computed:
-    the "mIoU delta" of the headline metric, measured on this workload's own bank."""
+def cpu_sample_queries(w, seconds, cap):
+    """How many queries a ~`seconds` CPU sample holds, assuming ~0.4 TFLOP/s of host GEMM with ~60 % on
+    top for the exact top-k pass (measured on this pool's hosts in round 1); at least 32."""
+    per_query = 2.0 * w["N"] * w["d"] * 1.6
+    return int(max(32, min(cap, seconds * 4e11 / per_query)))
+
+
+def cpu_sample(O, w, fm, lm, q, y_one, repeats=1):
+    """The oracle port of the reference path on the host cores: exact fp32 IP search + neighbour
+    gather + cross-attention for the n_q sampled queries against the FULL bank (the per-query
+    stages, where all the time goes), plus the pixel stages (upsample, argmax, bincount) of one
+    whole image.  Returns (seconds, (idx, dist, label_hat))."""
     import numpy as np
 
+    S, C, H = w["S"], w["C"], w["S"] * w["ps"]
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        idx, dist = O.search_exact_ip(q, fm, K_NEIGH)
+        lh = O.transfer_labels(q[None], fm, lm, idx, BETA)[0]
+        full = np.zeros((1, S * S, C), dtype=np.float32)
+        full[0, :min(len(lh), S * S)] = lh[:S * S]
+        pred = O.predict_map(full, S, H, H)
+        O.confusion_matrix(O.decode_mask(y_one, False).reshape(-1), pred.reshape(-1), C, C, w["ignore"])
+    return (time.perf_counter() - t0) / repeats, (idx, dist, lh)
+
+
+def sample_queries(w, ring_host, n_q):
+    """n_q queries spread evenly over the first validation batch (numpy) + the mask of its first image."""
+    import numpy as np
+
+    q_all, y_all = ring_host
+    pick = np.linspace(0, q_all.shape[0] - 1, num=min(n_q, q_all.shape[0])).astype(np.int64)
+    return pick, np.ascontiguousarray(q_all[pick]), y_all[:1]
+
+
+def parity_block(torch, dist, ops, O, w, bank, table, ring, world, rank, offset, n_q, n_img, cpu_time=False):
+    """The timed inputs through the CUDA path against the oracle.
+    (1) n_q queries sampled from the first validation batch: the CPU oracle's exact search runs on
+        every rank's host against that rank's rows of the bank (exported from HBM) and the per-shard
+        lists are merged with the oracle's IndexShards restatement (search_faiss.py:53-63) ->
+        recall@30 and score error of the CUDA result.
+    (2) n_img whole images: mIoU, confusion matrix and pixel agreement against the oracle's label
+        transfer / upsample / argmax / bincount (numpy).  The oracle's exact search would take ~35 s
+        per 518-px image on the host, so for these images the exact fp32 neighbours are computed with
+        torch.matmul (TF32 off) on the GPUs — and that stand-in is itself checked against the CPU
+        oracle on the queries of (1).
+    Returns (dict or None on ranks > 0, seconds of CPU oracle time of (1) on this rank)."""
+    import numpy as np
+
+    from hbird_b200 import distributed as hdist
     from hbird_b200.utils.eval_metrics import miou_from_confusion
 
-    ref_miou, ref_conf, det = ref
-    S, d, H, C = w["S"], w["d"], w["S"] * w["ps"], w["C"]
-    n_img = min(n_img, w["B"] * len(ring))
-    qs = torch.cat([q for q, _ in ring])[:n_img * S * S].contiguous()
-    ys = torch.cat([y for _, y in ring])[:n_img].contiguous()
-    scores, idx, qn = bank.search(qs, K_NEIGH, K_PRIME)
-    lh = ops.label_transfer(table, w["ps"] ** 2, scores, idx, qn, BETA)
-    pred = ops.upsample_argmax(lh, n_img, S, H, H)
-    conf = torch.zeros((C, C), dtype=torch.int64, device=qs.device)
-    ops.confusion_accumulate(conf, ops.decode_mask(ys, False).view(n_img, H, H), pred, w["ignore"])
-    miou = miou_from_confusion(conf.cpu().numpy())[0]
-    ref_idx = np.concatenate(det["idx"])
-    ref_dist = np.concatenate(det["dist"])
-    got_idx, got_s = idx.cpu().numpy(), scores.cpu().numpy()
-    recall = float((got_idx[:, :, None] == ref_idx[:, None, :]).any(axis=2).mean())
-    rel = float((np.abs(got_s - ref_dist) / np.maximum(np.abs(ref_dist), 1e-6)).max())
-    ref_pred = np.concatenate(det["pred"])[:, 0]
-    agree = float((pred.cpu().numpy() == ref_pred).mean())
-    return {"images": n_img, "queries": n_img * S * S, "miou_b200": miou, "miou_oracle": ref_miou,
-            "miou_delta_points": abs(miou - ref_miou) * 100.0, "recall_at_30": recall, "score_max_rel_err": rel,
-            "pred_pixel_agreement": agree, "confusion_abs_diff": int(np.abs(conf.cpu().numpy() - ref_conf).sum()),
-            "gates": "recall>=0.999, rel<=1e-3, |dmIoU|<=0.05 points"}
+    dev = ring[0][0].device
+    S, d, C, H, k = w["S"], w["d"], w["C"], w["S"] * w["ps"], K_NEIGH
+    per = S * S
+    q0, y0 = ring[0]
+    q_host, y_host = q0.cpu().numpy(), y0.cpu().numpy()
+    pick, qs, y_one = sample_queries(w, (q_host, y_host), n_q)
+    # this rank's bank rows on the host, in slabs
+    rows = bank.rows
+    fm = np.empty((rows, d), dtype=np.float32)
+    for a in range(0, rows, 1 << 20):
+        m = min(1 << 20, rows - a)
+        fm[a:a + m] = bank.export(a, m, labels=False)[0].cpu().numpy()
+    t0 = time.perf_counter()
+    li, ld = O.search_exact_ip(qs, fm, min(k, rows))
+    cpu_s = time.perf_counter() - t0
+    li = li + offset
+
+    def exact_gpu(q_dev):
+        """exact fp32 top-k of q_dev against this rank's rows (torch.matmul, TF32 off), global ids"""
+        bs, bi = None, None
+        for a in range(0, rows, 1 << 18):
+            m = min(1 << 18, rows - a)
+            f = bank.export(a, m, labels=False)[0]
+            sc = q_dev @ f.T
+            v, i = sc.topk(min(k, m), dim=1)
+            i = i + (a + offset)
+            bs, bi = (v, i) if bs is None else (torch.cat([bs, v], 1), torch.cat([bi, i], 1))
+            if bs.shape[1] > k:
+                v, j = bs.topk(k, dim=1)
+                bs, bi = v, bi.gather(1, j)
+        order = torch.argsort(bs, dim=1, descending=True, stable=True)
+        return bs.gather(1, order), bi.gather(1, order)
+
+    n_img = min(n_img, w["B"])
+    qi_dev = q0[:n_img * per].contiguous()
+    gs, gi = exact_gpu(torch.cat([q0[torch.from_numpy(pick).to(dev)], qi_dev]))
+    if world > 1:
+        kk = gs.shape[1]
+        pad = k - kk
+        if pad:
+            gs = torch.cat([gs, torch.full((gs.shape[0], pad), float("-inf"), device=dev)], 1)
+            gi = torch.cat([gi, torch.full((gi.shape[0], pad), -1, device=dev, dtype=torch.int64)], 1)
+            li = np.concatenate([li, np.full((li.shape[0], pad), -1, np.int64)], 1)
+            ld = np.concatenate([ld, np.full((ld.shape[0], pad), -np.inf, np.float32)], 1)
+        ags, agi = hdist.all_gather_topk(gs, gi)
+        als, ali = hdist.all_gather_topk(torch.from_numpy(ld).to(dev), torch.from_numpy(li).to(dev))
+        mi, md = O.merge_shards(agi.cpu().numpy(), ags.cpu().numpy(), k)
+        oi, od = O.merge_shards(ali.cpu().numpy(), als.cpu().numpy(), k)
+    else:
+        mi, md = gi.cpu().numpy(), gs.cpu().numpy()
+        oi, od = li, ld
+    # the product path on the same queries
+    conf = torch.zeros((C, C), dtype=torch.int64, device=dev)
+    if world == 1:
+        lh, qn, s_all, i_all = bank.search_transfer(q0, k, K_PRIME, 0, BETA, None, True)
+        got_s, got_i = s_all[torch.from_numpy(pick).to(dev)].cpu().numpy(), i_all[torch.from_numpy(pick).to(dev)].cpu().numpy()
+        pred = ops.predict_score(lh[:n_img * per].contiguous(), n_img, S, H, H, conf, y=y0[:n_img], ignore_index=w["ignore"],
+                                 return_pred=True)
+        lh_img = lh[:n_img * per]
+    else:
+        # row-sharded: per-shard K2/K2b, NCCL all-gather, merge with the label transfer fused in (the
+        # fused NVLink exchange is bit-identical to this path: tests/test_gpu_fused.py, tools/dist_check.py)
+        s, i, qn = bank.search(q0, k, K_PRIME, offset)
+        ags2, agi2 = hdist.all_gather_topk(s, i)
+        lh, s_all, i_all = ops.merge_topk_transfer(ags2, agi2, table, w["ps"] ** 2, qn, BETA, True)
+        got_s, got_i = s_all[torch.from_numpy(pick).to(dev)].cpu().numpy(), i_all[torch.from_numpy(pick).to(dev)].cpu().numpy()
+        pred = ops.predict_score(lh[:n_img * per].contiguous(), n_img, S, H, H, conf, y=y0[:n_img], ignore_index=w["ignore"],
+                                 return_pred=True)
+        lh_img = lh[:n_img * per]
+    # neighbour rows for the oracle's cross-attention (it re-normalises the gathered keys, :594-609)
+    nb = torch.from_numpy(mi[len(pick):]).to(dev).reshape(-1)
+    local = nb - offset
+    mine = (local >= 0) & (local < rows)
+    kf = torch.zeros((nb.numel(), d), dtype=torch.float32, device=dev)
+    sel = local[mine]
+    for a in range(0, rows, 1 << 20):
+        m = min(1 << 20, rows - a)
+        inside = (sel >= a) & (sel < a + m)
+        if bool(inside.any()):
+            f = bank.export(a, m, labels=False)[0]
+            where = mine.nonzero().squeeze(1)[inside]
+            kf[where] = f[sel[inside] - a]
+    if world > 1:
+        dist.all_reduce(kf)
+    if rank != 0:
+        return None, cpu_s
+    tbl = torch.as_tensor(table)
+    kl = (tbl[nb.clamp_min(0)].to(torch.float32) / float(w["ps"] ** 2)).cpu().numpy()
+    ref_lh = O.cross_attention(qi_dev.cpu().numpy()[None], kf.cpu().numpy().reshape(1, -1, k, d), kl.reshape(1, -1, k, C), BETA)[0]
+    ref_pred = O.predict_map(ref_lh.reshape(n_img, per, C), S, H, H)[:, 0]
+    gt = O.decode_mask(y_host[:n_img], False).reshape(n_img, H, H)
+    ref_conf = O.confusion_matrix(gt.reshape(-1), ref_pred.reshape(-1), C, C, w["ignore"])
+    ref_miou = O.miou_from_confusion(ref_conf)[0]
+    got_conf = conf.cpu().numpy()
+    miou = miou_from_confusion(got_conf)[0]
+    got_pred = pred.cpu().numpy()
+    same = got_pred == ref_pred
+    # confusion matrix restricted to the pixels whose predicted label matches: must be bit-exact
+    conf_same_ref = O.confusion_matrix(gt[same], ref_pred[same], C, C, w["ignore"])
+    conf_same_got = O.confusion_matrix(gt[same], got_pred[same], C, C, w["ignore"])
+
+    def rec(a, b):
+        return float((a[:, :, None] == b[:, None, :]).any(axis=2).mean())
+
+    out = {
+        "queries_vs_cpu_oracle": int(len(pick)), "recall_at_30": rec(got_i, oi),
+        "score_max_rel_err": float((np.abs(got_s - od) / np.maximum(np.abs(od), 1e-6)).max()),
+        "gpu_exact_standin_vs_cpu_oracle_recall": rec(mi[:len(pick)], oi),
+        "gpu_exact_standin_score_max_rel_err": float((np.abs(md[:len(pick)] - od) / np.maximum(np.abs(od), 1e-6)).max()),
+        "images": int(n_img), "miou_b200": miou, "miou_oracle": ref_miou, "miou_delta_points": abs(miou - ref_miou) * 100.0,
+        "label_hat_max_abs_err": float(np.abs(lh_img.cpu().numpy() - ref_lh).max()),
+        "pred_pixel_agreement": float(same.mean()), "confusion_abs_diff": int(np.abs(got_conf - ref_conf).sum()),
+        "confusion_bit_exact_where_labels_match": bool(np.array_equal(conf_same_ref, conf_same_got)),
+        "recall_at_30_whole_images": rec(i_all[:n_img * per].cpu().numpy(), mi[len(pick):]),
+        "oracle": "numpy port of the reference path; whole-image neighbours by fp32 torch.matmul (TF32 off), checked "
+                  "against the CPU oracle on the sampled queries",
+        "gates": "recall>=0.999, rel<=1e-3, |dmIoU|<=0.05 points, confusion bit-exact where labels match",
+    }
+    out["ok"] = bool(out["recall_at_30"] >= 0.999 and out["score_max_rel_err"] <= 1e-3 and out["miou_delta_points"] <= 0.05
+                     and out["confusion_bit_exact_where_labels_match"])
+    return out, cpu_s
+
+
+# ----------------------------------------------------------------------------- HBM-bound kernels
+def hbm_kernels(torch, ops, w, bank, table, ring, peaks, rerank_ms):
+    """K1 pack, K2b+K4a (from the timed steps), fused tail: algorithmic GB/s vs the measured HBM copy
+    bandwidth.  Timed alone with an L2 flush (256 MB memset) between iterations."""
+    dev = ring[0][0].device
+    S, ps, C, d, B = w["S"], w["ps"], w["C"], w["d"], w["B"]
+    H, Q = S * ps, B * S * S
+    dpad = (d + 63) // 64 * 64
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timeit(fn, iters=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tot = 0.0
+        for _ in range(iters):
+            flush.zero_()
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot / iters
+
+    out = {}
+    feats, maps, _, n_rows = next(bank_slabs(w, 0, 1 << 19, dev))
+    tmp = ops.MemoryBank(d, C, ps * ps, n_rows * 14, dev.index, keep_f32=True)
+    ms = timeit(lambda: tmp.append(feats, maps, S, ps))
+    by = n_rows * (4 * d + ps * ps + 2 * dpad + 4 * d + 2 * C)
+    out["K1_pack"] = {"ms": ms, "rows": n_rows, "bytes": by, "gbs": by / ms / 1e6, "frac": by / ms / 1e6 / peaks["hbm"]}
+    tmp.close()
+    by = Q * (K_PRIME * 4 * d + K_NEIGH * 2 * C + 4 * C)
+    if rerank_ms:
+        out["K2b_rerank_plus_K4a_label_transfer"] = {"ms": rerank_ms, "queries": Q, "bytes": by, "gbs": by / rerank_ms / 1e6,
+                                                     "frac": by / rerank_ms / 1e6 / peaks["hbm"], "timed": "inside the timed steps"}
+    q, y = ring[0]
+    lh, _, _, _ = bank.search_transfer(q, K_NEIGH, K_PRIME, 0, BETA, table)
+    conf = torch.zeros((C, C), dtype=torch.int64, device=dev)
+    ms = timeit(lambda: ops.predict_score(lh, B, S, H, H, conf, y=y, ignore_index=w["ignore"]))
+    by = B * (4 * S * S * C + 4 * H * H)
+    out["tail_decode_upsample_argmax_confusion"] = {
+        "ms": ms, "pixels": B * H * H, "bytes": by, "gbs": by / ms / 1e6, "frac": by / ms / 1e6 / peaks["hbm"],
+        "note": "instruction-bound (6 instructions per class per pixel in torch's rounding order), not HBM-bound"}
+    return out
 
 
 def _claim_stdout():
@@ -296,6 +515,63 @@ def _claim_stdout():
     return real
 
 
+# ----------------------------------------------------------------------------- reference arm
+def reference_arm(args, w, real_stdout):
+    """The CPU oracle port of the reference path on the host cores, on a bounded sample of the
+    workload.  The bank is the same synthetic bank as the B200 arm's (bench_synth is a pure function
+    of the row number), generated and normalised on the host; no product library is loaded."""
+    n_threads = host_threads()
+    import numpy as np
+    import torch
+
+    import bench_synth as syn
+    from oracle import hbird_oracle as O
+
+    threads = pin_host_threads(n_threads)
+    cpu = torch.device("cpu")
+    N, d, C = w["N"], w["d"], w["C"]
+    fm = np.empty((N, d), dtype=np.float32)
+    lm = np.empty((N, C), dtype=np.float32)
+    r = 0
+    for feats, maps, sel, n in bank_slabs(w, 0, N, cpu, slab_rows=1 << 18):
+        f = feats.view(-1, d)
+        l = syn.soft_labels(w, maps)  # == oracle.build_memory's one_hot().mean() (tests/test_bench_contract.py)
+        if sel is not None:
+            f, l = f[sel.long()], l[sel.long()]
+        fm[r:r + n] = O.normalise_rows(f.numpy())
+        lm[r:r + n] = l.numpy()
+        r += n
+    ring = make_query_ring(w, cpu, 0, 1)
+    q_host, y_host = ring[0][0].numpy(), ring[0][1].numpy()
+    n_q = cpu_sample_queries(w, seconds=4.0, cap=q_host.shape[0])  # ~4 s of host work per step
+    _, qs, y_one = sample_queries(w, (q_host, y_host), n_q)
+    times = []
+    for i in range(args.warmup + args.steps):
+        dt, _ = cpu_sample(O, w, fm, lm, qs, y_one)
+        if i >= args.warmup:
+            times.append(dt)
+    tot = sum(times)
+    value = len(qs) * len(times) / tot
+    sample = (f"{len(qs)} patch-queries per step (spread over the first validation batch) against the full {N:,}-row bank: "
+              f"exact fp32 IP search + gather + cross-attention, plus the pixel stages of one image")
+    line = {
+        "impl": "reference", "metric": "patch_queries_per_sec", "value": value, "unit": "patch-queries/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / max(1, len(times)),
+        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {w['desc']}", "bank_rows": N, "d": d, "k": K_NEIGH, "classes": C,
+                   "path": "oracle port of the reference CPU path (exact fp32 IP search + gather + cross-attention + "
+                           "bilinear upsample + argmax + bincount), numpy/BLAS",
+                   "parallelism": f"host CPU, {threads} threads"},
+        "cpu_baseline": {"value": value, "unit": "patch-queries/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "patch-queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), file=real_stdout, flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------- main
 def main():
     real_stdout = _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -303,137 +579,109 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-sharded", action="store_true")
-    ap.add_argument("--cta-group", type=int, default=0)
+    ap.add_argument("--no-extras", action="store_true", help="headline workload only (no by_workload block)")
+    ap.add_argument("--extras", default="", help="comma list of by_workload entries to run (default: all)")
     args = ap.parse_args()
-
-    import torch
-    import torch.distributed as dist
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     w = dict(WORKLOADS[args.workload])
-    warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-    Q = w["B"] * w["S"] * w["S"]
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        return reference_arm(args, w, real_stdout)
 
-    if args.impl == "reference" and rank != 0:
-        return 0
+    n_threads = host_threads()  # the CPU oracle legs use every host core, also under torchrun
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    warmup = max(args.warmup, 3)
+    Q = w["B"] * w["S"] ** 2
     if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a B200: the hot path has no CPU fallback (the reference arm also "
-                           "builds its synthetic bank with the CUDA pack kernel)")
+        raise RuntimeError("bench.py needs a B200: the hot path has no CPU fallback")
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
-    from hbird_b200 import ops
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from hbird_b200 import HbirdEvaluation, ops
+    from hbird_b200 import distributed as hdist
+    from hbird_b200.models import FeatureExtractorSimple
+    from oracle import hbird_oracle as O  # the checker: parity block and cpu_baseline leg only
 
+    threads = pin_host_threads(n_threads)
     ops.device_check(device.index)
-
-    # ------------------------------------------------------------------ reference arm (CPU)
-    if args.impl == "reference":
-        bank = build_bank(w, w["N"], device, seed=1)
-        ring = make_query_ring(w, device, seed=2)
-        n_img = cpu_sample_images(w, seconds=1.5)  # per step
-        qps_list = []
-        for i in range(args.warmup + args.steps):
-            qps, dt, threads, _ = cpu_reference_sample(w, bank, ring, n_img)
-            if i >= args.warmup:
-                qps_list.append((qps, dt))
-        tot_q = n_img * w["S"] ** 2 * len(qps_list)
-        tot_t = sum(dt for _, dt in qps_list)
-        value = tot_q / tot_t
-        sample = f"{n_img} image(s) = {n_img * w['S'] ** 2} patch-queries per step against the full {w['N']:,}-row bank"
-        line = {
-            "impl": "reference", "metric": "patch_queries_per_sec", "value": value, "unit": "patch-queries/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, len(qps_list)),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {w['desc']}", "k": K_NEIGH, "path": "oracle port of the reference "
-                       "CPU path (exact fp32 IP search + gather + cross-attention + bilinear upsample + argmax + bincount)"},
-            "cpu_baseline": {"value": value, "unit": "patch-queries/s", "cores": threads, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": "patch-queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0,
-        }
-        print(json.dumps(line), file=real_stdout, flush=True)
-        return 0
-
-    # ------------------------------------------------------------------ B200 arm
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-    peak_tf, peak_src = load_peaks()
-    bank = build_bank(w, w["N"], device, seed=1)  # replica: the full bank on every GPU
-    if args.cta_group:
-        bank.configure_search(cta_group=args.cta_group)
-    table = bank.label_table()
-    ring = make_query_ring(w, device, seed=2 + rank)
-    conf = torch.zeros((w["C"], w["C"]), dtype=torch.int64, device=device)
-    torch.cuda.synchronize()
+    peaks = load_peaks()
+    extras = [e for e in args.extras.split(",") if e]
 
-    def step(i):
-        q, y = ring[i % RING]
-        run_step(ops, bank, table, w, q, y, conf)
+    def want(name):
+        return not args.no_extras and (not extras or name in extras)
+
+    # ------------------------------------------------------------------ headline workload
+    a, b = hdist.shard_bounds(w["N"], world, rank)
+    bank = build_bank(w, a, b, device)
+    ring = make_query_ring(w, device)  # every rank sees every validation batch
+    shard = None
+    table = bank.label_table()
+    xchg = None
+    collective = None
+    if world > 1:
+        counts = hdist.gather_counts(bank.rows, device)
+        table = hdist.all_gather_rows(bank.label_table(), counts)
+        shard = {"offset": hdist.offsets_from_counts(counts)[rank], "world": world, "rank": rank}
+        per_rank = -(-w["B"] // world) * w["S"] ** 2
+        xchg = hdist.connect_shard_exchange(per_rank, K_NEIGH, device)
+        collective = "NCCL all-gather of (score f32, idx i64)[Q,k] + k-way merge kernel with the label transfer fused in"
+        if xchg is not None:
+            shard["xchg"], shard["qsplit"] = xchg, hdist.query_split(w["B"], w["S"] ** 2, world)
+            collective = ("fused exchange: K2b stores each query's shard top-k into the owner rank's window over NVLink "
+                          "(CUDA IPC peer memory), the merge + label-transfer kernel waits on per-rank step flags; no NCCL call")
+    torch.cuda.synchronize()
 
     sampler = ClockSampler(device.index)
-    bank.enable_kernel_timing(True)
-    for i in range(warmup):  # warm-up outside the clock-sampling window
-        step(i)
-    torch.cuda.synchronize()
-    bank.enable_kernel_timing(True)  # reset the event ring: only timed steps are averaged
-    sampler.start()
-    ms_total = timed_loop(torch, dist, world, step, args.steps, 0)
+    head, conf = measure_workload(torch, dist, ops, w, bank, table, ring, args.steps, warmup, world, peaks, shard,
+                                  sampler=sampler)
     clocks = sampler.stop()
-    kern_ms, kern_n = bank.kernel_time_ms()
-    bank.enable_kernel_timing(False)
-    launches_per_step = bank.last_search_launches() + 4  # decode, label transfer, upsample+argmax, confusion
-    ms_per_step = ms_total / args.steps
-    value = world * Q / (ms_per_step * 1e-3)
+    ms_per_step = head["ms_per_step"]
+    value = Q / (ms_per_step * 1e-3)  # world == 1: this GPU; world > 1: all ranks work on the same Q queries
+    launches_per_step = 4 if world == 1 else 5
 
-    # ---- e2e: host buffers in, host result out, copies inside the timed region.  Every step copies its
-    # own inputs from pinned host memory and reads its result back; the copy of step i+1 is issued on a
-    # second stream while step i computes (double-buffered device inputs), as a serving loop would.
-    host_ring = [(q.cpu().pin_memory(), y.cpu().pin_memory()) for q, y in ring]
-    dev_in = [(torch.empty_like(ring[0][0]), torch.empty_like(ring[0][1])) for _ in range(2)]
-    copied = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
-    copy_stream = torch.cuda.Stream(device)
-    conf_host = torch.zeros((w["C"], w["C"]), dtype=torch.int64).pin_memory()
-    issued = {"next": None}
+    nccl_ms = None
+    if world > 1 and xchg is not None:
+        plain = dict(shard)
+        plain.pop("xchg")
+        m2, conf_nccl = measure_workload(torch, dist, ops, w, bank, table, ring, max(3, args.steps // 4), warmup, world, peaks, plain)
+        nccl_ms = m2["ms_per_step"]
 
-    def issue_copy(i):
-        b = i % 2
-        qh, yh = host_ring[i % RING]
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[b])
-            dev_in[b][0].copy_(qh, non_blocking=True)
-            dev_in[b][1].copy_(yh, non_blocking=True)
-            copied[b].record(copy_stream)
+    # ------------------------------------------------------------------ e2e: the engine's public call, host inputs
+    fe = FeatureExtractorSimple(torch.nn.Identity(), lambda m, x: (x, None), w["S"], w["d"])
+    nn_params = {"k_prime": K_PRIME, "idx_shard": world > 1}
+    ev = HbirdEvaluation.from_bank(fe, bank, w["C"], K_NEIGH, device, nn_params,
+                                   shard_counts=(counts if world > 1 else None))
+    if world > 1 and xchg is not None:
+        ev._xchg = xchg  # reuse the connected windows
+    host_ring = [(q.view(w["B"], w["S"] ** 2, w["d"]).cpu().pin_memory(), y.cpu().pin_memory()) for q, y in ring]
+    last = {}
 
     def step_e2e(i):
-        if issued["next"] != i:  # first step of a loop: nothing was prefetched
-            issue_copy(i)
-        issue_copy(i + 1)
-        issued["next"] = i + 1
-        b = i % 2
-        cur = torch.cuda.current_stream()
-        cur.wait_event(copied[b])
-        run_step(ops, bank, table, w, dev_in[b][0], dev_in[b][1], conf)
-        consumed[b].record(cur)
-        conf_host.copy_(conf, non_blocking=True)
-        cur.synchronize()  # the caller reads the step's result
+        last["miou"] = ev.evaluate([host_ring[i % RING]], w["S"], ignore_index=w["ignore"])
 
-    for b in range(2):
-        consumed[b].record(torch.cuda.current_stream())
     ms_e2e = timed_loop(torch, dist, world, step_e2e, args.steps, warmup) / args.steps
     h2d = host_ring[0][0].numel() * 4 + host_ring[0][1].numel() * 4
-    d2h = conf_host.numel() * 8
-    e2e_value = world * Q / (ms_e2e * 1e-3)
+    if world > 1:
+        h2d = h2d // world  # each rank copies its image slice only; the queries then travel over NVLink
+    d2h = w["C"] * w["C"] * 8
+    e2e_value = Q / (ms_e2e * 1e-3)
+    ev._xchg = None
 
-    # ---- the reference's literal plugin call (search_faiss.py:83-90): pageable host queries in,
-    # host (indices, distances) out, every copy synchronous -- what a third party using the ABC gets
+    # ---- the reference's literal plugin call (search_faiss.py:83-90): host queries in, host (indices,
+    # distances) out -- what third-party code using the ABC gets
     plugin = None
     if world == 1:
-        import time
-
         from hbird_b200 import NearestNeighborSearchB200
 
         nn = NearestNeighborSearchB200(None, n_neighbors=K_NEIGH, bank=bank, k_prime=K_PRIME, gpu_ids=[device.index])
@@ -449,96 +697,155 @@ def main():
                   "call": "NearestNeighborSearchB200.find_nearest_neighbors(q_cpu) -> (indices, distances) ndarrays",
                   "h2d_bytes_per_call": Q * w["d"] * 4, "d2h_bytes_per_call": int(idx_np.nbytes + dist_np.nbytes)}
 
-    # ---- row-sharded bank: per-shard search -> NCCL all-gather -> merge kernel (strong scaling)
-    sharded = None
-    if world > 1 and not args.no_sharded:
-        from hbird_b200 import distributed as hdist
+    # ------------------------------------------------------------------ parity vs the oracle (+ CPU baseline at N = 1)
+    par_q = 256 if w["N"] > 2_000_000 else 1024
+    parity, _ = parity_block(torch, dist, ops, O, w, bank, table, ring, world, rank, 0 if shard is None else shard["offset"],
+                             n_q=par_q, n_img=2)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        rows = bank.rows
+        fm = np.empty((rows, w["d"]), dtype=np.float32)
+        lm = np.empty((rows, w["C"]), dtype=np.float32)
+        for r0 in range(0, rows, 1 << 20):
+            m = min(1 << 20, rows - r0)
+            f, l = bank.export(r0, m)
+            fm[r0:r0 + m], lm[r0:r0 + m] = f.cpu().numpy(), l.cpu().numpy()
+        q_host_np, y_host_np = ring[0][0].cpu().numpy(), ring[0][1].cpu().numpy()
+        n_q = cpu_sample_queries(w, seconds=15.0, cap=Q)
+        _, qs, y_one = sample_queries(w, (q_host_np, y_host_np), n_q)
+        dt, _ = cpu_sample(O, w, fm, lm, qs, y_one)
+        cpu = {"value": len(qs) / dt, "unit": "patch-queries/s", "cores": threads, "kind": "port",
+               "sample": f"{len(qs)} patch-queries (spread over the first validation batch) against the full {rows:,}-row bank: "
+                         f"exact fp32 IP search + gather + cross-attention, plus the pixel stages of one image; "
+                         f"{dt:.1f} s of oracle (numpy/BLAS) time"}
+        del fm, lm
 
-        a, b = hdist.shard_bounds(w["N"], world, rank)
-        shard_bank = build_bank(w, b - a, device, seed=100 + rank)
-        counts = hdist.gather_counts(shard_bank.rows, device)
-        full_table = hdist.all_gather_rows(shard_bank.label_table(), counts)
-        info = {"offset": hdist.offsets_from_counts(counts)[rank], "world": world, "rank": rank}
-        shared_ring = make_query_ring(w, device, seed=2)  # every rank sees every query batch
-        conf2 = torch.zeros_like(conf)
+    hbm = hbm_kernels(torch, ops, w, bank, table, ring, peaks, head["rerank_kernel_ms"]) if rank == 0 else None
+    if world > 1:
+        dist.barrier()
 
-        def step_sh(i):
-            q, y = shared_ring[i % RING]
-            run_step(ops, shard_bank, full_table, w, q, y, conf2, shard=info)
+    # ------------------------------------------------------------------ the other configurations, same line
+    by_workload = {}
+    if xchg is not None:
+        torch.cuda.synchronize()
+        dist.barrier()
+        hdist.close_shard_exchange(xchg)
+        xchg = None
+    ev.bank = None  # the evaluator does not own the bench's bank
+    bank.close()
+    del bank, table, ring, host_ring
+    torch.cuda.empty_cache()
+    few = max(5, args.steps // 2)
 
-        ms_nccl = timed_loop(torch, dist, world, step_sh, args.steps, warmup) / args.steps
-        conf_nccl = conf2.clone()
-        # fused exchange over NVLink peer memory (K2b peer stores + waiting merge kernel)
-        per_rank = -(-w["B"] // world) * w["S"] ** 2
-        xchg = hdist.connect_shard_exchange(per_rank, K_NEIGH, device)
-        ms_sh, collective = ms_nccl, "NCCL all-gather of (score f32, idx i64)[Q,k] + k-way merge kernel"
-        exchange_parity = None
-        if xchg is not None:
-            info["xchg"], info["qsplit"] = xchg, hdist.query_split(w["B"], w["S"] ** 2, world)
-            conf2.zero_()
-            ms_sh = timed_loop(torch, dist, world, step_sh, args.steps, warmup) / args.steps
-            collective = ("fused: K2b stores each query's shard top-k into the owner rank's window over "
-                          "NVLink (CUDA IPC), merge kernel waits on per-rank step flags; no NCCL call")
-            exchange_parity = bool(torch.equal(conf2, conf_nccl))  # same steps, same batches
-        sharded = {"value": Q / (ms_sh * 1e-3), "unit": "patch-queries/s", "ms_per_step": ms_sh,
-                   "bank_rows_total": w["N"], "bank_rows_per_gpu": b - a, "scaling": "strong",
-                   "collective": collective, "nccl_path_ms_per_step": ms_nccl,
-                   "confusion_equals_nccl_path": exchange_parity}
-        if xchg is not None:
+    def side_workload(name, ww, sharded, keep_f32=True, graph=False, search_only=False):
+        """value / kernel fraction of another configuration (single GPU, or row-sharded over the ranks)"""
+        a2, b2 = hdist.shard_bounds(ww["N"], world, rank) if sharded else (0, ww["N"])
+        bk = build_bank(ww, a2, b2, device, keep_f32)
+        rg = make_query_ring(ww, device, 0, 4)
+        tb, sh, xc = bk.label_table(), None, None
+        if sharded and world > 1:
+            cts = hdist.gather_counts(bk.rows, device)
+            tb = hdist.all_gather_rows(bk.label_table(), cts)
+            sh = {"offset": hdist.offsets_from_counts(cts)[rank], "world": world, "rank": rank}
+            xc = hdist.connect_shard_exchange(-(-ww["B"] // world) * ww["S"] ** 2, K_NEIGH, device)
+            if xc is not None:
+                sh["xchg"], sh["qsplit"] = xc, hdist.query_split(ww["B"], ww["S"] ** 2, world)
+        m, _ = measure_workload(torch, dist, ops, ww, bk, tb, rg, few, 3, world, peaks, sh, graph=graph)
+        q_step = ww["B"] * ww["S"] ** 2
+        per_step = q_step * (1 if sharded or world == 1 else world)  # replicas: every rank its own batch
+        res = {"workload": ww["desc"], "bank_rows": ww["N"], "bank_rows_per_gpu": bk.rows, "d": ww["d"],
+               "layout": ("row-sharded, fused exchange" if (sharded and world > 1 and xc is not None) else
+                          "row-sharded, NCCL all-gather + merge" if (sharded and world > 1) else
+                          "single GPU" if world == 1 else "replicas (full bank per GPU, batches split)"),
+               "value": per_step / (m["ms_per_step"] * 1e-3), "unit": "patch-queries/s", "ms_per_step": m["ms_per_step"],
+               "search_kernel_ms": m["search_kernel_ms"], "search_kernel_frac_of_sustained_bf16": m["frac"],
+               "search_kernel_tflops": m["search_tflops"], "scaling": "strong" if sharded and world > 1 else "weak"}
+        if "ms_per_step_cuda_graph" in m:
+            res["ms_per_step_cuda_graph"] = m["ms_per_step_cuda_graph"]
+            res["value_cuda_graph"] = per_step / (m["ms_per_step_cuda_graph"] * 1e-3)
+        if xc is not None:
             torch.cuda.synchronize()
             dist.barrier()
-            hdist.close_shard_exchange(xchg)
-        shard_bank.close()
+            hdist.close_shard_exchange(xc)
+        bk.close()
+        torch.cuda.empty_cache()
+        by_workload[name] = res
 
-    # ---- CPU baseline beside it (rank 0, N = 1 only)
-    cpu = None
-    parity = None
-    if world == 1 and not args.no_cpu_baseline:
-        n_img = cpu_sample_images(w, seconds=15.0)
-        qps, dt, threads, ref = cpu_reference_sample(w, bank, ring, n_img)
-        parity = parity_vs_oracle(ops, torch, w, bank, table, ring, n_img, ref)
-        cpu = {"value": qps, "unit": "patch-queries/s", "cores": threads, "kind": "port",
-               "sample": f"{n_img} images = {n_img * w['S'] ** 2} patch-queries against the full {w['N']:,}-row bank, "
-                         f"{dt:.1f} s of oracle (numpy/BLAS) time"}
+    if world == 1:
+        if want("cfg1"):
+            side_workload("cfg1", dict(WORKLOADS["cfg1"]), False, graph=True)
+        if want("cfg2") and args.workload != "cfg2":
+            side_workload("cfg2", dict(WORKLOADS["cfg2"]), False, graph=True)
+        if want("cfg4") and args.workload != "cfg4":
+            side_workload("cfg4", dict(WORKLOADS["cfg4"]), False)
+        for n_rows in (100_000, 1_000_000):  # cfg5 sweep, d = 768; the 1e7 point is the headline (cfg3)
+            if want("cfg5"):
+                ww = dict(WORKLOADS["cfg3"], N=n_rows, desc=f"bank-size sweep (BASELINE configs[4]): {n_rows:,} rows, d=768, k=30")
+                side_workload(f"cfg5_{n_rows:.0e}".replace("+0", ""), ww, False)
+    else:
+        if want("cfg3_replicas") and args.workload == "cfg3":
+            side_workload("cfg3_replicas", dict(WORKLOADS["cfg3"]), False)
+        if want("cfg2"):
+            side_workload("cfg2_sharded", dict(WORKLOADS["cfg2"]), True)
+        if want("cfg4") and args.workload != "cfg4":
+            side_workload("cfg4_sharded", dict(WORKLOADS["cfg4"]), True)
+        if want("cfg5"):
+            for n_rows in (1_000_000, 100_000_000):
+                if n_rows // world > 30_000_000:
+                    continue  # 1e8 rows need >= 4 GPUs with the fp32 re-rank copy resident
+                ww = dict(WORKLOADS["cfg3"], N=n_rows, desc=f"bank-size sweep (BASELINE configs[4]): {n_rows:,} rows, d=768, k=30")
+                side_workload(f"cfg5_{n_rows:.0e}".replace("+0", "") + "_sharded", ww, True)
 
     if rank == 0:
-        flop = 2.0 * w["N"] * w["d"] * Q
-        achieved = flop / (kern_ms * 1e-3) / 1e12 if kern_ms > 0 else None
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "search_kernel_traffic.json"))).get(args.workload)
         except Exception:
             pass
+        per_gpu_rows = b - a
         line = {
             "metric": "patch_queries_per_sec", "value": value, "unit": "patch-queries/s", "n_gpus": world,
             "steps": args.steps, "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {
-                "workload": f"{args.workload}: {w['desc']}", "bank_rows": w["N"], "d": w["d"], "k": K_NEIGH,
-                "k_prime": K_PRIME, "queries_per_step_per_gpu": Q, "classes": w["C"],
-                "parallelism": "single GPU" if world == 1 else f"replicas x{world} (full bank per GPU, queries split; no data-path collective)",
-                "path": "decode -> tcgen05 bf16 GEMM + fused top-k' -> fp32 exact re-rank -> label transfer -> upsample+argmax -> confusion",
-                "l2": f"inputs larger than L2: bf16 bank {w['N'] * w['d'] * 2 / 1e6:.0f} MB streamed every step, {RING} distinct query batches cycled",
+                "workload": f"{args.workload}: {w['desc']}", "bank_rows": w["N"], "bank_rows_per_gpu": per_gpu_rows,
+                "d": w["d"], "k": K_NEIGH, "k_prime": K_PRIME, "queries_per_step": Q, "classes": w["C"],
+                "parallelism": "single GPU" if world == 1 else
+                               f"bank row-sharded over {world} GPUs ({per_gpu_rows:,} rows each); every rank searches all "
+                               f"{Q} queries of a step, exchange, each rank post-processes its image slice",
+                "collective": collective,
+                "path": PATH,
+                "l2": f"inputs larger than L2: bf16 bank shard {per_gpu_rows * w['d'] * 2 / 1e6:.0f} MB streamed every step, "
+                      f"{RING} distinct query batches cycled",
             },
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic,
-                         "frac_of_nominal_2250": (achieved / 2250.0) if achieved else None,
-                         "kernel": "search_topk_kernel (tcgen05 GEMM + fused top-k')", "kernel_ms": kern_ms,
-                         "kernel_launches_timed": kern_n, "flop_per_launch": flop, "peak_source": peak_src,
-                         "kernel_share_of_step": kern_ms / ms_per_step if ms_per_step else None},
+            "roofline": {"bound": "tensor", "achieved": head["search_tflops"], "peak": peaks["tf"], "unit": "TFLOP/s",
+                         "frac": head["frac"], "traffic": traffic,
+                         "frac_of_burst_peak": (head["search_tflops"] / peaks["tf_burst"]) if head["search_tflops"] else None,
+                         "frac_of_nominal_2250": (head["search_tflops"] / 2250.0) if head["search_tflops"] else None,
+                         "kernel": "search_topk_kernel (tcgen05 GEMM + fused top-k')", "kernel_ms": head["search_kernel_ms"],
+                         "kernel_launches_timed": head["kernel_launches_timed"], "flop_per_launch": head["flop_per_launch"],
+                         "algorithmic_flop": "2 * bank rows on this GPU * d per query (SURVEY.md 8d)",
+                         "peak_source": peaks["src"], "kernel_share_of_step": head["kernel_share_of_step"]},
+            "roofline_hbm": hbm,
             "cpu_baseline": cpu,
             "parity": parity,
             "e2e": {"value": e2e_value, "unit": "patch-queries/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "call": "HbirdEvaluation.evaluate([one batch of pinned host (features, masks)]) -> mIoU float, once per step",
+                    "miou_last_step": last.get("miou")},
             "plugin_call": plugin,
             "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step,
             "clocks": clocks,
+            "by_workload": by_workload,
         }
-        if sharded is not None:
-            line["sharded"] = sharded
+        if world > 1:
+            line["sharded"] = {"value": value, "unit": "patch-queries/s", "ms_per_step": ms_per_step, "scaling": "strong",
+                               "bank_rows_total": w["N"], "bank_rows_per_gpu": per_gpu_rows, "collective": collective,
+                               "nccl_path_ms_per_step": nccl_ms, "parity": parity}
         print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 

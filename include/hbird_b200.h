@@ -183,6 +183,9 @@ int hb_search_last_launches(const hb_bank_t* bank);
  * kernels recorded since timing was (re-)enabled, and how many there were. */
 int hb_search_timing(hb_bank_t* bank, int enable);
 int hb_search_kernel_time(hb_bank_t* bank, float* mean_ms_out, int* count_out);
+/* Same, for the kernel that follows it in the same searches: K2b (exact re-rank, with whatever is
+ * fused into it: label transfer, scatter into the exchange windows). */
+int hb_search_rerank_time(hb_bank_t* bank, float* mean_ms_out, int* count_out);
 
 /* Host-only (no GPU needed): the work decomposition hb_search would use for a bank of `rows`
  * rows and Q queries on `num_sms` SMs.  out4 = {n_tiles, n_qblocks, n_chunks, n_units}; chunk c

@@ -303,6 +303,7 @@ int hb_bank_destroy(hb_bank_t* bank) {
   for (int i = 0; i < 64; ++i) {
     if (b->ev_begin[i]) cudaEventDestroy(b->ev_begin[i]);
     if (b->ev_end[i]) cudaEventDestroy(b->ev_end[i]);
+    if (b->ev_rerank[i]) cudaEventDestroy(b->ev_rerank[i]);
   }
   (void)cudaGetLastError();
   delete b;

@@ -65,6 +65,7 @@ struct Bank {
   int timing_count = 0;
   cudaEvent_t ev_begin[64] = {};
   cudaEvent_t ev_end[64] = {};
+  cudaEvent_t ev_rerank[64] = {};  // after K2b (+ fused K4a / scatter)
 };
 
 // ---- fused shard exchange (exchange.cu, rerank.cu) ----------------------------------------

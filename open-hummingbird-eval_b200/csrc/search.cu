@@ -745,6 +745,7 @@ int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_t idx_o
   rc = rerank_launch(b, q, Q, k, kp, plan.n_chunks, q_pad, cand, idx_offset, out_scores, out_idx, sc,
                      lo ? &label : nullptr, st);
   if (rc != HB_OK) return rc;
+  if (b->timing) HB_CHECK_CUDA(cudaEventRecord(b->ev_rerank[slot], st));
   b->last_launches++;
   return HB_OK;
 }
@@ -875,6 +876,7 @@ int hb_search_timing(hb_bank_t* bank, int enable) {
     for (int i = 0; i < 64; ++i) {
       HB_CHECK_CUDA(cudaEventCreate(&b->ev_begin[i]));
       HB_CHECK_CUDA(cudaEventCreate(&b->ev_end[i]));
+      HB_CHECK_CUDA(cudaEventCreate(&b->ev_rerank[i]));
     }
   }
   b->timing = enable != 0;
@@ -896,6 +898,29 @@ int hb_search_kernel_time(hb_bank_t* bank, float* mean_ms_out, int* count_out) {
   }
   *mean_ms_out = n ? static_cast<float>(sum / n) : 0.f;
   *count_out = n;
+  return HB_OK;
+}
+
+int hb_search_rerank_time(hb_bank_t* bank, float* mean_ms_out, int* count_out) {
+  HB_REQUIRE(bank != nullptr && mean_ms_out != nullptr && count_out != nullptr, "hb_search_rerank_time: NULL argument");
+  Bank* b = reinterpret_cast<Bank*>(bank);
+  HB_CHECK_CUDA(cudaSetDevice(b->device));
+  const int n = b->timing_count < 64 ? b->timing_count : 64;
+  double sum = 0.0;
+  int used = 0;
+  for (int i = 0; i < n; ++i) {
+    float ms = 0.f;
+    // a search that stopped after K2 (validation dump) never recorded this slot's event: skip it
+    if (cudaEventSynchronize(b->ev_rerank[i]) != cudaSuccess ||
+        cudaEventElapsedTime(&ms, b->ev_end[i], b->ev_rerank[i]) != cudaSuccess) {
+      (void)cudaGetLastError();
+      continue;
+    }
+    sum += ms;
+    ++used;
+  }
+  *mean_ms_out = used ? static_cast<float>(sum / used) : 0.f;
+  *count_out = used;
   return HB_OK;
 }
 

@@ -54,6 +54,7 @@ _SIGNATURES = [
     ("hb_search_last_launches", c_int, [c_void_p]),
     ("hb_search_timing", c_int, [c_void_p, c_int]),
     ("hb_search_kernel_time", c_int, [c_void_p, POINTER(c_float), POINTER(c_int)]),
+    ("hb_search_rerank_time", c_int, [c_void_p, POINTER(c_float), POINTER(c_int)]),
     ("hb_plan_search", c_int, [c_int64, c_int64, c_int, c_int, c_int, POINTER(c_int)]),
     ("hb_search_dump_scores", c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p]),
     ("hb_merge_topk", c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),

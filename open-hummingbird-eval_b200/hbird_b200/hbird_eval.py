@@ -113,6 +113,48 @@ class HbirdEvaluation:
         self._save_memory()
         self._create_nn(self.n_neighbours, nn_method=self.nn_method, **self.nn_params)
 
+    @classmethod
+    def from_bank(cls, feature_extractor: torch.nn.Module, bank: "ops.MemoryBank", num_classes: int,
+                  n_neighbours: int = 30, device: torch.device | str = "cuda",
+                  nn_params: Optional[Dict[str, Any]] = None, shard_counts=None) -> "HbirdEvaluation":
+        """An evaluator around a memory bank that already lives in HBM (built with ops.MemoryBank, or
+        kept from an earlier run): `evaluate()` behaves exactly as after a constructor that built the
+        bank from a loader.  With a row-sharded bank (torch.distributed initialised, nn_params
+        idx_shard=True) `bank` is this rank's shard and the label table is replicated here."""
+        self = cls.__new__(cls)
+        self.nn_params = dict(nn_params or {})
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("hbird_b200 runs on a CUDA device (sm_100); there is no CPU fallback.")
+        if self.device.index is None:
+            self.device = torch.device("cuda", bank.device)
+        unknown = sorted(set(self.nn_params) - set(cls._B200_PARAMS))
+        if unknown:
+            raise TypeError(f"nn_params not understood by the b200 backend: {unknown}")
+        self.nn_method = "b200"
+        self.feature_extractor = feature_extractor.to(self.device)
+        self.feature_extractor.eval()
+        self.augmentation_epoch, self.memory_size, self.num_sampled_features = 1, None, None
+        self.n_neighbours, self.num_classes = int(n_neighbours), num_classes
+        self.f_mem_p = self.l_mem_p = None
+        self.rank, self.world = hdist.dist_info()
+        self.idx_shard = bool(self.nn_params.get("idx_shard", False)) and self.world > 1
+        self.k_prime = int(self.nn_params.get("k_prime", 64 if self.n_neighbours <= 32 else 128))
+        self.keep_f32 = True
+        self.bank = bank
+        if not bank.finalized:
+            bank.finalize()
+        if self.idx_shard:
+            counts = list(shard_counts) if shard_counts is not None else hdist.gather_counts(bank.rows, self.device)
+            self.idx_offset = hdist.offsets_from_counts(counts)[self.rank]
+            self.label_table = hdist.all_gather_rows(bank.label_table(), counts)
+        else:
+            counts, self.idx_offset = [bank.rows], 0
+            self.label_table = bank.label_table()
+        self.shard_counts, self.total_rows = counts, sum(counts)
+        self._create_nn(self.n_neighbours, nn_method="b200", **self.nn_params)
+        return self
+
     # ------------------------------------------------------------------ bank construction
     def _capacity_rows(self, loader_len: Optional[int], first_batch: int, S: int) -> int:
         """Rows this rank can be asked to hold: its share of the loader's batches over ALL
@@ -400,20 +442,52 @@ class HbirdEvaluation:
             self.bank.close()
             self.bank = None
 
+    def _prefetched(self, loader):
+        """(step, x, y) with batch i+1's host->device copies issued on a side stream while batch i is
+        being evaluated (asynchronous when the loader yields pinned tensors, as a DataLoader with
+        pin_memory=True does).  Only the image slice / batches this rank works on are copied."""
+        copy_stream = getattr(self, "_copy_stream", None)
+        if copy_stream is None:
+            copy_stream = self._copy_stream = torch.cuda.Stream(self.device)
+        replicas = self.world > 1 and not self.idx_shard
+
+        def stage(step, x, y):
+            B = x.shape[0]
+            b0, b1 = hdist.split_range(B, self.world, self.rank) if self.idx_shard else (0, B)
+            main = torch.cuda.current_stream(self.device)
+            with torch.cuda.stream(copy_stream):
+                xd = x[b0:b1].to(self.device, non_blocking=True)
+                yd = y[b0:b1].to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            for t in (xd, yd):
+                t.record_stream(main)
+            return step, B, b0, b1, xd, yd, ev
+
+        pending = None
+        for step, (x, y) in enumerate(loader):
+            if replicas and step % self.world != self.rank:
+                continue  # replicas: the batches are dealt round-robin, nothing is exchanged
+            nxt = stage(step, x, y)
+            if pending is not None:
+                yield pending
+            pending = nxt
+        if pending is not None:
+            yield pending
+
     def _features(self, x: torch.Tensor) -> torch.Tensor:
         feats, _ = self.feature_extractor.forward_features(x)
         return feats.to(torch.float32).contiguous()
 
-    def _sharded_batch(self, x: torch.Tensor, want_neighbours: bool):
-        """Row-sharded bank: (label_hat, scores, idx, b0, b1) for the image slice [b0, b1) of the
-        batch this rank post-processes.  Features are extracted once across the ranks: each rank runs
-        the extractor on its slice and the query rows are all-gathered (every shard must see every
-        query).  Then K2/K2b per shard -> exchange -> merge with the label transfer fused in."""
-        B = x.shape[0]
-        b0, b1 = hdist.split_range(B, self.world, self.rank)
+    def _sharded_batch(self, x_slice: torch.Tensor, B: int, b0: int, b1: int, want_neighbours: bool):
+        """Row-sharded bank: (label_hat, scores, idx, q) for the image slice [b0, b1) of the batch this
+        rank post-processes.  Features are extracted once across the ranks: each rank runs the
+        extractor on its slice (x_slice, already on the device) and the query rows are all-gathered
+        (every shard must see every query).  Then K2/K2b per shard -> exchange -> merge with the
+        label transfer fused in."""
         img_counts = [hdist.split_range(B, self.world, r) for r in range(self.world)]
         if b1 > b0:
-            mine = self._features(x[b0:b1].to(self.device))
+            mine = self._features(x_slice)
             N, d = mine.shape[1], mine.shape[2]
         else:
             N, d = self.feature_extractor.eval_spatial_resolution ** 2, self.feature_extractor.d_model
@@ -431,7 +505,7 @@ class HbirdEvaluation:
             sl = slice(b0 * N, b1 * N)
             lh, s, i = ops.merge_topk_transfer(gs[:, sl].contiguous(), gi[:, sl].contiguous(), self.label_table, pp,
                                                qn[sl].contiguous(), BETA, want_neighbours)
-        return lh, s, i, q, b0, b1
+        return lh, s, i, q
 
     @torch.no_grad()
     def evaluate(self, val_loader, eval_spatial_resolution: int, return_knn_details: bool = False,
@@ -443,21 +517,18 @@ class HbirdEvaluation:
         conf = metric.confusion_buffer()
         details = []  # per batch: (batch number, knns, knns_labels, knns_ca_labels) CPU tensors
         replicas = self.world > 1 and not self.idx_shard
-        for step, (x, y) in enumerate(val_loader):
-            if replicas and step % self.world != self.rank:
-                continue  # replicas: the batches are dealt round-robin, nothing is exchanged
-            B, _, h, w = x.shape
+        for step, B, b0, b1, x, ys, copied in self._prefetched(val_loader):
+            torch.cuda.current_stream(self.device).wait_event(copied)
+            h, w = int(ys.shape[-2]), int(ys.shape[-1])  # the mask has the input's spatial size (:219,:240)
             if self.idx_shard:
-                lh, s, i, q, b0, b1 = self._sharded_batch(x, return_knn_details)
+                lh, s, i, q = self._sharded_batch(x, B, b0, b1, return_knn_details)
                 if b1 > b0:
-                    ys = y[b0:b1].to(self.device, dtype=torch.float32).contiguous()
                     ops.predict_score(lh, b1 - b0, S, h, w, conf, y=ys, ignore_index=ignore_index)
                 N, d = q.shape[0] // B, q.shape[1]
             else:
-                feats = self._features(x.to(self.device))
+                feats = self._features(x)
                 N, d = feats.shape[1], feats.shape[2]
                 q = feats.view(B * N, d)
-                ys = y.to(self.device, dtype=torch.float32).contiguous()
                 if self.nn_method != "b200":
                     s, i, qn = self._legacy_neighbours(q)
                     lh = ops.label_transfer(self.label_table, self.bank.patch_pixels, s, i, qn, BETA)

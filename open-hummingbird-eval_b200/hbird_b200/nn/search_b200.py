@@ -24,15 +24,24 @@ from .search_base import NearestNeighborSearchBase
 
 class NearestNeighborSearchB200(NearestNeighborSearchBase):
     def __init__(self, feature_memory, n_neighbors: int = 30, distance_measure: str = "dot_product",
-                 gpu_ids=None, k_prime: int = 64, keep_f32: bool = True, idx_offset: int = 0,
+                 idx_shard: bool = False, use_fp16: bool = False, gpu_ids=None, k_prime: Optional[int] = None,
+                 keep_f32: Optional[bool] = None, idx_offset: int = 0,
                  label_memory: Optional[torch.Tensor] = None, patch_pixels: int = 256,
                  bank: Optional[ops.MemoryBank] = None, cta_group: int = 0, max_chunks: int = 0,
                  renormalise: bool = False, **kwargs):
         """feature_memory: fp32 (N, d) unit-norm rows, CPU or CUDA (the reference hands over a CPU
         tensor, hbird_eval.py:178-182) — or None when a pre-built `bank` is adopted.
-        gpu_ids: [device] to use (default: current device); this class is one shard — multi-GPU
-        sharding is one process per GPU (hbird_b200.distributed)."""
+        idx_shard / use_fp16 / gpu_ids: the faiss backend's knobs (search_faiss.py:7).  This class is
+        ONE index on ONE GPU: idx_shard is recorded for the engine, which lays a multi-GPU bank out
+        as row shards or replicas with one process per GPU (hbird_b200.hbird_eval); use_fp16=True
+        drops the fp32 copy of the rows (the re-rank then reads the bf16 rows).
+        k_prime: candidates kept by the bf16 tensor-core pass (32, 64 or 128; default 64 for
+        n_neighbors <= 32, else 128 — the best k_prime/2 are strict, include/hbird_b200.h).
+        Unknown keyword arguments raise TypeError (the faiss backend ignores them silently)."""
+        if kwargs:
+            raise TypeError(f"NearestNeighborSearchB200 got unexpected keyword arguments {sorted(kwargs)}")
         self.n_neighbors = int(n_neighbors)
+        self.idx_shard, self.use_fp16 = bool(idx_shard), bool(use_fp16)
         self.distance_measure = distance_measure.lower()
         if self.distance_measure not in ("dot_product", "l2", "euclidean"):
             # search_faiss.py:48 / search_scann.py:20
@@ -51,11 +60,15 @@ class NearestNeighborSearchB200(NearestNeighborSearchBase):
                              "(torchrun) for a sharded bank")
         self.gpu_id = int(gpu_ids[0])
         ops.device_check(self.gpu_id)
-        self.k_prime = max(int(k_prime), 32)
+        if not 1 <= self.n_neighbors <= 128:
+            raise ValueError(f"n_neighbors={n_neighbors} outside the b200 backend's range [1, 128]")
+        if k_prime is None:
+            k_prime = 64 if self.n_neighbors <= 32 else 128
+        self.k_prime = int(k_prime)
         if self.k_prime not in (32, 64, 128) or self.n_neighbors > self.k_prime:
             raise ValueError(f"k_prime={k_prime} must be 32, 64 or 128 and >= n_neighbors={n_neighbors}")
         self.idx_offset = int(idx_offset)
-        self.keep_f32 = bool(keep_f32)
+        self.keep_f32 = (not self.use_fp16) if keep_f32 is None else bool(keep_f32)
         self._label_memory = label_memory
         self._patch_pixels = int(patch_pixels)
         self._renormalise = bool(renormalise)
@@ -105,9 +118,34 @@ class NearestNeighborSearchB200(NearestNeighborSearchBase):
             k = self.n_neighbors
         if isinstance(q, np.ndarray):
             q = torch.from_numpy(q)
-        q_dev = q.to(self.device, dtype=torch.float32).contiguous()
+        Q = q.shape[0]
+        if q.is_cuda:
+            q_dev = q.to(self.device, dtype=torch.float32).contiguous()
+        else:
+            # pinned staging buffers (grown on demand): asynchronous copies both ways, one
+            # synchronisation per call instead of three pageable, synchronous transfers
+            st = self._staging(Q, int(k))
+            st["q"][:Q].copy_(q.to(torch.float32))
+            q_dev = st["q_dev"][:Q]
+            q_dev.copy_(st["q"][:Q], non_blocking=True)
         scores, idx, _ = self.search_device(q_dev, k)
-        return idx.cpu().numpy(), scores.cpu().numpy()
+        if q.is_cuda:
+            return idx.cpu().numpy(), scores.cpu().numpy()
+        st["idx"][:Q].copy_(idx, non_blocking=True)
+        st["scores"][:Q].copy_(scores, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return st["idx"][:Q].numpy().copy(), st["scores"][:Q].numpy().copy()
+
+    def _staging(self, Q: int, k: int):
+        st = getattr(self, "_stage", None)
+        if st is None or st["q"].shape[0] < Q or st["k"] != k:
+            cap = max(Q, 1024)
+            st = {"k": k, "q": torch.empty((cap, self.embed_d), dtype=torch.float32).pin_memory(),
+                  "q_dev": torch.empty((cap, self.embed_d), dtype=torch.float32, device=self.device),
+                  "idx": torch.empty((cap, k), dtype=torch.int64).pin_memory(),
+                  "scores": torch.empty((cap, k), dtype=torch.float32).pin_memory()}
+            self._stage = st
+        return st
 
     # --- device-resident path -----------------------------------------------------------------
     def search_device(self, q_dev: torch.Tensor, k: Optional[int] = None):

@@ -222,6 +222,14 @@ class MemoryBank:
         check(lib.hb_search_kernel_time(self._h, ctypes.byref(ms), ctypes.byref(n)))
         return ms.value, n.value
 
+    def rerank_time_ms(self):
+        """(mean ms, count) of K2b (+ fused K4a / scatter) over the same searches."""
+        import ctypes
+
+        ms, n = ctypes.c_float(0), ctypes.c_int(0)
+        check(lib.hb_search_rerank_time(self._h, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
+
     def last_search_launches(self) -> int:
         return int(lib.hb_search_last_launches(self._h))
 

@@ -79,13 +79,13 @@ def miou_from_confusion(conf: np.ndarray, many_to_one: bool = False, precision_b
 class PredsmIoU:
     def __init__(self, num_pred_classes: int, num_gt_classes: int, device: Optional[torch.device] = None,
                  ignore_index: Optional[int] = None, prefer_cuda: bool = True,
-                 store_reordered_preds: bool = False):
+                 store_reordered_preds: bool = True):
         self.num_pred_classes = int(num_pred_classes)
         self.num_gt_classes = int(num_gt_classes)
         self.ignore_index = int(ignore_index) if ignore_index is not None else None
-        # The reference keeps every prediction on the host to return `reordered_preds`
-        # (eval_metrics.py:107-109,277-284); evaluate() discards that list (hbird_eval.py:253),
-        # so it is opt-in here.
+        # As the reference, every prediction is kept on the host by default so that compute() can
+        # return `reordered_preds` (eval_metrics.py:32,107-109,277-284).  HbirdEvaluation.evaluate()
+        # discards that list (hbird_eval.py:253) and passes False.
         self.store_reordered_preds = bool(store_reordered_preds)
         if device is None:
             if not torch.cuda.is_available():
@@ -133,6 +133,11 @@ class PredsmIoU:
     def confusion_matrix(self) -> np.ndarray:
         return self._conf_mat.cpu().numpy()
 
+    def confusion_buffer(self) -> torch.Tensor:
+        """The int64 (C_gt, C_pred) device matrix itself, for kernels that score a batch in place
+        (hb_eval_step / hb_predict_score) instead of going through update()."""
+        return self._conf_mat
+
     @torch.no_grad()
     def compute(self, is_global_zero: bool, many_to_one: bool = False, precision_based: bool = False,
                 linear_probe: bool = False, sync_distributed: bool = False,
@@ -145,7 +150,10 @@ class PredsmIoU:
             self.confusion_matrix(), many_to_one=many_to_one, precision_based=precision_based,
             linear_probe=linear_probe)
         reordered: List[int] = []
-        if return_reordered and self.store_reordered_preds:
+        if return_reordered and not self.store_reordered_preds:
+            # eval_metrics.py:272-276
+            raise RuntimeError("return_reordered=True requires store_reordered_preds=True at construction time.")
+        if return_reordered:
             allp = torch.cat(self._pred_chunks).long().numpy() if self._pred_chunks else np.zeros(0, np.int64)
             reordered = (allp if mapping is None else mapping[allp]).astype(np.int64).tolist()
         return miou, tp, fp, fn, reordered, bg

@@ -61,6 +61,22 @@ def _worker(rank, world, port, out_dir):
         qs = hdist.query_split(7, 196, world)
         assert qs[0] == 0 and qs[-1] == 7 * 196 and len(qs) == world + 1
         assert (qs[rank], qs[rank + 1]) == tuple(196 * v for v in hdist.split_range(7, world, rank))
+        # query-parallel feature extraction with a row-sharded bank: every rank extracts the features of
+        # its image slice and the ragged (n_r * S*S, d) blocks are all-gathered in image order; with
+        # fewer images than ranks a slice is empty
+        for n_img in (5, 1):
+            per_img, dd = 9, 8
+            allq = np.arange(n_img * per_img * dd, dtype=np.float32).reshape(n_img * per_img, dd)
+            spans = [hdist.split_range(n_img, world, r) for r in range(world)]
+            i0, i1 = spans[rank]
+            mine = torch.from_numpy(allq[i0 * per_img:i1 * per_img].copy())
+            got = hdist.all_gather_rows(mine, [(e - a) * per_img for a, e in spans])
+            assert got.dtype == torch.float32 and np.array_equal(got.numpy(), allq)
+        # replicas: validation batches are dealt round-robin, every batch to exactly one rank
+        dealt = [step for step in range(7) if step % world == rank]
+        every = [None] * world
+        dist.all_gather_object(every, dealt)
+        assert sorted(v for part in every for v in part) == list(range(7))
         # no CUDA device here: window creation fails on every rank and all ranks fall back together
         assert hdist.connect_shard_exchange(100, 30, torch.device("cpu")) is None
         b0, b1 = hdist.split_range(7, world, rank)

@@ -296,3 +296,102 @@ def test_small_banks_run_with_wide_lists():
     assert recall(i.cpu().numpy(), ref.indices.cpu().numpy()) >= 0.999
     np.testing.assert_allclose(s.cpu().numpy(), ref.values.cpu().numpy(), rtol=1e-3, atol=1e-5)
     bank.close()
+
+
+# ------------------------------------------------------------------ engine: parameters, legacy plugins, prebuilt banks
+def _engine(data, nn_method="b200", **kw):
+    from hbird_b200 import HbirdEvaluation
+    from hbird_b200.models import FeatureExtractorSimple
+
+    fe = FeatureExtractorSimple(data.model, data.ftr_extr_fn, data.S, data.d)
+    return HbirdEvaluation(fe, data.train_dataloader(), num_classes=data.C, n_neighbours=kw.pop("n_neighbours", 30),
+                           device=DEV, nn_method=nn_method, dataset_size=data.get_train_dataset_size(), **kw)
+
+
+def test_engine_rejects_unknown_nn_params_and_accepts_the_faiss_knobs():
+    cfg, g = load_golden("voc_tiny")
+    data = SyntheticSegmentationData(**cfg)
+    with pytest.raises(TypeError, match="k_prim"):
+        _engine(data, nn_params={"k_prim": 64})  # a typo must not be swallowed (search_faiss.py:7 swallows it)
+    # the faiss backend's own knobs are understood: idx_shard is a layout choice (single process: none),
+    # use_fp16 drops the fp32 copy of the rows (the re-rank then reads the bf16 rows)
+    ev = _engine(data, nn_params={"idx_shard": True, "use_fp16": True, "gpu_ids": [0]})
+    assert ev.keep_f32 is False and ev.idx_shard is False
+    miou = ev.evaluate(data.val_dataloader(), data.S, ignore_index=data.ignore_index)
+    assert abs(miou - float(g["miou"])) <= 5e-3  # bf16 rows: the reference's use_fp16 trade
+    ev.close()
+    # k' follows n_neighbours: 64 up to 32 neighbours, 128 beyond; more than 128 is out of range
+    ev = _engine(data, n_neighbours=40)
+    assert ev.k_prime == 128 and ev.NN_algorithm.k_prime == 128
+    ev.close()
+    with pytest.raises(ValueError, match="n_neighbours"):
+        _engine(data, n_neighbours=129)
+    from hbird_b200 import NearestNeighborSearchB200
+
+    with pytest.raises(TypeError, match="unexpected keyword"):
+        NearestNeighborSearchB200(torch.randn(300, 64), n_neighbors=5, nprobe=3)
+
+
+def test_legacy_plugin_path_ignores_the_backend_distances():
+    """A third-party backend behind the reference's ABC (here: exact ids, but L2 distances — the wrong
+    sign and scale for a softmax over cosines).  The engine must use the ids only and recompute the
+    inner products from the bank rows, as the reference's _cross_attention does (hbird_eval.py:594-609)."""
+    from hbird_b200 import register_nn_backend
+    from hbird_b200.nn.search_base import NearestNeighborSearchBase
+
+    class ExactIdsL2Distances(NearestNeighborSearchBase):
+        def __init__(self, feature_memory, n_neighbors=30, distance_measure="dot_product", **kwargs):
+            self.fm, self.k = feature_memory.clone(), n_neighbors
+
+        def _initialize_index(self):
+            return None
+
+        def _add_features_to_index(self):
+            return None
+
+        def find_nearest_neighbors(self, q, k=None):
+            ip = q.float() @ self.fm.T
+            idx = ip.topk(self.k, dim=1).indices
+            dist = torch.cdist(q.float(), self.fm).gather(1, idx) ** 2
+            return idx.numpy(), dist.numpy()
+
+    register_nn_backend("exact-ids-l2", ExactIdsL2Distances)
+    cfg, g = load_golden("voc_tiny")
+    data = SyntheticSegmentationData(**cfg)
+    ev = _engine(data, nn_method="exact-ids-l2")
+    miou, det = ev.evaluate(data.val_dataloader(), data.S, return_knn_details=True, ignore_index=data.ignore_index)
+    assert abs(miou - float(g["miou"])) <= 5e-4
+    np.testing.assert_allclose(det["knns_ca_labels"].numpy().reshape(g["label_hat"].shape), g["label_hat"], rtol=0, atol=2e-5)
+    ev.close()
+
+
+def test_evaluator_from_a_prebuilt_bank_takes_host_features():
+    """HbirdEvaluation.from_bank + a loader of pinned host (features, masks): the e2e call bench.py
+    times.  Same result as the engine that built the bank itself from images."""
+    from hbird_b200 import HbirdEvaluation
+    from hbird_b200.models import FeatureExtractorSimple
+
+    cfg, g = load_golden("ade_tiny")
+    data = SyntheticSegmentationData(**cfg)
+    bank = build_bank_from_loader(data)
+    fe = FeatureExtractorSimple(torch.nn.Identity(), lambda m, x: (x, None), data.S, data.d)
+    ev = HbirdEvaluation.from_bank(fe, bank, data.C, 30, DEV, {"k_prime": 64})
+    loader = [(torch.from_numpy(f).pin_memory(), torch.from_numpy(y).pin_memory()) for f, y in batches_np(data, data.val_dataloader())]
+    miou = ev.evaluate(loader, data.S, ignore_index=data.ignore_index)
+    assert abs(miou - float(g["miou"])) <= 5e-4
+    assert np.abs(ev.last_confusion - g["conf"]).sum() <= 5e-4 * g["conf"].sum()
+    ev.close()
+
+
+def test_bench_synthetic_inputs_are_bit_identical_on_cpu_and_gpu():
+    """bench.py's two arms must look at the same bank: bench_synth is integer hashing plus single fp32
+    operations, so the CPU (reference arm) and the GPU (B200 arm) produce the same bits."""
+    import bench
+    import bench_synth as syn
+
+    for name in ("cfg1", "cfg4"):
+        w = bench.WORKLOADS[name]
+        fc, mc = syn.images(w, 37, 3, torch.device("cpu"), stream=1)
+        fg, mg = syn.images(w, 37, 3, torch.device(DEV), stream=1)
+        assert torch.equal(fg.cpu(), fc) and torch.equal(mg.cpu(), mc)
+        assert torch.equal(syn.prototypes(w, torch.device(DEV)).cpu(), syn.prototypes(w, torch.device("cpu")))

@@ -1,4 +1,5 @@
-"""Multi-GPU (one process per GPU, NCCL) parity of the row-sharded engine.  Needs >= 2 B200s."""
+"""Multi-GPU (one process per GPU, NCCL) parity of the engine in both layouts (row shards with the
+fused exchange and with NCCL, replicas).  Needs >= 2 B200s."""
 import json
 import os
 import subprocess
@@ -12,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs at least 2 GPUs")
-def test_sharded_engine_matches_reference_golden():
+def test_multi_gpu_engine_matches_reference_golden():
     n = 2  # the golden miniatures have 2-3 training batches: every rank must own at least one
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
            "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tools", "dist_check.py")]

@@ -119,3 +119,26 @@ def test_metric_math_rectangular_and_precision_modes_match_reference():
         omiou, otp, ofp, ofn, obg = O.miou_from_confusion(conf, **kw)
         assert omiou == pytest.approx(k["miou"], abs=1e-12) and (otp, ofp, ofn) == (k["tp"], k["fp"], k["fn"])
         assert obg == pytest.approx(k["bg"])
+
+
+@pytest.mark.parametrize("L,W,aug,bounded", [(3, 2, 2, False), (3, 2, 2, True), (5, 4, 3, False), (2, 2, 1, False), (7, 8, 1, True), (1, 1, 4, False)])
+def test_per_rank_bank_capacity_covers_the_batches_a_rank_takes(L, W, aug, bounded):
+    """_create_memory deals batch number `step` to rank step % W and `step` runs on across augmentation
+    epochs (hbird_b200/hbird_eval.py); every rank's capacity must cover what it is dealt — and, in
+    bounded mode, no rank reserves the whole memory_size."""
+    from types import SimpleNamespace
+
+    from hbird_b200.hbird_eval import HbirdEvaluation
+
+    B, S, K = 4, 7, 5
+    per_image = K if bounded else S * S
+    total = aug * L * B * per_image
+    for rank in range(W):
+        me = SimpleNamespace(memory_size=(total if bounded else None), num_sampled_features=K, augmentation_epoch=aug,
+                             rank=rank, world=W)
+        cap = HbirdEvaluation._capacity_rows(me, L, B, S)
+        dealt = sum(1 for step in range(aug * L) if step % W == rank)
+        assert cap >= max(1, dealt * B * per_image)
+        assert cap <= max(1, (dealt * B * per_image)) or W == 1
+        if bounded and W > 1 and dealt:
+            assert cap < total

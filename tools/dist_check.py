@@ -1,7 +1,11 @@
-"""Run under torchrun (one rank per GPU): the row-sharded engine must reproduce the reference's
-golden result (tests/golden) — per-shard search, shard exchange (fused peer-memory exchange and
-the NCCL all-gather + K3 merge path, which must agree bit for bit), replicated label table,
-all-reduced confusion matrix."""
+"""Run under torchrun (one rank per GPU): the multi-GPU engine must reproduce the reference's golden
+result (tests/golden) in both of the reference's faiss layouts (search_faiss.py:53-74):
+row shards (nn_params idx_shard=True: per-shard search, shard exchange — fused peer-memory exchange
+and the NCCL all-gather + K3 merge path, which must agree bit for bit — replicated label table,
+features extracted once across the ranks and all-gathered) and replicas (idx_shard=False, the
+default: full bank on every rank, validation batches dealt round-robin); all-reduced confusion
+matrix in both.  Also: augmentation epochs with a loader length that does not divide by the world
+size (per-rank capacity), memory save / load with a sharded bank."""
 import json
 import os
 import sys
@@ -27,10 +31,11 @@ for name in ("voc_tiny", "ade_tiny"):
     cfg, g = load_golden(name)
     data = SyntheticSegmentationData(**cfg)
     confs = {}
-    for mode in ("p2p", "nccl"):
+    for mode in ("p2p", "nccl", "replicas"):
         fe = FeatureExtractorSimple(data.model, data.ftr_extr_fn, data.S, data.d)
+        nn_params = {"idx_shard": False} if mode == "replicas" else {"idx_shard": True, "exchange": mode}
         ev = HbirdEvaluation(fe, data.train_dataloader(), num_classes=data.C, n_neighbours=30,
-                             device=f"cuda:{local}", nn_method="b200", nn_params={"exchange": mode},
+                             device=f"cuda:{local}", nn_method="b200", nn_params=nn_params,
                              dataset_size=data.get_train_dataset_size())
         miou, det = ev.evaluate(data.val_dataloader(), data.S, return_knn_details=True, ignore_index=data.ignore_index)
         conf = ev.last_confusion
@@ -47,7 +52,8 @@ for name in ("voc_tiny", "ade_tiny"):
         fused = getattr(ev, "_xchg", None) is not None
         good = abs(miou - float(g["miou"])) <= 5e-4 and conf.sum() == g["conf"].sum() and \
             np.abs(conf - g["conf"]).sum() <= 2e-4 * conf.sum() and sum(rows) == g["feature_memory"].shape[0] and \
-            len(rows) == world and fused == (mode == "p2p") and bool(details_ok)
+            len(rows) == (1 if mode == "replicas" else world) and fused == (mode == "p2p") and bool(details_ok) and \
+            ev.bank.rows == (sum(rows) if mode == "replicas" else rows[rank])
         report[f"{name}_{mode}"] = {"miou": miou, "ref": float(g["miou"]), "shard_rows": rows,
                                     "fused_exchange": fused, "details_ok": bool(details_ok), "ok": bool(good)}
         ok = ok and good
@@ -60,7 +66,7 @@ for name in ("voc_tiny", "ade_tiny"):
     dist.barrier()
     fe = FeatureExtractorSimple(data.model, data.ftr_extr_fn, data.S, data.d)
     ev = HbirdEvaluation(fe, data.train_dataloader(), num_classes=data.C, n_neighbours=30, device=f"cuda:{local}",
-                         nn_method="b200", dataset_size=data.get_train_dataset_size(),
+                         nn_method="b200", nn_params={"idx_shard": True}, dataset_size=data.get_train_dataset_size(),
                          f_mem_p=os.path.join(tmp, "f.pt"), l_mem_p=os.path.join(tmp, "l.pt"))
     saved_f, saved_l = torch.load(os.path.join(tmp, "f.pt")).numpy(), torch.load(os.path.join(tmp, "l.pt")).numpy()
     order_s = np.lexsort(np.concatenate([saved_f, saved_l], 1).T[::-1])
@@ -76,9 +82,31 @@ for name in ("voc_tiny", "ade_tiny"):
                                    "shard_rows": ev.shard_counts}
     ok = ok and bool(files_ok) and reload_ok
     ev.close()
-    same = bool((confs["p2p"] == confs["nccl"]).all())
+    same = bool((confs["p2p"] == confs["nccl"]).all()) and bool((confs["p2p"] == confs["replicas"]).all())
     report[f"{name}_paths_identical"] = same
     ok = ok and same
+# augmentation epochs x a loader whose length does not divide by the world size: the batch counter runs
+# on across epochs, so ranks take different numbers of batches; capacity must cover each of them and the
+# doubled bank must still reproduce the single-epoch result (duplicate rows, ties by row id)
+cfg, g = load_golden("ade_tiny")  # 3 training batches: with 2 ranks and 2 epochs rank 1 takes 3 of the 6
+data = SyntheticSegmentationData(**cfg)
+aug_conf = {}
+for shard in (True, False):
+    fe = FeatureExtractorSimple(data.model, data.ftr_extr_fn, data.S, data.d)
+    ev = HbirdEvaluation(fe, data.train_dataloader(), num_classes=data.C, n_neighbours=30, augmentation_epoch=2,
+                         device=f"cuda:{local}", nn_method="b200", nn_params={"idx_shard": shard},
+                         dataset_size=data.get_train_dataset_size())
+    miou = ev.evaluate(data.val_dataloader(), data.S, ignore_index=data.ignore_index)
+    aug_conf[shard] = ev.last_confusion
+    good = ev.total_rows == 2 * g["feature_memory"].shape[0] and 0.0 < miou <= 1.0 and \
+        ev.last_confusion.sum() == g["conf"].sum()
+    report[f"aug2_{'shards' if shard else 'replicas'}"] = {"loader_len": len(data.train_dataloader()), "rows": ev.shard_counts,
+                                                          "miou": miou, "ok": bool(good)}
+    ok = ok and good
+    ev.close()
+# duplicate rows tie on the score and resolve by row id, which both layouts number alike (rank-major)
+report["aug2_layouts_identical"] = bool((aug_conf[True] == aug_conf[False]).all())
+ok = ok and report["aug2_layouts_identical"]
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
