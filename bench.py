@@ -152,6 +152,10 @@ class ClockSampler:
             self._t = threading.Thread(target=self._loop, daemon=True)
             self._t.start()
 
+    def pause(self):
+        """Stop sampling (the timed region is over); stop() then only reports."""
+        self._stop.set()
+
     def stop(self):
         self._stop.set()
         if self._t is not None:
@@ -186,10 +190,14 @@ def run_step(ops, bank, table, w, q, y, conf, shard=None):
         ops.predict_score(lh, b1 - b0, S, H, H, conf, y=y[b0:b1], ignore_index=w["ignore"])
 
 
-def timed_loop(torch, dist, world, fn, steps, warmup):
-    """W untimed + K timed steps, barrier + synchronize on both sides, CUDA events, max over ranks."""
+def timed_loop(torch, dist, world, fn, steps, warmup, drain=None):
+    """W untimed + K timed steps, barrier + synchronize on both sides, CUDA events, max over ranks.
+    drain: called after the last step inside the timed region (a pipelined step function still owes
+    the post-processing of its last batch)."""
     for i in range(warmup):
         fn(i)
+    if drain is not None:
+        drain()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -198,6 +206,8 @@ def timed_loop(torch, dist, world, fn, steps, warmup):
     e0.record()
     for i in range(steps):
         fn(warmup + i)
+    if drain is not None:
+        drain()
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -211,33 +221,60 @@ def timed_loop(torch, dist, world, fn, steps, warmup):
 
 def measure_workload(torch, dist, ops, w, bank, table, ring, steps, warmup, world, peaks, shard=None, graph=False,
                      sampler=None):
-    """Device-resident throughput of one workload + the search kernel's share and roofline fraction."""
+    """Device-resident throughput of one workload + the search kernel's share and roofline fraction.
+    The timed loop is the two-stream pipeline (hbird_b200.pipeline.EvalPipeline: K2 of batch i+1 on one
+    stream, the HBM-bound post-processing of batch i on another, under it); the one-call-per-batch
+    form (run_step) is timed next to it for comparison."""
+    from hbird_b200 import distributed as hdist
+    from hbird_b200 import pipeline as hpipe
+    from hbird_b200.pipeline import EvalPipeline
+
     Q = w["B"] * w["S"] ** 2
     conf = torch.zeros((w["C"], w["C"]), dtype=torch.int64, device=ring[0][0].device)
+    rank = 0 if shard is None else shard["rank"]
+    b0, b1 = hdist.split_range(w["B"], world, rank) if shard is not None else (0, w["B"])
+    pipe = EvalPipeline(bank, table, w["S"], conf, w["ignore"], K_NEIGH, K_PRIME, BETA,
+                        0 if shard is None else shard["offset"], world if shard is not None else 1, rank,
+                        None if shard is None else shard.get("xchg"))
+    slices = [(q, y[b0:b1].contiguous()) for q, y in ring]
+    # the engine's own policy: pipeline when the bank (shard) is small enough for the overlap to pay
+    pipelined = hpipe.worthwhile(bank)
 
     def step(i):
-        q, y = ring[i % len(ring)]
-        run_step(ops, bank, table, w, q, y, conf, shard)
+        if pipelined:
+            q, y = slices[i % len(slices)]
+            pipe.submit(q, y, w["B"])
+        else:
+            run_step(ops, bank, table, w, *ring[i % len(ring)], conf, shard)
 
     for i in range(warmup):
         step(i)
+    pipe.flush()
     torch.cuda.synchronize()
     bank.enable_kernel_timing(True)
     if sampler is not None:
         sampler.start()  # clocks are sampled during the timed region only
-    ms = timed_loop(torch, dist, world, step, steps, 0) / steps
+    ms = timed_loop(torch, dist, world, step, steps, 0, drain=pipe.flush) / steps
+    if sampler is not None:
+        sampler.pause()
     k2_ms, k2_n = bank.kernel_time_ms()
+    k2b_under_ms, _ = bank.rerank_time_ms()
+    # the same batches, one blocking call sequence per batch (no overlap between batches)
+    bank.enable_kernel_timing(True)
+    plain_steps = max(3, steps // 4)
+    ms_plain = timed_loop(torch, dist, world, lambda i: run_step(ops, bank, table, w, *ring[i % len(ring)], conf, shard),
+                          plain_steps, 2) / plain_steps
     k2b_ms, _ = bank.rerank_time_ms()
     bank.enable_kernel_timing(False)
     rows = bank.rows
     flop = 2.0 * rows * w["d"] * Q  # per GPU: this shard's rows x all queries
     tf = flop / (k2_ms * 1e-3) / 1e12 if k2_ms > 0 else None
-    out = {"ms_per_step": ms, "search_kernel_ms": k2_ms, "rerank_kernel_ms": k2b_ms, "kernel_launches_timed": k2_n,
+    out = {"ms_per_step": ms, "pipelined": pipelined, "ms_per_step_unpipelined": ms_plain, "search_kernel_ms": k2_ms, "rerank_kernel_ms": k2b_ms,
+           "rerank_kernel_ms_under_next_search": k2b_under_ms, "kernel_launches_timed": k2_n,
            "search_tflops": tf, "frac": (tf / peaks["tf"]) if tf else None,
            "kernel_share_of_step": (k2_ms / ms) if ms else None, "flop_per_launch": flop}
     if graph and shard is None:
-        # the same 4 launches replayed from CUDA graphs (one per ring slot): what a serving loop that
-        # knows its batch shape does; matters where a step is ~1 ms (cfg1)
+        # the one-call step (4 launches) replayed from CUDA graphs, one per ring slot
         lh = torch.empty((Q, w["C"]), dtype=torch.float32, device=conf.device)
         graphs = []
         side = torch.cuda.Stream()
@@ -654,7 +691,7 @@ def main():
     if world > 1 and xchg is not None:
         plain = dict(shard)
         plain.pop("xchg")
-        m2, conf_nccl = measure_workload(torch, dist, ops, w, bank, table, ring, max(3, args.steps // 4), warmup, world, peaks, plain)
+        m2, conf_nccl = measure_workload(torch, dist, ops, w, bank, table, ring, max(4, args.steps // 4), warmup, world, peaks, plain)
         nccl_ms = m2["ms_per_step"]
 
     # ------------------------------------------------------------------ e2e: the engine's public call, host inputs
@@ -759,7 +796,8 @@ def main():
                           "single GPU" if world == 1 else "replicas (full bank per GPU, batches split)"),
                "value": per_step / (m["ms_per_step"] * 1e-3), "unit": "patch-queries/s", "ms_per_step": m["ms_per_step"],
                "search_kernel_ms": m["search_kernel_ms"], "search_kernel_frac_of_sustained_bf16": m["frac"],
-               "search_kernel_tflops": m["search_tflops"], "scaling": "strong" if sharded and world > 1 else "weak"}
+               "search_kernel_tflops": m["search_tflops"], "scaling": "strong" if sharded and world > 1 else "weak",
+               "pipelined": m["pipelined"], "ms_per_step_unpipelined": m["ms_per_step_unpipelined"]}
         if "ms_per_step_cuda_graph" in m:
             res["ms_per_step_cuda_graph"] = m["ms_per_step_cuda_graph"]
             res["value_cuda_graph"] = per_step / (m["ms_per_step_cuda_graph"] * 1e-3)
@@ -815,6 +853,10 @@ def main():
                                f"{Q} queries of a step, exchange, each rank post-processes its image slice",
                 "collective": collective,
                 "path": PATH,
+                "pipelining": ("two streams: K2 of batch i+1 (high priority) over the re-rank / exchange / merge / tail of "
+                               "batch i (shared-memory-free kernels co-resident with the search CTAs); every batch is complete "
+                               "inside the timed region") if head["pipelined"] else
+                              "none: one blocking call sequence per batch (the engine pipelines banks of <= 2M rows per GPU only)",
                 "l2": f"inputs larger than L2: bf16 bank shard {per_gpu_rows * w['d'] * 2 / 1e6:.0f} MB streamed every step, "
                       f"{RING} distinct query batches cycled",
             },
@@ -825,7 +867,8 @@ def main():
                          "kernel": "search_topk_kernel (tcgen05 GEMM + fused top-k')", "kernel_ms": head["search_kernel_ms"],
                          "kernel_launches_timed": head["kernel_launches_timed"], "flop_per_launch": head["flop_per_launch"],
                          "algorithmic_flop": "2 * bank rows on this GPU * d per query (SURVEY.md 8d)",
-                         "peak_source": peaks["src"], "kernel_share_of_step": head["kernel_share_of_step"]},
+                         "peak_source": peaks["src"], "kernel_share_of_step": head["kernel_share_of_step"],
+                         "ms_per_step_unpipelined": head["ms_per_step_unpipelined"]},
             "roofline_hbm": hbm,
             "cpu_baseline": cpu,
             "parity": parity,

@@ -147,6 +147,22 @@ int hb_search_transfer(hb_bank_t* bank, const uint16_t* label_table_dev, int64_t
                        float beta, float* out_scores_dev, int64_t* out_idx_dev,
                        float* out_qnorm_dev, float* out_label_hat_dev, void* stream);
 
+/* Split form of hb_search / hb_search_transfer for software pipelining across batches.  begin =
+ * query prep + K2 (the tensor-core pass) into pipeline slot `slot` (0 or 1) on `stream`; finish = K2b
+ * (exact re-rank, outputs as hb_search / hb_search_transfer: give out_scores/out_idx, out_label_hat,
+ * or all three) from that slot on ANY stream that is ordered after the begin (event).  The plain and
+ * the scatter re-rank kernels own no shared memory, so they run on the SMs under the K2 of the NEXT
+ * batch, whose CTAs take all but ~2 KB of it: the HBM-bound half of batch i hides under the
+ * tensor-bound half of batch i+1.  A slot is reused only after its finish has run (enforced with an
+ * event inside the library); q_dev must stay valid until the finish has executed; the scratch block is
+ * sized for both slots by the first begin (it must not have to grow while a slot is in flight). */
+int hb_search_begin(hb_bank_t* bank, const float* q_dev, int64_t Q, int k_prime, int slot,
+                    float* out_qnorm_dev, void* stream);
+int hb_search_finish(hb_bank_t* bank, int slot, const float* q_dev, int k, int64_t idx_offset,
+                     const uint16_t* label_table_dev, int64_t table_rows, float beta,
+                     float* out_scores_dev, int64_t* out_idx_dev, float* out_label_hat_dev,
+                     void* stream);
+
 /* One validation batch through the whole path in 4 launches (query prep, K2, K2b+K4a, fused tail):
  * replaces hbird_eval.py:217-252 for a bank that is not row-sharded.  q_dev fp32 (B*S*S, d) raw
  * features; y_dev fp32 (B, H, W) = class id / 255 (loader contract, :219); label_hat_dev fp32
@@ -246,6 +262,10 @@ int hb_exchange_disconnect(hb_exchange_t* xchg);
 int hb_search_scatter(hb_bank_t* bank, hb_exchange_t* xchg, const float* q_dev, int64_t Q, int k,
                       int k_prime, int64_t idx_offset, const int64_t* qsplit_host,
                       float* out_qnorm_dev, void* stream);
+/* hb_search_scatter's second half for a search started with hb_search_begin (see there): K2b of
+ * pipeline slot `slot` with the scatter into the owner ranks' windows, on `stream`. */
+int hb_search_finish_scatter(hb_bank_t* bank, hb_exchange_t* xchg, int slot, const float* q_dev, int k,
+                             int64_t idx_offset, const int64_t* qsplit_host, void* stream);
 /* Outputs: fp32 / int64 (rows, k) for this rank's slice of the last scatter, sorted descending,
  * global indices; rows = hb_exchange_slice_rows().  A peer that never arrives makes the kernel
  * trap after 10 min instead of hanging the GPU. */

@@ -304,6 +304,11 @@ int hb_bank_destroy(hb_bank_t* bank) {
     if (b->ev_begin[i]) cudaEventDestroy(b->ev_begin[i]);
     if (b->ev_end[i]) cudaEventDestroy(b->ev_end[i]);
     if (b->ev_rerank[i]) cudaEventDestroy(b->ev_rerank[i]);
+    if (b->ev_rerank0[i]) cudaEventDestroy(b->ev_rerank0[i]);
+  }
+  for (int i = 0; i < 2; ++i) {
+    if (b->pipe[i].buf) cudaFree(b->pipe[i].buf);
+    if (b->pipe[i].done) cudaEventDestroy(b->pipe[i].done);
   }
   (void)cudaGetLastError();
   delete b;

@@ -32,6 +32,21 @@ void clear_error();
     }                                                                                    \
   } while (0)
 
+// A search between its two halves (search.cu): hb_search_begin = query prep + K2 (tensor-core
+// pass) fills the slot's candidate buffer, hb_search_finish* = K2b reads it — possibly on another
+// stream, while the K2 of the next batch already runs (two slots alternate).
+struct PipeSlot {
+  bool begun = false;
+  int kp = 0, n_chunks = 0;
+  int64_t Q = 0, q_pad = 0;
+  const uint64_t* cand = nullptr;
+  const float* qnorm = nullptr;
+  int timing_slot = -1;
+  cudaEvent_t done = nullptr;  // recorded by the finish on its stream; reuse of the slot waits for it
+  void* buf = nullptr;         // the slot's own scratch: norms | candidate keys (grown on demand)
+  size_t buf_bytes = 0;
+};
+
 // One shard of the memory bank, resident in HBM.
 struct Bank {
   int device = 0;
@@ -65,7 +80,9 @@ struct Bank {
   int timing_count = 0;
   cudaEvent_t ev_begin[64] = {};
   cudaEvent_t ev_end[64] = {};
-  cudaEvent_t ev_rerank[64] = {};  // after K2b (+ fused K4a / scatter)
+  cudaEvent_t ev_rerank0[64] = {};  // before / after K2b (+ fused K4a / scatter), on the finish stream
+  cudaEvent_t ev_rerank[64] = {};
+  PipeSlot pipe[2];
 };
 
 // ---- fused shard exchange (exchange.cu, rerank.cu) ----------------------------------------
@@ -132,6 +149,11 @@ int predict_score_launch(const float* label_hat, int B, int S, int C, int H, int
 int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_t idx_offset,
                 float* out_scores, int64_t* out_idx, float* out_qnorm, float* dump, int cg_override,
                 cudaStream_t st, const Scatter* sc, const LabelOut* lo);
+// The two halves of search_impl (which is begin + finish of slot 0 on one stream).
+int search_begin_impl(Bank* b, const float* q, int64_t Q, int kp, int slot, float* out_qnorm, float* dump,
+                      int cg_override, cudaStream_t st);
+int search_finish_impl(Bank* b, int slot, const float* q, int k, int64_t idx_offset, float* out_scores,
+                       int64_t* out_idx, const Scatter* sc, const LabelOut* lo, cudaStream_t st);
 int rerank_launch(const Bank* b, const float* q, int64_t Q, int k, int kp, int n_chunks,
                   int64_t q_pad, const uint64_t* cand, int64_t idx_offset, float* out_scores,
                   int64_t* out_idx, const Scatter* sc, const LabelOut* lo, cudaStream_t st);  // rerank.cu

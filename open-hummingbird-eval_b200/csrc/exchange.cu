@@ -132,53 +132,86 @@ int hb_exchange_connect_local(hb_exchange_t* xchg, hb_exchange_t* const* peers, 
   return HB_OK;
 }
 
+// Argument checks shared by the one-call and the split form of the scatter, and the Scatter record
+// (where each query's rows go) for exchange number `step`.
+static int prepare_scatter(Bank* b, Exchange* x, int64_t Q, int k, int k_prime, const int64_t* qsplit_host,
+                           uint32_t step, hb::Scatter* sc, const char* who) {
+  if (!b->finalized) {
+    hb::set_error("%s: bank not finalized (call hb_bank_finalize first)", who);
+    return HB_ERR_STATE;
+  }
+  if (!x->connected) {
+    hb::set_error("%s: exchange not connected (call hb_exchange_connect first)", who);
+    return HB_ERR_STATE;
+  }
+  HB_REQUIRE(b->device == x->device, "%s: bank on device %d, exchange on device %d", who, b->device, x->device);
+  HB_REQUIRE(Q >= 1 && Q < (int64_t(1) << 31), "%s: Q=%lld out of range", who, (long long)Q);
+  HB_REQUIRE(k >= 1 && k <= k_prime && k <= x->kmax, "%s: need 1 <= k (%d) <= min(k_prime %d, max_k %d)", who, k, k_prime, x->kmax);
+  HB_REQUIRE(k_prime == 32 || k_prime == 64 || k_prime == 128, "%s: k_prime=%d not in {32, 64, 128}", who, k_prime);
+  HB_REQUIRE(qsplit_host != nullptr, "%s: NULL pointer", who);
+  HB_REQUIRE(b->rows >= 1, "%s: the bank shard is empty", who);
+  // the cross-shard merge keeps the LARGEST scores; squared-L2 results are ascending distances
+  HB_REQUIRE((b->flags & HB_BANK_L2) == 0, "%s: squared-L2 banks cannot be row-sharded (inner-product metric only)", who);
+  HB_REQUIRE(qsplit_host[0] == 0 && qsplit_host[x->world] == Q, "%s: qsplit must run from 0 to Q", who);
+  for (int p = 0; p < x->world; ++p) {
+    const int64_t n = qsplit_host[p + 1] - qsplit_host[p];
+    HB_REQUIRE(n >= 0 && n <= x->cap, "%s: slice %d has %lld rows, window capacity is %lld", who, p, (long long)n, (long long)x->cap);
+  }
+  const int parity = static_cast<int>(step & 1u);
+  sc->world = x->world;
+  sc->rank = x->rank;
+  sc->step = step;
+  sc->done_ctas = x->done_ctas;
+  for (int p = 0; p <= x->world; ++p) sc->qsplit[p] = qsplit_host[p];
+  for (int p = 0; p < x->world; ++p) {
+    uint8_t* win = x->window[p];
+    sc->scores[p] = reinterpret_cast<float*>(win + x->scores_off(parity)) + x->slot_elems() * x->rank;
+    sc->idx[p] = reinterpret_cast<int64_t*>(win + x->idx_off(parity)) + x->slot_elems() * x->rank;
+    sc->flag[p] = reinterpret_cast<uint32_t*>(win) + x->rank;
+  }
+  return HB_OK;
+}
+
 int hb_search_scatter(hb_bank_t* bank, hb_exchange_t* xchg, const float* q_dev, int64_t Q, int k,
                       int k_prime, int64_t idx_offset, const int64_t* qsplit_host,
                       float* out_qnorm_dev, void* stream) {
   HB_REQUIRE(bank && xchg, "hb_search_scatter: NULL handle");
   Bank* b = reinterpret_cast<Bank*>(bank);
   Exchange* x = reinterpret_cast<Exchange*>(xchg);
-  if (!b->finalized) {
-    hb::set_error("hb_search_scatter: bank not finalized (call hb_bank_finalize first)");
-    return HB_ERR_STATE;
-  }
-  if (!x->connected) {
-    hb::set_error("hb_search_scatter: exchange not connected (call hb_exchange_connect first)");
-    return HB_ERR_STATE;
-  }
-  HB_REQUIRE(b->device == x->device, "hb_search_scatter: bank on device %d, exchange on device %d", b->device, x->device);
-  HB_REQUIRE(Q >= 1 && Q < (int64_t(1) << 31), "hb_search_scatter: Q=%lld out of range", (long long)Q);
-  HB_REQUIRE(k >= 1 && k <= k_prime && k <= x->kmax, "hb_search_scatter: need 1 <= k (%d) <= min(k_prime %d, max_k %d)", k, k_prime, x->kmax);
-  HB_REQUIRE(k_prime == 32 || k_prime == 64 || k_prime == 128, "hb_search_scatter: k_prime=%d not in {32, 64, 128}", k_prime);
-  HB_REQUIRE(q_dev && qsplit_host, "hb_search_scatter: NULL pointer");
-  HB_REQUIRE(b->rows >= 1, "hb_search_scatter: the bank shard is empty");
-  // the cross-shard merge keeps the LARGEST scores; squared-L2 results are ascending distances
-  HB_REQUIRE((b->flags & HB_BANK_L2) == 0, "hb_search_scatter: squared-L2 banks cannot be row-sharded (inner-product metric only)");
-  HB_REQUIRE(qsplit_host[0] == 0 && qsplit_host[x->world] == Q, "hb_search_scatter: qsplit must run from 0 to Q");
-  for (int p = 0; p < x->world; ++p) {
-    const int64_t n = qsplit_host[p + 1] - qsplit_host[p];
-    HB_REQUIRE(n >= 0 && n <= x->cap, "hb_search_scatter: slice %d has %lld rows, window capacity is %lld", p, (long long)n, (long long)x->cap);
-  }
-  HB_CHECK_CUDA(cudaSetDevice(b->device));
-
+  HB_REQUIRE(q_dev != nullptr, "hb_search_scatter: NULL pointer");
   // the step counter advances only once the launches are in the stream: a call that fails before
   // that leaves this end of the exchange as it was
   const uint32_t step = x->step + 1;
-  const int parity = static_cast<int>(step & 1u);
   hb::Scatter sc;
-  sc.world = x->world;
-  sc.rank = x->rank;
-  sc.step = step;
-  sc.done_ctas = x->done_ctas;
-  for (int p = 0; p <= x->world; ++p) sc.qsplit[p] = qsplit_host[p];
-  for (int p = 0; p < x->world; ++p) {
-    uint8_t* win = x->window[p];
-    sc.scores[p] = reinterpret_cast<float*>(win + x->scores_off(parity)) + x->slot_elems() * x->rank;
-    sc.idx[p] = reinterpret_cast<int64_t*>(win + x->idx_off(parity)) + x->slot_elems() * x->rank;
-    sc.flag[p] = reinterpret_cast<uint32_t*>(win) + x->rank;
+  int rc = prepare_scatter(b, x, Q, k, k_prime, qsplit_host, step, &sc, "hb_search_scatter");
+  if (rc != HB_OK) return rc;
+  HB_CHECK_CUDA(cudaSetDevice(b->device));
+  rc = hb::search_impl(b, q_dev, Q, k, k_prime, idx_offset, nullptr, nullptr, out_qnorm_dev, nullptr, 0,
+                       static_cast<cudaStream_t>(stream), &sc, nullptr);
+  if (rc != HB_OK) return rc;
+  x->step = step;
+  x->last_rows = qsplit_host[x->rank + 1] - qsplit_host[x->rank];
+  x->last_k = k;
+  return HB_OK;
+}
+
+int hb_search_finish_scatter(hb_bank_t* bank, hb_exchange_t* xchg, int slot, const float* q_dev, int k,
+                             int64_t idx_offset, const int64_t* qsplit_host, void* stream) {
+  HB_REQUIRE(bank && xchg, "hb_search_finish_scatter: NULL handle");
+  Bank* b = reinterpret_cast<Bank*>(bank);
+  Exchange* x = reinterpret_cast<Exchange*>(xchg);
+  HB_REQUIRE(slot == 0 || slot == 1, "hb_search_finish_scatter: slot=%d not in {0, 1}", slot);
+  HB_REQUIRE(q_dev != nullptr, "hb_search_finish_scatter: NULL pointer");
+  if (!b->pipe[slot].begun) {
+    hb::set_error("hb_search_finish_scatter: pipeline slot %d holds no begun search (call hb_search_begin first)", slot);
+    return HB_ERR_STATE;
   }
-  const int rc = hb::search_impl(b, q_dev, Q, k, k_prime, idx_offset, nullptr, nullptr, out_qnorm_dev, nullptr, 0,
-                                 static_cast<cudaStream_t>(stream), &sc, nullptr);
+  const uint32_t step = x->step + 1;
+  hb::Scatter sc;
+  int rc = prepare_scatter(b, x, b->pipe[slot].Q, k, b->pipe[slot].kp, qsplit_host, step, &sc, "hb_search_finish_scatter");
+  if (rc != HB_OK) return rc;
+  HB_CHECK_CUDA(cudaSetDevice(b->device));
+  rc = hb::search_finish_impl(b, slot, q_dev, k, idx_offset, nullptr, nullptr, &sc, nullptr, static_cast<cudaStream_t>(stream));
   if (rc != HB_OK) return rc;
   x->step = step;
   x->last_rows = qsplit_host[x->rank + 1] - qsplit_host[x->rank];

@@ -67,7 +67,7 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 template <int R>
 __device__ __forceinline__ void
 label_transfer_lanes(const LabelOut& lo, int64_t qi, int64_t out_row, int k, const float (&sc)[R],
-                     const int64_t (&id)[R], float* s_w, int64_t* s_i) {
+                     const int64_t (&id)[R]) {
   const int lane = threadIdx.x & 31;
   // F.normalize clamps the norm at eps = 1e-12 (hbird_eval.py:594)
   const float qn = fmaxf(lo.qnorm[qi], 1e-12f);
@@ -89,37 +89,46 @@ label_transfer_lanes(const LabelOut& lo, int64_t qi, int64_t out_row, int k, con
     sum += ex[r];
   }
   sum = warp_sum(sum);
+  // softmax weight and table row of element e = r*32 + lane stay in this lane's registers and are
+  // broadcast with shuffles below: no shared memory, so these kernels fit beside a resident search
+  // CTA.  A missing neighbour keeps weight 0 and reads row 0 (no branch in the gather loop).
+  float w[R];
+  int64_t row[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    const int e = r * 32 + lane;
-    if (e < k) {
-      const bool ok = logit[r] != -INFINITY;
-      s_w[e] = ok ? ex[r] / sum : 0.f;  // a missing neighbour keeps weight 0 and reads row 0
-      s_i[e] = ok ? id[r] : 0;
-    }
+    const bool ok = logit[r] != -INFINITY;
+    w[r] = ok ? ex[r] / sum : 0.f;
+    row[r] = ok ? id[r] : 0;
   }
-  __syncwarp();
   const float fpp = static_cast<float>(lo.pp);
   const int C = lo.C;
-  for (int c = lane; c < C; c += 32) {
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    const int c = c0 + lane;
+    const bool live = c < C;
     float acc = 0.f;
-#pragma unroll 10
-    for (int j = 0; j < k; ++j) {
-      const float lab = static_cast<float>(__ldg(lo.table + s_i[j] * C + c)) / fpp;
-      acc += s_w[j] * lab;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int n = k - r * 32 < 32 ? k - r * 32 : 32;  // neighbours held in register slot r (warp-uniform)
+#pragma unroll 8
+      for (int j = 0; j < n; ++j) {
+        const float wj = __shfl_sync(0xffffffffu, w[r], j);
+        const int64_t rj = __shfl_sync(0xffffffffu, row[r], j);
+        // soft label = histogram / pixels-per-patch (one_hot(...).mean(3), hbird_eval.py:319-320)
+        const float lab = live ? static_cast<float>(__ldg(lo.table + rj * C + c)) / fpp : 0.f;
+        acc += wj * lab;
+      }
     }
-    lo.out[out_row * C + c] = acc;
+    if (live) lo.out[out_row * C + c] = acc;
   }
-  __syncwarp();
 }
 
-template <int R, bool L2>
+template <int R, bool L2, bool LABEL>
 __device__ __forceinline__ void
 rerank_query(const float* __restrict__ q, const float* __restrict__ bank_f32,
              const __nv_bfloat16* __restrict__ bank_bf16, const uint64_t* __restrict__ cand,
              int n_chunks, int64_t q_pad, int64_t Q, int d, int dpad, int k, int64_t idx_offset,
              float* __restrict__ out_scores, int64_t* __restrict__ out_idx, const Scatter& sc,
-             const LabelOut& lo, float* s_w, int64_t* s_i) {
+             const LabelOut& lo) {
   constexpr int KP = 32 * R;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t qi = static_cast<int64_t>(blockIdx.x) * 4 + warp;
@@ -226,20 +235,21 @@ rerank_query(const float* __restrict__ q, const float* __restrict__ bank_f32,
       oi[e] = fi[r];
     }
   }
-  if (!L2 && lo.table != nullptr) label_transfer_lanes<R>(lo, qi, qi, k, fs, fi, s_w, s_i);
+  if (LABEL && !L2) label_transfer_lanes<R>(lo, qi, qi, k, fs, fi);
 }
 
-template <int R, bool L2>
+// LABEL = with the fused label transfer.  No variant owns shared memory, so one of these CTAs fits
+// on an SM beside a resident search CTA (which takes all but ~2 KB of the shared memory and 82 % of
+// the registers): K2b of one batch runs under the K2 of the next one (hb_search_begin / _finish).
+template <int R, bool L2, bool LABEL>
 __global__ void __launch_bounds__(128)
 rerank_kernel(const float* __restrict__ q, const float* __restrict__ bank_f32,
               const __nv_bfloat16* __restrict__ bank_bf16, const uint64_t* __restrict__ cand,
               int n_chunks, int64_t q_pad, int64_t Q, int d, int dpad, int k, int64_t idx_offset,
               float* __restrict__ out_scores, int64_t* __restrict__ out_idx,
               const __grid_constant__ Scatter sc, const LabelOut lo) {
-  __shared__ float s_w[4][32 * R];
-  __shared__ int64_t s_i[4][32 * R];
-  rerank_query<R, L2>(q, bank_f32, bank_bf16, cand, n_chunks, q_pad, Q, d, dpad, k, idx_offset,
-                      out_scores, out_idx, sc, lo, s_w[threadIdx.x >> 5], s_i[threadIdx.x >> 5]);
+  rerank_query<R, L2, LABEL>(q, bank_f32, bank_bf16, cand, n_chunks, q_pad, Q, d, dpad, k, idx_offset,
+                             out_scores, out_idx, sc, lo);
   if (sc.world) {
     // Fused exchange: every thread's peer stores are ordered before the CTA counts itself done;
     // the last CTA of the grid then raises this rank's arrival flag on every peer.
@@ -263,14 +273,15 @@ int rerank_launch(const Bank* b, const float* q, int64_t Q, int k, int kp,
   const unsigned blocks = static_cast<unsigned>(ceil_div64(Q, 4));
   const Scatter scatter = sc ? *sc : Scatter();
   const LabelOut label = lo ? *lo : LabelOut();
+#define HB_RERANK_ARGS q, b->feat_f32, b->feat_bf16, cand, n_chunks, q_pad, Q, b->d, b->dpad, k, idx_offset, out_scores, out_idx, scatter, label
 #define HB_RERANK(R)                                                                              \
   do {                                                                                            \
     if (b->flags & HB_BANK_L2)                                                                    \
-      rerank_kernel<R, true><<<blocks, 128, 0, st>>>(q, b->feat_f32, b->feat_bf16, cand, n_chunks, q_pad, Q, \
-                                                     b->d, b->dpad, k, idx_offset, out_scores, out_idx, scatter, label); \
+      rerank_kernel<R, true, false><<<blocks, 128, 0, st>>>(HB_RERANK_ARGS);                      \
+    else if (label.table != nullptr)                                                              \
+      rerank_kernel<R, false, true><<<blocks, 128, 0, st>>>(HB_RERANK_ARGS);                      \
     else                                                                                          \
-      rerank_kernel<R, false><<<blocks, 128, 0, st>>>(q, b->feat_f32, b->feat_bf16, cand, n_chunks, q_pad, Q, \
-                                                      b->d, b->dpad, k, idx_offset, out_scores, out_idx, scatter, label); \
+      rerank_kernel<R, false, false><<<blocks, 128, 0, st>>>(HB_RERANK_ARGS);                     \
   } while (0)
   if (kp == 32) HB_RERANK(1);
   else if (kp == 64) HB_RERANK(2);
@@ -280,6 +291,7 @@ int rerank_launch(const Bank* b, const float* q, int64_t Q, int k, int kp,
     return HB_ERR_INVALID;
   }
 #undef HB_RERANK
+#undef HB_RERANK_ARGS
   HB_CHECK_CUDA(cudaGetLastError());
   return HB_OK;
 }
@@ -289,8 +301,7 @@ int rerank_launch(const Bank* b, const float* q, int64_t Q, int k, int kp,
 template <int R>
 __device__ __forceinline__ void
 merge_query(const float* ss, const int64_t* si, int G, int64_t slot_stride, int64_t qi, int k,
-            float* __restrict__ out_scores, int64_t* __restrict__ out_idx, const LabelOut& lo,
-            float* s_w, int64_t* s_i) {
+            float* __restrict__ out_scores, int64_t* __restrict__ out_idx, const LabelOut& lo) {
   // keys here carry a 64-bit index, so sort (ordered score, then index) pairs held as two words
   const int lane = threadIdx.x & 31;
   // candidate slots: position in the gathered (G, k) list, encoded as g*k + j in the low word
@@ -339,7 +350,7 @@ merge_query(const float* ss, const int64_t* si, int G, int64_t slot_stride, int6
       }
     }
   }
-  if (lo.table != nullptr) label_transfer_lanes<R>(lo, qi, qi, k, fs, fi, s_w, s_i);
+  if (lo.table != nullptr) label_transfer_lanes<R>(lo, qi, qi, k, fs, fi);
 }
 
 template <int R>
@@ -347,11 +358,9 @@ __global__ void __launch_bounds__(128)
 merge_topk_kernel(const float* __restrict__ ss, const int64_t* __restrict__ si, int G, int64_t Q,
                   int k, float* __restrict__ out_scores, int64_t* __restrict__ out_idx,
                   const LabelOut lo) {
-  __shared__ float s_w[4][32 * R];
-  __shared__ int64_t s_i[4][32 * R];
   const int64_t qi = static_cast<int64_t>(blockIdx.x) * 4 + (threadIdx.x >> 5);
   if (qi >= Q) return;
-  merge_query<R>(ss, si, G, Q * k, qi, k, out_scores, out_idx, lo, s_w[threadIdx.x >> 5], s_i[threadIdx.x >> 5]);
+  merge_query<R>(ss, si, G, Q * k, qi, k, out_scores, out_idx, lo);
 }
 
 // K3x: the receiving half of the fused exchange.  Waits until every source rank has published
@@ -364,8 +373,6 @@ merge_window_kernel(const float* ss, const int64_t* si, const uint32_t* flags, u
                     int64_t slot_stride, int64_t rows, int k, unsigned long long timeout_ns,
                     unsigned int* timeout_flag, float* __restrict__ out_scores,
                     int64_t* __restrict__ out_idx, const LabelOut lo) {
-  __shared__ float s_w[4][32 * R];
-  __shared__ int64_t s_i[4][32 * R];
   if (threadIdx.x < G) {
     unsigned long long t0 = 0;
     // flags count exchanges; a peer may already be one step ahead (its data for that step went
@@ -385,7 +392,7 @@ merge_window_kernel(const float* ss, const int64_t* si, const uint32_t* flags, u
   __syncthreads();
   const int64_t qi = static_cast<int64_t>(blockIdx.x) * 4 + (threadIdx.x >> 5);
   if (qi >= rows) return;
-  merge_query<R>(ss, si, G, slot_stride, qi, k, out_scores, out_idx, lo, s_w[threadIdx.x >> 5], s_i[threadIdx.x >> 5]);
+  merge_query<R>(ss, si, G, slot_stride, qi, k, out_scores, out_idx, lo);
 }
 
 int merge_window_launch(const Exchange* x, uint32_t step, int64_t rows, int k, float* out_scores,

@@ -645,9 +645,19 @@ static int dispatch_search(const Bank* b, int cg, int kp, const CUtensorMap& tma
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_t idx_offset,
-                float* out_scores, int64_t* out_idx, float* out_qnorm, float* dump, int cg_override,
-                cudaStream_t st, const Scatter* sc, const LabelOut* lo) {
+// Cross-stream slot hand-over uses events recorded outside of any capture; inside a CUDA-graph capture
+// the whole search sits on the captured stream and needs (and may use) none of them.
+static bool stream_is_capturing(cudaStream_t st) {
+  cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &status) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return false;
+  }
+  return status != cudaStreamCaptureStatusNone;
+}
+
+int search_begin_impl(Bank* b, const float* q, int64_t Q, int kp, int slot, float* out_qnorm, float* dump,
+                      int cg_override, cudaStream_t st) {
   // measured on B200 (profiles/): CTA pairs (cta_group::2: half the B-operand shared-memory traffic
   // per SM) win at every bank size and feature dim; cta_group 1 stays selectable
   int cg = cg_override ? cg_override : (b->cfg_cta_group ? b->cfg_cta_group : 2);
@@ -657,14 +667,11 @@ int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_t idx_o
   if (b->rows <= kSmallBankRows && kp < 128 && dump == nullptr) kp = 128;
   const SearchPlan plan = plan_search(b->rows, Q, cg, b->num_sms, b->cfg_max_chunks);
   const int64_t q_pad = static_cast<int64_t>(plan.n_qblocks) * BM * cg;
+  PipeSlot& ps = b->pipe[slot];
+  // the slot's buffers may still be read by the finish of the search that used it last
+  const bool capturing = stream_is_capturing(st);
+  if (ps.done != nullptr && !capturing) HB_CHECK_CUDA(cudaStreamWaitEvent(st, ps.done, 0));
 
-  // scratch: bf16 queries | norms | candidate keys
-  const size_t off_q = 0;
-  const size_t off_norm = align_up(off_q + sizeof(__nv_bfloat16) * static_cast<size_t>(Q) * b->dpad, 256);
-  const size_t off_cand = align_up(off_norm + sizeof(float) * static_cast<size_t>(Q), 256);
-  // threshold board: 2 planes x (2 lists per chunk) x padded queries
-  const size_t off_board = align_up(off_cand + sizeof(uint64_t) * static_cast<size_t>(plan.n_chunks) * q_pad * kp, 256);
-  const size_t board_bytes = sizeof(uint32_t) * 4 * static_cast<size_t>(plan.n_chunks) * q_pad;
   int n_units_used = 1;
   const int variant = dump ? 1 : (b->cfg_ablate ? 2 + b->cfg_ablate : (b->cfg_stats ? 2 : 0));
   int& cached_fit = b->fit_cache[cg - 1][kp == 128 ? 2 : (kp == 64 ? 1 : 0)][variant];
@@ -673,8 +680,6 @@ int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_t idx_o
     n_units_used = std::min(want_units, cached_fit);
   } else {
     SearchParams probe_p{};
-    probe_p.n_qblocks = plan.n_qblocks;
-    probe_p.n_chunks = plan.n_chunks;
     probe_p.dump = dump;
     probe_p.stats = b->cfg_stats;
     probe_p.ablate = b->cfg_ablate;
@@ -686,18 +691,36 @@ int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_t idx_o
     if (rc0 != HB_OK) return rc0;
     n_units_used = std::min(want_units, cached_fit);
   }
+  // Scratch.  Shared by every search (used by prep + K2 only, which run one after the other on the
+  // begin stream): bf16 queries | threshold board (2 planes x 2 lists per chunk x padded queries) |
+  // pacing counters.  Per pipeline slot, in a block of its own (read by the slot's finish, possibly on
+  // another stream while the next begin already runs): norms | candidate keys.
   const int n_rounds = (plan.n_qblocks * plan.n_chunks + n_units_used - 1) / n_units_used;
   const int pace_groups = (plan.n_tiles / plan.n_chunks + 1) / kPaceTiles + 2;
+  const size_t off_q = 0;
+  const size_t off_board = align_up(off_q + sizeof(__nv_bfloat16) * static_cast<size_t>(Q) * b->dpad, 256);
+  const size_t board_bytes = sizeof(uint32_t) * 4 * static_cast<size_t>(plan.n_chunks) * q_pad;
   const size_t off_pace = align_up(off_board + board_bytes, 256);
-  const size_t total = off_pace + sizeof(uint32_t) * static_cast<size_t>(n_rounds) * pace_groups;
+  const size_t total = align_up(off_pace + sizeof(uint32_t) * static_cast<size_t>(n_rounds) * pace_groups, 256);
   int rc = ensure_workspace(b, total, st);
   if (rc != HB_OK) return rc;
+  const size_t norm_bytes = align_up(sizeof(float) * static_cast<size_t>(Q), 256);
+  const size_t slot_bytes = norm_bytes + align_up(sizeof(uint64_t) * static_cast<size_t>(plan.n_chunks) * q_pad * kp, 256);
+  if (slot_bytes > ps.buf_bytes) {
+    // stream-ordered: `st` already waits for the slot's last finish (ps.done above)
+    if (ps.buf) HB_CHECK_CUDA(cudaFreeAsync(ps.buf, st));
+    ps.buf = nullptr;
+    ps.buf_bytes = 0;
+    HB_CHECK_CUDA(cudaMallocAsync(&ps.buf, slot_bytes + slot_bytes / 4, st));
+    ps.buf_bytes = slot_bytes + slot_bytes / 4;
+  }
   uint8_t* ws = static_cast<uint8_t*>(b->ws);
   __nv_bfloat16* q_bf16 = reinterpret_cast<__nv_bfloat16*>(ws + off_q);
-  float* qnorm = out_qnorm ? out_qnorm : reinterpret_cast<float*>(ws + off_norm);
-  uint64_t* cand = reinterpret_cast<uint64_t*>(ws + off_cand);
   uint32_t* board = reinterpret_cast<uint32_t*>(ws + off_board);
   uint32_t* pace = reinterpret_cast<uint32_t*>(ws + off_pace);
+  uint8_t* slot_base = static_cast<uint8_t*>(ps.buf);
+  float* qnorm = out_qnorm ? out_qnorm : reinterpret_cast<float*>(slot_base);
+  uint64_t* cand = reinterpret_cast<uint64_t*>(slot_base + norm_bytes);
   // board and pacing counters are contiguous: one memset
   HB_CHECK_CUDA(cudaMemsetAsync(board, 0, total - off_board, st));
 
@@ -726,28 +749,59 @@ int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_t idx_o
   p.stats = b->cfg_stats;
   p.prefetch_tiles = b->cfg_prefetch_tiles >= 0 ? b->cfg_prefetch_tiles : (cg == 2 ? 4 : 0);
   p.ablate = b->cfg_ablate;
-  const int slot = b->timing_count & 63;
-  if (b->timing) HB_CHECK_CUDA(cudaEventRecord(b->ev_begin[slot], st));
+  const int tslot = b->timing_count & 63;
+  if (b->timing) HB_CHECK_CUDA(cudaEventRecord(b->ev_begin[tslot], st));
   rc = dispatch_search(b, cg, kp, tmap_q, p, st, nullptr, n_units_used);
   if (rc != HB_OK) return rc;
+  ps.timing_slot = -1;
   if (b->timing) {
-    HB_CHECK_CUDA(cudaEventRecord(b->ev_end[slot], st));
+    HB_CHECK_CUDA(cudaEventRecord(b->ev_end[tslot], st));
+    ps.timing_slot = tslot;
     b->timing_count++;
   }
   b->last_launches++;
-  if (dump != nullptr) return HB_OK;  // validation call: raw scores only
+  ps.begun = dump == nullptr;
+  ps.kp = kp;
+  ps.n_chunks = plan.n_chunks;
+  ps.Q = Q;
+  ps.q_pad = q_pad;
+  ps.cand = cand;
+  ps.qnorm = qnorm;
+  return HB_OK;
+}
 
+int search_finish_impl(Bank* b, int slot, const float* q, int k, int64_t idx_offset, float* out_scores,
+                       int64_t* out_idx, const Scatter* sc, const LabelOut* lo, cudaStream_t st) {
+  PipeSlot& ps = b->pipe[slot];
+  if (!ps.begun) {
+    set_error("hb_search_finish: pipeline slot %d holds no begun search (call hb_search_begin first)", slot);
+    return HB_ERR_STATE;
+  }
   LabelOut label;
   if (lo != nullptr) {
     label = *lo;
-    label.qnorm = qnorm;
+    label.qnorm = ps.qnorm;
   }
-  rc = rerank_launch(b, q, Q, k, kp, plan.n_chunks, q_pad, cand, idx_offset, out_scores, out_idx, sc,
-                     lo ? &label : nullptr, st);
+  if (ps.timing_slot >= 0) HB_CHECK_CUDA(cudaEventRecord(b->ev_rerank0[ps.timing_slot], st));
+  int rc = rerank_launch(b, q, ps.Q, k, ps.kp, ps.n_chunks, ps.q_pad, ps.cand, idx_offset, out_scores, out_idx, sc,
+                         lo ? &label : nullptr, st);
   if (rc != HB_OK) return rc;
-  if (b->timing) HB_CHECK_CUDA(cudaEventRecord(b->ev_rerank[slot], st));
+  if (ps.timing_slot >= 0) HB_CHECK_CUDA(cudaEventRecord(b->ev_rerank[ps.timing_slot], st));
+  if (!stream_is_capturing(st)) {
+    if (ps.done == nullptr) HB_CHECK_CUDA(cudaEventCreateWithFlags(&ps.done, cudaEventDisableTiming));
+    HB_CHECK_CUDA(cudaEventRecord(ps.done, st));
+  }
+  ps.begun = false;
   b->last_launches++;
   return HB_OK;
+}
+
+int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_t idx_offset,
+                float* out_scores, int64_t* out_idx, float* out_qnorm, float* dump, int cg_override,
+                cudaStream_t st, const Scatter* sc, const LabelOut* lo) {
+  int rc = search_begin_impl(b, q, Q, kp, 0, out_qnorm, dump, cg_override, st);
+  if (rc != HB_OK || dump != nullptr) return rc;  // validation call: raw scores only
+  return search_finish_impl(b, 0, q, k, idx_offset, out_scores, out_idx, sc, lo, st);
 }
 
 }  // namespace hb
@@ -815,6 +869,47 @@ int hb_search_transfer(hb_bank_t* bank, const uint16_t* label_table_dev, int64_t
                          nullptr, 0, static_cast<cudaStream_t>(stream), nullptr, &lo);
 }
 
+int hb_search_begin(hb_bank_t* bank, const float* q_dev, int64_t Q, int k_prime, int slot, float* out_qnorm_dev,
+                    void* stream) {
+  HB_REQUIRE(bank != nullptr, "hb_search_begin: bank is NULL");
+  Bank* b = reinterpret_cast<Bank*>(bank);
+  if (!b->finalized) {
+    hb::set_error("hb_search_begin: bank not finalized (call hb_bank_finalize first)");
+    return HB_ERR_STATE;
+  }
+  HB_REQUIRE(slot == 0 || slot == 1, "hb_search_begin: slot=%d not in {0, 1}", slot);
+  HB_REQUIRE(Q >= 1 && Q < (int64_t(1) << 31), "hb_search_begin: Q=%lld out of range", (long long)Q);
+  HB_REQUIRE(k_prime == 32 || k_prime == 64 || k_prime == 128, "hb_search_begin: k_prime=%d not in {32, 64, 128}", k_prime);
+  HB_REQUIRE(q_dev != nullptr, "hb_search_begin: q_dev is NULL");
+  HB_REQUIRE(b->rows >= 1, "hb_search_begin: the bank is empty");
+  if (b->pipe[slot].begun) {
+    hb::set_error("hb_search_begin: pipeline slot %d already holds a begun search (finish it first)", slot);
+    return HB_ERR_STATE;
+  }
+  HB_CHECK_CUDA(cudaSetDevice(b->device));
+  return hb::search_begin_impl(b, q_dev, Q, k_prime, slot, out_qnorm_dev, nullptr, 0, static_cast<cudaStream_t>(stream));
+}
+
+int hb_search_finish(hb_bank_t* bank, int slot, const float* q_dev, int k, int64_t idx_offset,
+                     const uint16_t* label_table_dev, int64_t table_rows, float beta, float* out_scores_dev,
+                     int64_t* out_idx_dev, float* out_label_hat_dev, void* stream) {
+  HB_REQUIRE(bank != nullptr, "hb_search_finish: bank is NULL");
+  Bank* b = reinterpret_cast<Bank*>(bank);
+  HB_REQUIRE(slot == 0 || slot == 1, "hb_search_finish: slot=%d not in {0, 1}", slot);
+  HB_REQUIRE(q_dev != nullptr, "hb_search_finish: q_dev is NULL");
+  HB_REQUIRE((out_scores_dev == nullptr) == (out_idx_dev == nullptr), "hb_search_finish: give both or neither of out_scores/out_idx");
+  HB_REQUIRE(out_scores_dev != nullptr || out_label_hat_dev != nullptr, "hb_search_finish: no output requested");
+  HB_REQUIRE(k >= 1 && (!b->pipe[slot].begun || k <= b->pipe[slot].kp), "hb_search_finish: k=%d exceeds the k_prime of the begun search", k);
+  hb::LabelOut lo;
+  if (out_label_hat_dev != nullptr) {
+    int rc = fill_label_out(b, label_table_dev, table_rows, beta, out_label_hat_dev, &lo, "hb_search_finish");
+    if (rc != HB_OK) return rc;
+  }
+  HB_CHECK_CUDA(cudaSetDevice(b->device));
+  return hb::search_finish_impl(b, slot, q_dev, k, idx_offset, out_scores_dev, out_idx_dev, nullptr,
+                                out_label_hat_dev ? &lo : nullptr, static_cast<cudaStream_t>(stream));
+}
+
 int hb_eval_step(hb_bank_t* bank, const uint16_t* label_table_dev, int64_t table_rows, const float* q_dev,
                  int B, int S, int H, int W, const float* y_dev, int k, int k_prime, int64_t idx_offset,
                  float beta, int ignore_index, float* label_hat_dev, int64_t* conf_dev,
@@ -876,6 +971,7 @@ int hb_search_timing(hb_bank_t* bank, int enable) {
     for (int i = 0; i < 64; ++i) {
       HB_CHECK_CUDA(cudaEventCreate(&b->ev_begin[i]));
       HB_CHECK_CUDA(cudaEventCreate(&b->ev_end[i]));
+      HB_CHECK_CUDA(cudaEventCreate(&b->ev_rerank0[i]));
       HB_CHECK_CUDA(cudaEventCreate(&b->ev_rerank[i]));
     }
   }
@@ -912,7 +1008,7 @@ int hb_search_rerank_time(hb_bank_t* bank, float* mean_ms_out, int* count_out) {
     float ms = 0.f;
     // a search that stopped after K2 (validation dump) never recorded this slot's event: skip it
     if (cudaEventSynchronize(b->ev_rerank[i]) != cudaSuccess ||
-        cudaEventElapsedTime(&ms, b->ev_end[i], b->ev_rerank[i]) != cudaSuccess) {
+        cudaEventElapsedTime(&ms, b->ev_rerank0[i], b->ev_rerank[i]) != cudaSuccess) {
       (void)cudaGetLastError();
       continue;
     }

@@ -45,6 +45,9 @@ _SIGNATURES = [
     ("hb_search", c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     ("hb_search_transfer", c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int64, c_float,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    ("hb_search_begin", c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    ("hb_search_finish", c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_int64, c_float, c_void_p, c_void_p,
+                                 c_void_p, c_void_p]),
     ("hb_eval_step", c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
                              c_int64, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     ("hb_search_config", c_int, [c_void_p, c_int, c_int]),
@@ -67,6 +70,7 @@ _SIGNATURES = [
     ("hb_exchange_connect_local", c_int, [c_void_p, POINTER(c_void_p), c_int]),
     ("hb_exchange_disconnect", c_int, [c_void_p]),
     ("hb_search_scatter", c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int64, POINTER(c_int64), c_void_p, c_void_p]),
+    ("hb_search_finish_scatter", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int64, POINTER(c_int64), c_void_p]),
     ("hb_exchange_merge", c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     ("hb_exchange_merge_transfer", c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p,
                                            c_void_p, c_void_p]),

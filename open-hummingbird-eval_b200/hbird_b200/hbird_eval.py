@@ -31,6 +31,8 @@ import torch
 from . import distributed as hdist
 from . import ops
 from .models import FeatureExtractorSimple
+from . import pipeline as hpipe
+from .pipeline import EvalPipeline
 from .registry import NN_BACKENDS, create_nn_backend
 from .utils.eval_metrics import PredsmIoU
 
@@ -479,12 +481,10 @@ class HbirdEvaluation:
         feats, _ = self.feature_extractor.forward_features(x)
         return feats.to(torch.float32).contiguous()
 
-    def _sharded_batch(self, x_slice: torch.Tensor, B: int, b0: int, b1: int, want_neighbours: bool):
-        """Row-sharded bank: (label_hat, scores, idx, q) for the image slice [b0, b1) of the batch this
-        rank post-processes.  Features are extracted once across the ranks: each rank runs the
-        extractor on its slice (x_slice, already on the device) and the query rows are all-gathered
-        (every shard must see every query).  Then K2/K2b per shard -> exchange -> merge with the
-        label transfer fused in."""
+    def _gathered_queries(self, x_slice: torch.Tensor, B: int, b0: int, b1: int) -> torch.Tensor:
+        """Row-sharded bank: features are extracted once across the ranks — each rank runs the extractor
+        on its image slice [b0, b1) (x_slice, already on the device) and the query rows of the whole
+        batch are all-gathered, because every shard must see every query."""
         img_counts = [hdist.split_range(B, self.world, r) for r in range(self.world)]
         if b1 > b0:
             mine = self._features(x_slice)
@@ -492,7 +492,16 @@ class HbirdEvaluation:
         else:
             N, d = self.feature_extractor.eval_spatial_resolution ** 2, self.feature_extractor.d_model
             mine = torch.empty((0, N, d), dtype=torch.float32, device=self.device)
-        q = hdist.all_gather_rows(mine.view(-1, d), [(e - a) * N for a, e in img_counts])
+        return hdist.all_gather_rows(mine.view(-1, d), [(e - a) * N for a, e in img_counts])
+
+    def _sharded_batch(self, x_slice: torch.Tensor, B: int, b0: int, b1: int, want_neighbours: bool):
+        """Row-sharded bank: (label_hat, scores, idx, q) for the image slice [b0, b1) of the batch this
+        rank post-processes.  Features are extracted once across the ranks: each rank runs the
+        extractor on its slice (x_slice, already on the device) and the query rows are all-gathered
+        (every shard must see every query).  Then K2/K2b per shard -> exchange -> merge with the
+        label transfer fused in."""
+        q = self._gathered_queries(x_slice, B, b0, b1)
+        N = q.shape[0] // B
         k, kp = self.n_neighbours, self.k_prime
         pp = self.bank.patch_pixels
         if self._exchange_for(B * N, B) is not None:
@@ -517,9 +526,29 @@ class HbirdEvaluation:
         conf = metric.confusion_buffer()
         details = []  # per batch: (batch number, knns, knns_labels, knns_ca_labels) CPU tensors
         replicas = self.world > 1 and not self.idx_shard
+        # Banks (or shards) of up to ~2 M rows per GPU go through a two-stream pipeline (pipeline.py):
+        # the tensor-core search of batch i+1 runs over the HBM-bound post-processing of batch i.
+        # Larger ones, and return_knn_details (every batch's neighbours go to the host), take the
+        # one-call-per-batch path below.
+        pipe = None
+        if self.nn_method == "b200" and not return_knn_details and hpipe.worthwhile(self.bank):
+            if getattr(self, "_pipe_streams", None) is None:
+                self._pipe_streams = hpipe.make_streams(self.device)
+            pipe = EvalPipeline(self.bank, self.label_table, S, conf, ignore_index, self.n_neighbours, self.k_prime, BETA,
+                                self.idx_offset, self.world if self.idx_shard else 1, self.rank, None,
+                                streams=self._pipe_streams)
         for step, B, b0, b1, x, ys, copied in self._prefetched(val_loader):
             torch.cuda.current_stream(self.device).wait_event(copied)
             h, w = int(ys.shape[-2]), int(ys.shape[-1])  # the mask has the input's spatial size (:219,:240)
+            if pipe is not None:
+                if self.idx_shard:
+                    q = self._gathered_queries(x, B, b0, b1)
+                    pipe.xchg = self._exchange_for(q.shape[0], B)
+                else:
+                    feats = self._features(x)
+                    q = feats.view(-1, feats.shape[2])
+                pipe.submit(q, ys, B)
+                continue
             if self.idx_shard:
                 lh, s, i, q = self._sharded_batch(x, B, b0, b1, return_knn_details)
                 if b1 > b0:
@@ -542,6 +571,8 @@ class HbirdEvaluation:
                 k = self.n_neighbours
                 kf, kl, lhd = self._gather_details(i, lh, B, N)
                 details.append((step, kf.view(-1, N, k, d).cpu(), kl.view(-1, N, k, C).cpu(), lhd.view(-1, N, C).cpu()))
+        if pipe is not None:
+            pipe.flush()
         jac, tp, fp, fn, _, _ = metric.compute(is_global_zero=True, sync_distributed=self.world > 1,
                                                return_reordered=False)
         self.last_confusion = metric.confusion_matrix()

@@ -168,6 +168,36 @@ class MemoryBank:
                                      stream_ptr(q.device)))
         return lh, qn, scores, idx
 
+    def search_begin(self, q: torch.Tensor, k_prime: int = 64, slot: int = 0) -> torch.Tensor:
+        """First half of a search on the CURRENT stream: query prep + K2 (tensor-core pass) into pipeline
+        slot 0/1.  Returns the (Q,) query norms.  Pair with search_finish / ShardExchange.finish_scatter,
+        which may run on another stream (ordered after this one by an event) while the next batch's
+        search_begin already executes — see hbird_b200.pipeline.EvalPipeline."""
+        q = _require_cuda(q, "q", torch.float32)
+        if q.dim() != 2 or q.shape[1] != self.d:
+            raise ValueError(f"queries must be (Q, {self.d}), got {tuple(q.shape)}")
+        qn = torch.empty((q.shape[0],), dtype=torch.float32, device=q.device)
+        check(lib.hb_search_begin(self._h, ptr(q), q.shape[0], int(k_prime), int(slot), ptr(qn), stream_ptr(q.device)))
+        return qn
+
+    def search_finish(self, slot: int, q: torch.Tensor, k: int = 30, idx_offset: int = 0, beta: float = 0.02,
+                      label_table: Optional[torch.Tensor] = None, want_label_hat: bool = True,
+                      want_neighbours: bool = False):
+        """Second half on the CURRENT stream: K2b (+ fused K4a) of the search begun in `slot`.
+        Returns (label_hat or None, scores or None, idx or None)."""
+        q = _require_cuda(q, "q", torch.float32)
+        Q = q.shape[0]
+        table_rows = 0
+        if label_table is not None:
+            label_table = _require_cuda(label_table, "label_table", torch.int16)
+            table_rows = label_table.shape[0]
+        lh = torch.empty((Q, self.num_classes), dtype=torch.float32, device=q.device) if want_label_hat else None
+        scores = torch.empty((Q, k), dtype=torch.float32, device=q.device) if want_neighbours else None
+        idx = torch.empty((Q, k), dtype=torch.int64, device=q.device) if want_neighbours else None
+        check(lib.hb_search_finish(self._h, int(slot), ptr(q), int(k), int(idx_offset), ptr(label_table), table_rows,
+                                   float(beta), ptr(scores), ptr(idx), ptr(lh), stream_ptr(q.device)))
+        return lh, scores, idx
+
     def eval_step(self, q: torch.Tensor, y: torch.Tensor, S: int, conf: torch.Tensor, ignore_index: Optional[int],
                   k: int = 30, k_prime: int = 64, beta: float = 0.02, label_table: Optional[torch.Tensor] = None,
                   idx_offset: int = 0, label_hat: Optional[torch.Tensor] = None, pred: Optional[torch.Tensor] = None,
@@ -327,6 +357,19 @@ class ShardExchange:
                                     ptr(qn), stream_ptr(q.device)))
         self._k = int(k)
         return qn
+
+    def finish_scatter(self, bank: "MemoryBank", slot: int, q: torch.Tensor, qsplit, k: int = 30, idx_offset: int = 0) -> None:
+        """Second half of search_scatter for a search begun with MemoryBank.search_begin(slot): K2b with the
+        scatter into the owner ranks' windows, on the CURRENT stream."""
+        import ctypes
+
+        q = _require_cuda(q, "q", torch.float32)
+        if len(qsplit) != self.world + 1:
+            raise ValueError(f"qsplit needs world+1 = {self.world + 1} entries")
+        arr = (ctypes.c_int64 * (self.world + 1))(*[int(v) for v in qsplit])
+        check(lib.hb_search_finish_scatter(bank._h, self._h, int(slot), ptr(q), int(k), int(idx_offset), arr,
+                                           stream_ptr(q.device)))
+        self._k = int(k)
 
     def merge_transfer(self, label_table: torch.Tensor, patch_pixels: int, qnorm_slice: torch.Tensor,
                        beta: float = 0.02, return_neighbours: bool = False):

@@ -395,3 +395,60 @@ def test_bench_synthetic_inputs_are_bit_identical_on_cpu_and_gpu():
         fg, mg = syn.images(w, 37, 3, torch.device(DEV), stream=1)
         assert torch.equal(fg.cpu(), fc) and torch.equal(mg.cpu(), mc)
         assert torch.equal(syn.prototypes(w, torch.device(DEV)).cpu(), syn.prototypes(w, torch.device("cpu")))
+
+
+# ------------------------------------------------------------------ split search + two-stream pipeline
+def test_split_search_two_slots_equal_the_one_call_search():
+    g = torch.Generator().manual_seed(41)
+    rows = torch.randn((60000, 128), generator=g).to(DEV)
+    bank = bank_from_rows(rows)
+    qa, qb = (torch.randn((700, 128), generator=g) * 2).to(DEV), (torch.randn((333, 128), generator=g) * 2).to(DEV)
+    sa, ia, na = bank.search(qa, 30, 64)
+    sb, ib, nb = bank.search(qb, 30, 64)
+    # both slots in flight at once, finished out of order, on another stream
+    other = torch.cuda.Stream()
+    n0 = bank.search_begin(qa, 64, 0)
+    n1 = bank.search_begin(qb, 64, 1)
+    done = torch.cuda.Event()
+    done.record()
+    other.wait_event(done)
+    with torch.cuda.stream(other):
+        _, s1, i1 = bank.search_finish(1, qb, 30, want_label_hat=False, want_neighbours=True)
+        lh0, s0, i0 = bank.search_finish(0, qa, 30, want_neighbours=True)
+    other.synchronize()
+    assert torch.equal(s0, sa) and torch.equal(i0, ia) and torch.equal(n0, na)
+    assert torch.equal(s1, sb) and torch.equal(i1, ib) and torch.equal(n1, nb)
+    assert torch.equal(lh0, ops.label_transfer(bank.label_table(), 1, sa, ia, na, 0.02))
+    with pytest.raises(RuntimeError, match="no begun search"):
+        bank.search_finish(0, qa, 30)
+    bank.search_begin(qa, 64, 0)
+    with pytest.raises(RuntimeError, match="already holds"):
+        bank.search_begin(qb, 64, 0)
+    with pytest.raises(ValueError, match="slot"):
+        bank.search_begin(qb, 64, 2)
+    bank.search_finish(0, qa, 30)
+    torch.cuda.synchronize()
+    bank.close()
+
+
+def test_pipeline_accumulates_the_same_confusion_matrix_as_one_call_steps(case):
+    """EvalPipeline (K2 of batch i+1 on one stream over the post-processing of batch i on another) is a
+    scheduling change only: bit-identical confusion matrix, over several passes of the validation set."""
+    from hbird_b200.pipeline import EvalPipeline
+
+    cfg, g, data = case
+    bank = build_bank_from_loader(data)
+    C, S = data.C, data.S
+    batches = [(cuda(f.reshape(-1, f.shape[-1])), cuda(y)) for f, y in batches_np(data, data.val_dataloader())] * 4
+    ref = torch.zeros((C, C), dtype=torch.int64, device=DEV)
+    for q, y in batches:
+        bank.eval_step(q, y, S, ref, data.ignore_index)
+    conf = torch.zeros_like(ref)
+    pipe = EvalPipeline(bank, bank.label_table(), S, conf, data.ignore_index, 30, 64, 0.02)
+    for q, y in batches:
+        pipe.submit(q, y, y.shape[0])
+    pipe.flush()
+    torch.cuda.synchronize()
+    assert torch.equal(conf, ref)
+    assert np.abs(conf.cpu().numpy() - 4 * g["conf"]).sum() <= 5e-4 * 4 * g["conf"].sum()
+    bank.close()
