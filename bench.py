@@ -339,6 +339,7 @@ def cpu_sample(O, w, fm, lm, q, y_one, repeats=1):
     t0 = time.perf_counter()
     for _ in range(repeats):
         idx, dist = O.search_exact_ip(q, fm, K_NEIGH)
+        cpu_sample.search_seconds = (time.perf_counter() - t0) if repeats == 1 else None
         lh = O.transfer_labels(q[None], fm, lm, idx, BETA)[0]
         full = np.zeros((1, S * S, C), dtype=np.float32)
         full[0, :min(len(lh), S * S)] = lh[:S * S]
@@ -600,7 +601,8 @@ def reference_arm(args, w, real_stdout):
                    "path": "oracle port of the reference CPU path (exact fp32 IP search + gather + cross-attention + "
                            "bilinear upsample + argmax + bincount), numpy/BLAS",
                    "parallelism": f"host CPU, {threads} threads"},
-        "cpu_baseline": {"value": value, "unit": "patch-queries/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "patch-queries/s", "cores": threads, "kind": "port", "sample": sample,
+                         "search_only_value": (len(qs) / cpu_sample.search_seconds) if cpu_sample.search_seconds else None},
         "e2e": {"value": value, "unit": "patch-queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -752,6 +754,7 @@ def main():
         _, qs, y_one = sample_queries(w, (q_host_np, y_host_np), n_q)
         dt, _ = cpu_sample(O, w, fm, lm, qs, y_one)
         cpu = {"value": len(qs) / dt, "unit": "patch-queries/s", "cores": threads, "kind": "port",
+               "search_only_value": (len(qs) / cpu_sample.search_seconds) if cpu_sample.search_seconds else None,
                "sample": f"{len(qs)} patch-queries (spread over the first validation batch) against the full {rows:,}-row bank: "
                          f"exact fp32 IP search + gather + cross-attention, plus the pixel stages of one image; "
                          f"{dt:.1f} s of oracle (numpy/BLAS) time"}

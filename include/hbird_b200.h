@@ -267,8 +267,8 @@ int hb_search_scatter(hb_bank_t* bank, hb_exchange_t* xchg, const float* q_dev, 
 int hb_search_finish_scatter(hb_bank_t* bank, hb_exchange_t* xchg, int slot, const float* q_dev, int k,
                              int64_t idx_offset, const int64_t* qsplit_host, void* stream);
 /* Outputs: fp32 / int64 (rows, k) for this rank's slice of the last scatter, sorted descending,
- * global indices; rows = hb_exchange_slice_rows().  A peer that never arrives makes the kernel
- * trap after 10 min instead of hanging the GPU. */
+ * global indices; rows = hb_exchange_slice_rows().  A peer that never arrives makes the kernel give
+ * up after the exchange's timeout (see hb_exchange_status) instead of hanging the GPU. */
 int hb_exchange_merge(hb_exchange_t* xchg, float* out_scores_dev, int64_t* out_idx_dev, void* stream);
 /* hb_exchange_merge with K4a fused into the merging warp: qnorm_slice_dev fp32 (rows,) are the norms
  * of this rank's query slice, out_label_hat_dev fp32 (rows, C); out_scores_dev / out_idx_dev may
@@ -278,6 +278,13 @@ int hb_exchange_merge_transfer(hb_exchange_t* xchg, const uint16_t* label_table_
                                float* out_scores_dev, int64_t* out_idx_dev,
                                float* out_label_hat_dev, void* stream);
 int64_t hb_exchange_slice_rows(const hb_exchange_t* xchg);
+/* Failure handling of the exchange.  A merge kernel waits for its peers at most `timeout_ms` (default
+ * 600 000); when a peer does not arrive it records that rank and returns without writing its outputs
+ * — no trap, the CUDA context stays usable.  hb_exchange_status synchronises `stream` and returns
+ * HB_ERR_STATE (message: which rank, which step) if a merge since the last call timed out, HB_OK
+ * otherwise. */
+int hb_exchange_set_timeout(hb_exchange_t* xchg, int64_t timeout_ms);
+int hb_exchange_status(hb_exchange_t* xchg, void* stream);
 
 /* ---- K4: label transfer ------------------------------------------------------------------
  * Replaces the neighbour gather (hbird_eval.py:611-637) and _cross_attention

@@ -130,6 +130,7 @@ struct Exchange {
   uint8_t* window[kMaxPeers] = {};  // [rank] = own allocation, others = mapped peers
   unsigned int* done_ctas = nullptr;
   unsigned int* timeout_flag = nullptr;
+  unsigned long long timeout_ms = 600000;  // bound of the merge kernel's wait for a peer
   size_t scores_off(int parity) const { return 256 + static_cast<size_t>(parity) * buffer_bytes(); }
   size_t idx_off(int parity) const { return scores_off(parity) + sizeof(float) * slot_elems() * world; }
   size_t slot_elems() const { return static_cast<size_t>(cap) * kmax; }

@@ -262,6 +262,30 @@ int hb_exchange_merge_transfer(hb_exchange_t* xchg, const uint16_t* label_table_
                                  x->last_rows > 0 ? &lo : nullptr, static_cast<cudaStream_t>(stream));
 }
 
+int hb_exchange_set_timeout(hb_exchange_t* xchg, int64_t timeout_ms) {
+  HB_REQUIRE(xchg != nullptr, "hb_exchange_set_timeout: exchange is NULL");
+  HB_REQUIRE(timeout_ms >= 1, "hb_exchange_set_timeout: timeout_ms=%lld must be positive", (long long)timeout_ms);
+  reinterpret_cast<Exchange*>(xchg)->timeout_ms = static_cast<unsigned long long>(timeout_ms);
+  return HB_OK;
+}
+
+int hb_exchange_status(hb_exchange_t* xchg, void* stream) {
+  HB_REQUIRE(xchg != nullptr, "hb_exchange_status: exchange is NULL");
+  Exchange* x = reinterpret_cast<Exchange*>(xchg);
+  HB_CHECK_CUDA(cudaSetDevice(x->device));
+  unsigned int flag = 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  HB_CHECK_CUDA(cudaMemcpyAsync(&flag, x->timeout_flag, sizeof(flag), cudaMemcpyDeviceToHost, st));
+  HB_CHECK_CUDA(cudaStreamSynchronize(st));
+  if (flag != 0u) {
+    HB_CHECK_CUDA(cudaMemsetAsync(x->timeout_flag, 0, sizeof(flag), st));  // reported once
+    hb::set_error("shard exchange: rank %u did not publish its results within %llu ms (step %u); the merged "
+                  "results of that step were not written", flag & 0x7fffffffu, x->timeout_ms, x->step);
+    return HB_ERR_STATE;
+  }
+  return HB_OK;
+}
+
 int64_t hb_exchange_slice_rows(const hb_exchange_t* xchg) {
   return xchg ? reinterpret_cast<const Exchange*>(xchg)->last_rows : -1;
 }

@@ -363,18 +363,22 @@ merge_topk_kernel(const float* __restrict__ ss, const int64_t* __restrict__ si, 
   merge_query<R>(ss, si, G, Q * k, qi, k, out_scores, out_idx, lo);
 }
 
-// K3x: the receiving half of the fused exchange.  Waits until every source rank has published
-// `step` in this rank's window (the rows were stored by the peers' K2b kernels over NVLink), then
-// merges the G lists of each query of the local slice.  The wait is bounded: after `timeout_ns`
-// the kernel records the missing rank and traps instead of hanging the GPU.
-template <int R>
-__global__ void __launch_bounds__(128)
-merge_window_kernel(const float* ss, const int64_t* si, const uint32_t* flags, uint32_t step, int G,
-                    int64_t slot_stride, int64_t rows, int k, unsigned long long timeout_ns,
-                    unsigned int* timeout_flag, float* __restrict__ out_scores,
-                    int64_t* __restrict__ out_idx, const LabelOut lo) {
+// K3x: the receiving half of the fused exchange, in two launches.
+// exchange_wait_kernel — ONE warp polls the G step flags of this rank's window until every source rank
+// has published `step` (the rows were stored by the peers' K2b kernels over NVLink; acquire at system
+// scope).  A single polling warp instead of a wait at the head of every merge CTA: the merge usually
+// runs under the next batch's search (pipeline.py), and hundreds of resident CTAs polling peer-visible
+// memory slowed that search by several per cent.  The wait is bounded: after `timeout_ns` the kernel
+// records which rank is missing in `timeout_flag` — no trap, the context stays usable;
+// hb_exchange_status() turns the flag into an error on the host.
+// merge_window_kernel — stream-ordered after it: merges the G lists of each query of the local slice
+// (+ fused label transfer); writes nothing if the wait gave up.
+__global__ void __launch_bounds__(32)
+exchange_wait_kernel(const uint32_t* flags, uint32_t step, int G, unsigned long long timeout_ns,
+                     unsigned int* timeout_flag) {
   if (threadIdx.x < G) {
     unsigned long long t0 = 0;
+    unsigned backoff = 64;
     // flags count exchanges; a peer may already be one step ahead (its data for that step went
     // to the other buffer), hence >= on the wrapped difference
     while (static_cast<int32_t>(ld_acquire_sys(flags + threadIdx.x) - step) < 0) {
@@ -382,14 +386,22 @@ merge_window_kernel(const float* ss, const int64_t* si, const uint32_t* flags, u
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
       if (t0 == 0) t0 = now;
       if (now - t0 > timeout_ns) {
-        atomicExch(timeout_flag, 0x80000000u | threadIdx.x);
-        __threadfence_system();
-        __trap();
+        atomicCAS(timeout_flag, 0u, 0x80000000u | threadIdx.x);  // first missing rank wins
+        break;
       }
-      __nanosleep(200);
+      __nanosleep(backoff);
+      if (backoff < 2048) backoff *= 2;
     }
   }
-  __syncthreads();
+  __threadfence_system();
+}
+
+template <int R>
+__global__ void __launch_bounds__(128)
+merge_window_kernel(const float* ss, const int64_t* si, int G, int64_t slot_stride, int64_t rows, int k,
+                    const unsigned int* timeout_flag, float* __restrict__ out_scores,
+                    int64_t* __restrict__ out_idx, const LabelOut lo) {
+  if (__ldcg(timeout_flag) != 0u) return;  // a peer never arrived: leave the outputs alone
   const int64_t qi = static_cast<int64_t>(blockIdx.x) * 4 + (threadIdx.x >> 5);
   if (qi >= rows) return;
   merge_query<R>(ss, si, G, slot_stride, qi, k, out_scores, out_idx, lo);
@@ -403,14 +415,16 @@ int merge_window_launch(const Exchange* x, uint32_t step, int64_t rows, int k, f
   const float* ss = reinterpret_cast<const float*>(win + x->scores_off(parity));
   const int64_t* si = reinterpret_cast<const int64_t*>(win + x->idx_off(parity));
   const uint32_t* flags = reinterpret_cast<const uint32_t*>(win);
-  // at least one CTA even for an empty slice: the wait keeps the ranks within one step of each
-  // other, which is what makes two window buffers enough
-  const unsigned blocks = static_cast<unsigned>(rows > 0 ? ceil_div64(rows, 4) : 1);
-  const unsigned long long timeout_ns = 600ull * 1000000000ull;  // hang protection only
+  const unsigned long long timeout_ns = x->timeout_ms * 1000000ull;  // hang protection only (default 10 min)
   const int64_t stride = static_cast<int64_t>(x->slot_elems());
+  // the wait runs even for an empty slice: it keeps the ranks within one step of each other, which is
+  // what makes two window buffers enough
+  exchange_wait_kernel<<<1, 32, 0, st>>>(flags, step, x->world, timeout_ns, x->timeout_flag);
+  HB_CHECK_CUDA(cudaGetLastError());
+  if (rows <= 0) return HB_OK;
+  const unsigned blocks = static_cast<unsigned>(ceil_div64(rows, 4));
 #define HB_MERGE_WIN(R)                                                                         \
-  merge_window_kernel<R><<<blocks, 128, 0, st>>>(ss, si, flags, step, x->world, stride, rows, k, \
-                                                 timeout_ns, x->timeout_flag, out_scores, out_idx, label)
+  merge_window_kernel<R><<<blocks, 128, 0, st>>>(ss, si, x->world, stride, rows, k, x->timeout_flag, out_scores, out_idx, label)
   if (k <= 32) HB_MERGE_WIN(1);
   else if (k <= 64) HB_MERGE_WIN(2);
   else HB_MERGE_WIN(4);

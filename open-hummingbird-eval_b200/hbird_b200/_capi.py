@@ -75,6 +75,8 @@ _SIGNATURES = [
     ("hb_exchange_merge_transfer", c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p,
                                            c_void_p, c_void_p]),
     ("hb_exchange_slice_rows", c_int64, [c_void_p]),
+    ("hb_exchange_set_timeout", c_int, [c_void_p, c_int64]),
+    ("hb_exchange_status", c_int, [c_void_p, c_void_p]),
     ("hb_label_transfer", c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p]),
     ("hb_upsample_argmax", c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     ("hb_predict_score", c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,

@@ -573,6 +573,8 @@ class HbirdEvaluation:
                 details.append((step, kf.view(-1, N, k, d).cpu(), kl.view(-1, N, k, C).cpu(), lhd.view(-1, N, C).cpu()))
         if pipe is not None:
             pipe.flush()
+        if self.idx_shard and getattr(self, "_xchg", None) is not None:
+            self._xchg.check_status()  # raises if a merge gave up waiting for a peer (results not written)
         jac, tp, fp, fn, _, _ = metric.compute(is_global_zero=True, sync_distributed=self.world > 1,
                                                return_reordered=False)
         self.last_confusion = metric.confusion_matrix()

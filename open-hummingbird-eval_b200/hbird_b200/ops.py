@@ -310,6 +310,15 @@ class ShardExchange:
         except Exception:
             pass
 
+    def set_timeout(self, timeout_ms: int) -> None:
+        """Bound of a merge kernel's wait for its peers (default 10 min)."""
+        check(lib.hb_exchange_set_timeout(self._h, int(timeout_ms)))
+
+    def check_status(self) -> None:
+        """Synchronise the current stream and raise RuntimeError if a merge since the last check gave up
+        waiting for a peer (its outputs were then not written)."""
+        check(lib.hb_exchange_status(self._h, stream_ptr(torch.device("cuda", self.device))))
+
     def disconnect(self) -> None:
         """Unmap the peers' windows (first half of an orderly multi-process teardown)."""
         if self._h.value:

@@ -452,3 +452,29 @@ def test_pipeline_accumulates_the_same_confusion_matrix_as_one_call_steps(case):
     assert torch.equal(conf, ref)
     assert np.abs(conf.cpu().numpy() - 4 * g["conf"]).sum() <= 5e-4 * 4 * g["conf"].sum()
     bank.close()
+
+
+def test_exchange_gives_up_on_a_missing_peer_without_killing_the_context():
+    """Two simulated ranks, only rank 0 scatters: rank 0's merge waits for rank 1 at most the configured
+    time, then returns without writing; check_status names the missing rank; the CUDA context, the bank
+    and the exchange stay usable (round 1 trapped the context after 10 minutes)."""
+    g = torch.Generator().manual_seed(47)
+    rows = torch.randn((9000, 64), generator=g).to(DEV)
+    bank = bank_from_rows(rows)
+    xs = [ops.ShardExchange(r, 2, 64, 30, 0) for r in range(2)]
+    ops.ShardExchange.connect_local(xs)
+    q = (torch.randn((100, 64), generator=g) * 2).to(DEV)
+    xs[0].set_timeout(30)
+    xs[0].search_scatter(bank, q, [0, 50, 100], 30, 64)
+    s, i = xs[0].merge()
+    with pytest.raises(RuntimeError, match="rank 1 did not publish"):
+        xs[0].check_status()
+    xs[0].check_status()  # reported once
+    # the late peer arrives: the same step can still be merged
+    xs[1].search_scatter(bank, q, [0, 50, 100], 30, 64, idx_offset=9000)
+    s0, i0, _ = bank.search(q, 30, 64)  # context and bank are alive
+    assert torch.isfinite(s0).all()
+    with pytest.raises(ValueError, match="positive"):
+        xs[0].set_timeout(0)
+    for o in xs + [bank]:
+        o.close()
