@@ -163,6 +163,10 @@ int hb_search_finish(hb_bank_t* bank, int slot, const float* q_dev, int k, int64
                      float* out_scores_dev, int64_t* out_idx_dev, float* out_label_hat_dev,
                      void* stream);
 
+/* Forget searches that were begun and will not be finished (error recovery of a pipelined caller):
+ * both slots become free again.  Host-side state only; work already in the streams runs to its end. */
+int hb_search_abort(hb_bank_t* bank);
+
 /* One validation batch through the whole path in 4 launches (query prep, K2, K2b+K4a, fused tail):
  * replaces hbird_eval.py:217-252 for a bank that is not row-sharded.  q_dev fp32 (B*S*S, d) raw
  * features; y_dev fp32 (B, H, W) = class id / 255 (loader contract, :219); label_hat_dev fp32

@@ -910,6 +910,14 @@ int hb_search_finish(hb_bank_t* bank, int slot, const float* q_dev, int k, int64
                                 out_label_hat_dev ? &lo : nullptr, static_cast<cudaStream_t>(stream));
 }
 
+int hb_search_abort(hb_bank_t* bank) {
+  HB_REQUIRE(bank != nullptr, "hb_search_abort: bank is NULL");
+  Bank* b = reinterpret_cast<Bank*>(bank);
+  b->pipe[0].begun = false;
+  b->pipe[1].begun = false;
+  return HB_OK;
+}
+
 int hb_eval_step(hb_bank_t* bank, const uint16_t* label_table_dev, int64_t table_rows, const float* q_dev,
                  int B, int S, int H, int W, const float* y_dev, int k, int k_prime, int64_t idx_offset,
                  float beta, int ignore_index, float* label_hat_dev, int64_t* conf_dev,

@@ -537,40 +537,45 @@ class HbirdEvaluation:
             pipe = EvalPipeline(self.bank, self.label_table, S, conf, ignore_index, self.n_neighbours, self.k_prime, BETA,
                                 self.idx_offset, self.world if self.idx_shard else 1, self.rank, None,
                                 streams=self._pipe_streams)
-        for step, B, b0, b1, x, ys, copied in self._prefetched(val_loader):
-            torch.cuda.current_stream(self.device).wait_event(copied)
-            h, w = int(ys.shape[-2]), int(ys.shape[-1])  # the mask has the input's spatial size (:219,:240)
-            if pipe is not None:
+        try:
+            for step, B, b0, b1, x, ys, copied in self._prefetched(val_loader):
+                torch.cuda.current_stream(self.device).wait_event(copied)
+                h, w = int(ys.shape[-2]), int(ys.shape[-1])  # the mask has the input's spatial size (:219,:240)
+                if pipe is not None:
+                    if self.idx_shard:
+                        q = self._gathered_queries(x, B, b0, b1)
+                        pipe.xchg = self._exchange_for(q.shape[0], B)
+                    else:
+                        feats = self._features(x)
+                        q = feats.view(-1, feats.shape[2])
+                    pipe.submit(q, ys, B)
+                    continue
                 if self.idx_shard:
-                    q = self._gathered_queries(x, B, b0, b1)
-                    pipe.xchg = self._exchange_for(q.shape[0], B)
+                    lh, s, i, q = self._sharded_batch(x, B, b0, b1, return_knn_details)
+                    if b1 > b0:
+                        ops.predict_score(lh, b1 - b0, S, h, w, conf, y=ys, ignore_index=ignore_index)
+                    N, d = q.shape[0] // B, q.shape[1]
                 else:
                     feats = self._features(x)
-                    q = feats.view(-1, feats.shape[2])
-                pipe.submit(q, ys, B)
-                continue
-            if self.idx_shard:
-                lh, s, i, q = self._sharded_batch(x, B, b0, b1, return_knn_details)
-                if b1 > b0:
-                    ops.predict_score(lh, b1 - b0, S, h, w, conf, y=ys, ignore_index=ignore_index)
-                N, d = q.shape[0] // B, q.shape[1]
-            else:
-                feats = self._features(x)
-                N, d = feats.shape[1], feats.shape[2]
-                q = feats.view(B * N, d)
-                if self.nn_method != "b200":
-                    s, i, qn = self._legacy_neighbours(q)
-                    lh = ops.label_transfer(self.label_table, self.bank.patch_pixels, s, i, qn, BETA)
-                    ops.predict_score(lh, B, S, h, w, conf, y=ys, ignore_index=ignore_index)
-                elif return_knn_details:
-                    lh, _, s, i = self.bank.search_transfer(q, self.n_neighbours, self.k_prime, 0, BETA, None, True)
-                    ops.predict_score(lh, B, S, h, w, conf, y=ys, ignore_index=ignore_index)
-                else:  # the whole batch in one call: prep, K2, K2b+K4a, fused tail
-                    self.bank.eval_step(q, ys, S, conf, ignore_index, self.n_neighbours, self.k_prime, BETA)
-            if return_knn_details:
-                k = self.n_neighbours
-                kf, kl, lhd = self._gather_details(i, lh, B, N)
-                details.append((step, kf.view(-1, N, k, d).cpu(), kl.view(-1, N, k, C).cpu(), lhd.view(-1, N, C).cpu()))
+                    N, d = feats.shape[1], feats.shape[2]
+                    q = feats.view(B * N, d)
+                    if self.nn_method != "b200":
+                        s, i, qn = self._legacy_neighbours(q)
+                        lh = ops.label_transfer(self.label_table, self.bank.patch_pixels, s, i, qn, BETA)
+                        ops.predict_score(lh, B, S, h, w, conf, y=ys, ignore_index=ignore_index)
+                    elif return_knn_details:
+                        lh, _, s, i = self.bank.search_transfer(q, self.n_neighbours, self.k_prime, 0, BETA, None, True)
+                        ops.predict_score(lh, B, S, h, w, conf, y=ys, ignore_index=ignore_index)
+                    else:  # the whole batch in one call: prep, K2, K2b+K4a, fused tail
+                        self.bank.eval_step(q, ys, S, conf, ignore_index, self.n_neighbours, self.k_prime, BETA)
+                if return_knn_details:
+                    k = self.n_neighbours
+                    kf, kl, lhd = self._gather_details(i, lh, B, N)
+                    details.append((step, kf.view(-1, N, k, d).cpu(), kl.view(-1, N, k, C).cpu(), lhd.view(-1, N, C).cpu()))
+        except BaseException:
+            if pipe is not None:
+                pipe.abort()  # the bank stays usable after a failed evaluation
+            raise
         if pipe is not None:
             pipe.flush()
         if self.idx_shard and getattr(self, "_xchg", None) is not None:

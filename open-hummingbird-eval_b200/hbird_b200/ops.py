@@ -198,6 +198,10 @@ class MemoryBank:
                                    float(beta), ptr(scores), ptr(idx), ptr(lh), stream_ptr(q.device)))
         return lh, scores, idx
 
+    def search_abort(self) -> None:
+        """Free both pipeline slots after an error between search_begin and search_finish."""
+        check(lib.hb_search_abort(self._h))
+
     def eval_step(self, q: torch.Tensor, y: torch.Tensor, S: int, conf: torch.Tensor, ignore_index: Optional[int],
                   k: int = 30, k_prime: int = 64, beta: float = 0.02, label_table: Optional[torch.Tensor] = None,
                   idx_offset: int = 0, label_hat: Optional[torch.Tensor] = None, pred: Optional[torch.Tensor] = None,

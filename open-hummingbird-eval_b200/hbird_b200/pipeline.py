@@ -103,6 +103,13 @@ class EvalPipeline:
             if b1 > b0:
                 ops.predict_score(lh, b1 - b0, S, H, W, self.conf, y=y, ignore_index=self.ignore)
 
+    def abort(self) -> None:
+        """After an exception: drop the batch in flight and free the bank's pipeline slots, so that the
+        bank can be searched again."""
+        self.pending = None
+        torch.cuda.synchronize(self.conf.device)
+        self.bank.search_abort()
+
     def flush(self) -> None:
         """Post-process the last batch and make the caller's stream wait for everything."""
         if self.pending is not None:

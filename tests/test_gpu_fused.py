@@ -478,3 +478,23 @@ def test_exchange_gives_up_on_a_missing_peer_without_killing_the_context():
         xs[0].set_timeout(0)
     for o in xs + [bank]:
         o.close()
+
+
+def test_failed_evaluation_leaves_the_bank_usable():
+    """An exception in the middle of a pipelined evaluation (here: a batch of the wrong feature width)
+    must not leave a pipeline slot 'begun': the next evaluation on the same bank works."""
+    from hbird_b200 import HbirdEvaluation
+    from hbird_b200.models import FeatureExtractorSimple
+
+    cfg, g = load_golden("voc_tiny")
+    data = SyntheticSegmentationData(**cfg)
+    bank = build_bank_from_loader(data)
+    fe = FeatureExtractorSimple(torch.nn.Identity(), lambda m, x: (x, None), data.S, data.d)
+    ev = HbirdEvaluation.from_bank(fe, bank, data.C, 30, DEV, {"k_prime": 64})
+    good = [(torch.from_numpy(f), torch.from_numpy(y)) for f, y in batches_np(data, data.val_dataloader())]
+    bad = [good[0], (torch.zeros((2, data.S * data.S, data.d + 8)), good[0][1][:2])]
+    with pytest.raises(ValueError):
+        ev.evaluate(bad, data.S, ignore_index=data.ignore_index)
+    miou = ev.evaluate(good, data.S, ignore_index=data.ignore_index)
+    assert abs(miou - float(g["miou"])) <= 5e-4
+    ev.close()
