@@ -25,6 +25,42 @@ def dist_info(group=None) -> Tuple[int, int]:
     return 0, 1
 
 
+def _host_transport(group=None) -> bool:
+    """NCCL moves device tensors itself; any other backend (gloo: CPU tests, or several ranks
+    time-sharing one GPU) is handed host copies and the result is moved back."""
+    return dist.get_backend(group) != "nccl"
+
+
+def _all_gather_into(out: torch.Tensor, inp: torch.Tensor, group=None) -> None:
+    if inp.is_cuda and _host_transport(group):
+        tmp = torch.empty(out.shape, dtype=out.dtype)
+        dist.all_gather_into_tensor(tmp, inp.cpu(), group=group)
+        out.copy_(tmp)
+    else:
+        dist.all_gather_into_tensor(out, inp, group=group)
+
+
+def all_reduce_sum(t: torch.Tensor, group=None) -> torch.Tensor:
+    """In-place SUM all-reduce (the (C, C) confusion matrix, eval_metrics.py:251-252)."""
+    if t.is_cuda and _host_transport(group):
+        tmp = t.cpu()
+        dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=group)
+        t.copy_(tmp)
+    else:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def broadcast(t: torch.Tensor, src: int, group=None) -> torch.Tensor:
+    if t.is_cuda and _host_transport(group):
+        tmp = t.cpu()
+        dist.broadcast(tmp, src=src, group=group)
+        t.copy_(tmp)
+    else:
+        dist.broadcast(t, src=src, group=group)
+    return t
+
+
 def shard_bounds(n_rows: int, world: int, rank: int) -> Tuple[int, int]:
     """Contiguous balanced split of n_rows global rows: rank r owns [begin, end)."""
     return (n_rows * rank) // world, (n_rows * (rank + 1)) // world
@@ -37,7 +73,7 @@ def gather_counts(n_local: int, device, group=None) -> List[int]:
         return [int(n_local)]
     t = torch.tensor([int(n_local)], dtype=torch.int64, device=device)
     out = torch.empty((world,), dtype=torch.int64, device=device)
-    dist.all_gather_into_tensor(out, t, group=group)
+    _all_gather_into(out, t, group)
     return [int(v) for v in out.tolist()]
 
 
@@ -65,7 +101,7 @@ def all_gather_rows(local: torch.Tensor, counts: List[int], group=None) -> torch
         buf[:counts[rank]] = local.contiguous().view(torch.uint8).reshape(counts[rank], row_bytes)
     # (world * nmax, row_bytes): the concatenated output form both NCCL and gloo accept
     gathered = torch.empty((world * nmax, row_bytes), dtype=torch.uint8, device=local.device)
-    dist.all_gather_into_tensor(gathered, buf, group=group)
+    _all_gather_into(gathered, buf, group)
     gathered = gathered.view(world, nmax, row_bytes)
     parts = [gathered[r, :counts[r]] for r in range(world)]
     flat = torch.cat(parts, dim=0).contiguous()
@@ -80,8 +116,8 @@ def all_gather_topk(scores: torch.Tensor, idx: torch.Tensor, group=None) -> Tupl
     Q, k = scores.shape
     gs = torch.empty((world * Q, k), dtype=scores.dtype, device=scores.device)
     gi = torch.empty((world * Q, k), dtype=idx.dtype, device=idx.device)
-    dist.all_gather_into_tensor(gs, scores.contiguous(), group=group)
-    dist.all_gather_into_tensor(gi, idx.contiguous(), group=group)
+    _all_gather_into(gs, scores.contiguous(), group)
+    _all_gather_into(gi, idx.contiguous(), group)
     return gs.view(world, Q, k), gi.view(world, Q, k)
 
 
@@ -92,7 +128,7 @@ def all_gather_bytes(blob: bytes, device, group=None) -> List[bytes]:
         return [blob]
     t = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(device)
     out = torch.empty((world * len(blob),), dtype=torch.uint8, device=device)
-    dist.all_gather_into_tensor(out, t, group=group)
+    _all_gather_into(out, t, group)
     raw = out.cpu().numpy().tobytes()
     return [raw[r * len(blob):(r + 1) * len(blob)] for r in range(world)]
 
@@ -102,7 +138,7 @@ def all_ranks_ok(ok: bool, device, group=None) -> bool:
     _, world = dist_info(group)
     if world == 1:
         return bool(ok)
-    t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+    t = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cpu" if _host_transport(group) else device)
     dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
     return bool(int(t.item()))
 

@@ -250,8 +250,8 @@ class HbirdEvaluation:
                 else:
                     f = torch.empty((m, d), dtype=torch.float32, device=self.device)
                     l = torch.empty((m, C), dtype=torch.float32, device=self.device)
-                dist.broadcast(f, src=r)
-                dist.broadcast(l, src=r)
+                hdist.broadcast(f, r)
+                hdist.broadcast(l, r)
                 full.append_soft(f, l, normalise=False)
         full.finalize()
         self.bank.close()
@@ -305,6 +305,8 @@ class HbirdEvaluation:
 
         d, C = self.bank.d, self.num_classes
         fs, ls = [], []
+        # point-to-point transfers of device tensors need NCCL; other backends (gloo) go through the host
+        via = self.device if dist.get_backend() == "nccl" else torch.device("cpu")
         for r, n in enumerate(self.shard_counts):
             for a in range(0, n, slab):
                 m = min(slab, n - a)
@@ -312,12 +314,12 @@ class HbirdEvaluation:
                     f, l = self.bank.export(a, m, features=want_f, labels=want_l)
                     if r != 0:
                         if want_f:
-                            dist.send(f, dst=0)
+                            dist.send(f.to(via), dst=0)
                         if want_l:
-                            dist.send(l, dst=0)
+                            dist.send(l.to(via), dst=0)
                 elif self.rank == 0:
-                    f = torch.empty((m, d), dtype=torch.float32, device=self.device) if want_f else None
-                    l = torch.empty((m, C), dtype=torch.float32, device=self.device) if want_l else None
+                    f = torch.empty((m, d), dtype=torch.float32, device=via) if want_f else None
+                    l = torch.empty((m, C), dtype=torch.float32, device=via) if want_l else None
                     if want_f:
                         dist.recv(f, src=r)
                     if want_l:
@@ -611,7 +613,7 @@ class HbirdEvaluation:
         mine = (local >= 0) & (local < self.bank.rows)
         kf = f.index_select(0, local.clamp(0, self.bank.rows - 1)) * mine.unsqueeze(1).to(f.dtype)
         if self.idx_shard:
-            torch.distributed.all_reduce(kf)
+            hdist.all_reduce_sum(kf)
         table = torch.as_tensor(self.label_table, device=self.device)
         kl = table.index_select(0, flat.clamp_min(0)).to(torch.float32) / float(self.bank.patch_pixels)
         return kf, kl, label_hat

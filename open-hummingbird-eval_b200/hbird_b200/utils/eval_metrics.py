@@ -145,7 +145,9 @@ class PredsmIoU:
         if not is_global_zero:
             return 0.0, [], [], [], [], 0.0
         if sync_distributed and torch.distributed.is_available() and torch.distributed.is_initialized():
-            torch.distributed.all_reduce(self._conf_mat, op=torch.distributed.ReduceOp.SUM)
+            from ..distributed import all_reduce_sum
+
+            all_reduce_sum(self._conf_mat)
         miou, tp, fp, fn, mapping, bg = miou_from_confusion(
             self.confusion_matrix(), many_to_one=many_to_one, precision_based=precision_based,
             linear_probe=linear_probe)

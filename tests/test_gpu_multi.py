@@ -22,3 +22,18 @@ def test_multi_gpu_engine_matches_reference_golden():
     line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
     rep = json.loads(line)
     assert rep["ok"] and rep["world"] == n
+
+
+def test_multi_process_engine_on_one_gpu():
+    """The same check with two processes time-sharing cuda:0 (gloo for the collectives, CUDA IPC for the
+    exchange windows): the row-sharded and the replicated engine, the fused exchange between processes,
+    details, save/load and augmentation epochs are exercised even where only one GPU is visible."""
+    n = 2
+    env = dict(os.environ, HB_DIST_ONE_GPU="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+           "--master-addr", "127.0.0.1", "--master-port", "29518", os.path.join(ROOT, "tools", "dist_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
+    rep = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert rep["ok"] and rep["world"] == n and rep["one_gpu"] is True
+    assert rep["voc_tiny_p2p"]["fused_exchange"] and rep["ade_tiny_paths_identical"] and rep["aug2_layouts_identical"]

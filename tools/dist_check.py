@@ -23,8 +23,17 @@ from hbird_b200.data import SyntheticSegmentationData  # noqa: E402
 from hbird_b200.models import FeatureExtractorSimple  # noqa: E402
 
 rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+# HB_DIST_ONE_GPU=1: every rank uses cuda:0 and the collectives go through gloo (NCCL refuses two ranks on
+# one device).  The kernels, the CUDA-IPC exchange windows and the engine logic are the same as on N GPUs —
+# the processes merely time-share the device — so the multi-process path can be checked on a 1-GPU box.
+ONE_GPU = os.environ.get("HB_DIST_ONE_GPU") == "1"
+if ONE_GPU:
+    local = 0
 torch.cuda.set_device(local)
-dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+if ONE_GPU:
+    dist.init_process_group("gloo")
+else:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ok = True
 report = {}
 for name in ("voc_tiny", "ade_tiny"):
@@ -107,9 +116,9 @@ for shard in (True, False):
 # duplicate rows tie on the score and resolve by row id, which both layouts number alike (rank-major)
 report["aug2_layouts_identical"] = bool((aug_conf[True] == aug_conf[False]).all())
 ok = ok and report["aug2_layouts_identical"]
-flag = torch.tensor([1 if ok else 0], device="cuda")
+flag = torch.tensor([1 if ok else 0], device="cpu" if ONE_GPU else "cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print(json.dumps({"world": world, "ok": bool(flag.item()), **report}))
+    print(json.dumps({"world": world, "one_gpu": ONE_GPU, "ok": bool(flag.item()), **report}))
 dist.destroy_process_group()
 sys.exit(0 if flag.item() else 1)
