@@ -668,6 +668,8 @@ def main():
     table = bank.label_table()
     xchg = None
     collective = None
+    balance = None
+    shares = None  # fraction of a bank's rows each rank holds (None = equal)
     if world > 1:
         counts = hdist.gather_counts(bank.rows, device)
         table = hdist.all_gather_rows(bank.label_table(), counts)
@@ -678,7 +680,24 @@ def main():
         if xchg is not None:
             shard["xchg"], shard["qsplit"] = xchg, hdist.query_split(w["B"], w["S"] ** 2, world)
             collective = ("fused exchange: K2b stores each query's shard top-k into the owner rank's window over NVLink "
-                          "(CUDA IPC peer memory), the merge + label-transfer kernel waits on per-rank step flags; no NCCL call")
+                          "(CUDA IPC peer memory), a one-warp wait kernel polls the per-rank step flags, the merge + "
+                          "label-transfer kernel follows; no NCCL call")
+        # Shards sized by measured search speed, as the engine does (HbirdEvaluation._balance_shards): every
+        # step ends with everybody's shard results, so the job runs at the pace of the slowest GPU.
+        times = hdist.gather_floats(bank.calibrate_search_ms(k_prime=K_PRIME), device)
+        new_counts = hdist.balanced_counts(counts, times)
+        balance = {"search_ms_per_rank_equal_shards": times, "rows_per_gpu_equal": counts, "rows_per_gpu": counts}
+        if max(abs(n - o) / o for n, o in zip(new_counts, counts)) >= 0.01:
+            eq, _ = measure_workload(torch, dist, ops, w, bank, table, ring, max(4, args.steps // 4), 3, world, peaks, shard)
+            balance["ms_per_step_equal_shards"] = eq["ms_per_step"]
+            bank.close()
+            off = hdist.offsets_from_counts(new_counts)
+            a, b = off[rank], off[rank] + new_counts[rank]
+            bank = build_bank(w, a, b, device)  # global row r has the same content wherever it lives
+            counts = new_counts
+            shard["offset"] = off[rank]
+            balance["rows_per_gpu"] = new_counts
+            shares = [c / w["N"] for c in new_counts]
     torch.cuda.synchronize()
 
     sampler = ClockSampler(device.index)
@@ -779,7 +798,13 @@ def main():
 
     def side_workload(name, ww, sharded, keep_f32=True, graph=False, search_only=False):
         """value / kernel fraction of another configuration (single GPU, or row-sharded over the ranks)"""
-        a2, b2 = hdist.shard_bounds(ww["N"], world, rank) if sharded else (0, ww["N"])
+        if sharded and world > 1 and shares is not None:  # same relative shard sizes as the headline's calibration
+            cum = [0.0]
+            for sh in shares:
+                cum.append(cum[-1] + sh)
+            a2, b2 = int(round(ww["N"] * cum[rank])), (ww["N"] if rank == world - 1 else int(round(ww["N"] * cum[rank + 1])))
+        else:
+            a2, b2 = hdist.shard_bounds(ww["N"], world, rank) if sharded else (0, ww["N"])
         bk = build_bank(ww, a2, b2, device, keep_f32)
         rg = make_query_ring(ww, device, 0, 4)
         tb, sh, xc = bk.label_table(), None, None
@@ -852,8 +877,9 @@ def main():
                 "workload": f"{args.workload}: {w['desc']}", "bank_rows": w["N"], "bank_rows_per_gpu": per_gpu_rows,
                 "d": w["d"], "k": K_NEIGH, "k_prime": K_PRIME, "queries_per_step": Q, "classes": w["C"],
                 "parallelism": "single GPU" if world == 1 else
-                               f"bank row-sharded over {world} GPUs ({per_gpu_rows:,} rows each); every rank searches all "
-                               f"{Q} queries of a step, exchange, each rank post-processes its image slice",
+                               f"bank row-sharded over {world} GPUs ({per_gpu_rows:,} rows on rank 0; shards sized by measured "
+                               f"search speed, +-10 % of equal); every rank searches all {Q} queries of a step, exchange, each "
+                               f"rank post-processes its image slice",
                 "collective": collective,
                 "path": PATH,
                 "pipelining": ("two streams: K2 of batch i+1 (high priority) over the re-rank / exchange / merge / tail of "
@@ -888,7 +914,7 @@ def main():
         if world > 1:
             line["sharded"] = {"value": value, "unit": "patch-queries/s", "ms_per_step": ms_per_step, "scaling": "strong",
                                "bank_rows_total": w["N"], "bank_rows_per_gpu": per_gpu_rows, "collective": collective,
-                               "nccl_path_ms_per_step": nccl_ms, "parity": parity}
+                               "nccl_path_ms_per_step": nccl_ms, "parity": parity, "balance": balance}
         print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
         dist.barrier()

@@ -66,6 +66,34 @@ def shard_bounds(n_rows: int, world: int, rank: int) -> Tuple[int, int]:
     return (n_rows * rank) // world, (n_rows * (rank + 1)) // world
 
 
+def balanced_counts(counts: List[int], times_ms: List[float], max_shift: float = 0.10) -> List[int]:
+    """Shard sizes proportional to each rank's measured search speed (rows per ms on its current
+    shard), so that all ranks finish a batch together: with a row-sharded bank every step ends with
+    everybody's results, i.e. the job runs at the pace of the slowest GPU, and GPUs under the same
+    power cap differ by a few per cent.  Each shard stays within +-max_shift of its current size;
+    the total is preserved exactly.  Pure integer/float host logic."""
+    total = sum(counts)
+    if len(counts) < 2 or total == 0 or any(t <= 0 for t in times_ms) or any(c <= 0 for c in counts):
+        return list(counts)
+    speed = [c / t for c, t in zip(counts, times_ms)]
+    share = [v / sum(speed) for v in speed]
+    want = [min(max(total * sh, c * (1.0 - max_shift)), c * (1.0 + max_shift)) for sh, c in zip(share, counts)]
+    scale = total / sum(want)
+    new = [max(1, int(round(x * scale))) for x in want]
+    new[new.index(max(new))] += total - sum(new)  # rounding remainder goes to the largest shard
+    return new
+
+
+def gather_floats(value: float, device, group=None) -> List[float]:
+    _, world = dist_info(group)
+    if world == 1:
+        return [float(value)]
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    out = torch.empty((world,), dtype=torch.float64, device=device)
+    _all_gather_into(out, t, group)
+    return [float(v) for v in out.tolist()]
+
+
 def gather_counts(n_local: int, device, group=None) -> List[int]:
     """Row count of every rank's shard (shards built from a strided loader split can differ)."""
     _, world = dist_info(group)

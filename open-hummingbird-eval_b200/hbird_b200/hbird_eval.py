@@ -57,7 +57,8 @@ class HbirdEvaluation:
                         slice of the batch and the queries are all-gathered."""
 
     _B200_PARAMS = ("k_prime", "keep_f32", "gpu_ids", "exchange", "idx_shard", "use_fp16", "distance_measure",
-                    "cta_group", "max_chunks")
+                    "cta_group", "max_chunks", "balance_shards")
+    _BALANCE_MIN_ROWS = 1 << 17  # below this a shard's search time says nothing about the GPU's speed
 
     def __init__(self, feature_extractor: torch.nn.Module, train_loader, num_classes: int,
                  n_neighbours: int = 30, augmentation_epoch: int = 1, device: torch.device | str = "cpu",
@@ -114,6 +115,7 @@ class HbirdEvaluation:
         self._create_memory(train_loader, num_classes, S)
         self._save_memory()
         self._create_nn(self.n_neighbours, nn_method=self.nn_method, **self.nn_params)
+        self._balance_shards()
 
     @classmethod
     def from_bank(cls, feature_extractor: torch.nn.Module, bank: "ops.MemoryBank", num_classes: int,
@@ -257,6 +259,68 @@ class HbirdEvaluation:
         self.bank.close()
         self.bank = full
 
+    def _balance_shards(self) -> None:
+        """Row shards sized by measured search speed (nn_params["balance_shards"], default on).  With a
+        sharded bank every batch ends with everybody's shard results, so the evaluation runs at the pace
+        of the slowest GPU; GPUs under the same power cap differ by a few per cent.  Each rank times the
+        search kernel on its shard, the times are all-gathered, and rows migrate between neighbouring
+        ranks until all shards take the same time (distributed.balanced_counts; at most +-10 %)."""
+        if not self.idx_shard or not bool(self.nn_params.get("balance_shards", True)):
+            return
+        if min(self.shard_counts) < self._BALANCE_MIN_ROWS:
+            return
+        times = hdist.gather_floats(self.bank.calibrate_search_ms(k_prime=self.k_prime), self.device)
+        new_counts = hdist.balanced_counts(self.shard_counts, times)
+        if max(abs(n - o) / o for n, o in zip(new_counts, self.shard_counts)) < 0.01:
+            return  # already even within a per cent
+        logger.info("Balancing shards by search speed: %s ms -> rows %s", [round(t, 2) for t in times], new_counts)
+        self.rebalance(new_counts)
+
+    def rebalance(self, new_counts) -> None:
+        """Re-shard the bank to `new_counts` rows per rank (same total).  Global row order is rank-major and
+        contiguous before and after, so global row ids — and the replicated label table — do not change:
+        rows only move between ranks.  Every rank rebuilds its shard from the pieces of the old shards
+        that fall into its new range (exported as fp32 unit rows + soft labels, re-packed bit-identically)."""
+        import torch.distributed as dist
+
+        old = list(self.shard_counts)
+        new = [int(c) for c in new_counts]
+        if len(new) != self.world or sum(new) != sum(old) or min(new) < 1:
+            raise ValueError(f"rebalance: {new} must hold {self.world} positive counts summing to {sum(old)}")
+        if new == old:
+            return
+        old_off, new_off = hdist.offsets_from_counts(old) + [sum(old)], hdist.offsets_from_counts(new) + [sum(new)]
+        d, C = self.bank.d, self.num_classes
+        via = self.device if dist.get_backend() == "nccl" else torch.device("cpu")
+        fresh = ops.MemoryBank(d, C, self.bank.patch_pixels, new[self.rank], self.device.index, self.keep_f32)
+        slab = 1 << 18
+        for src in range(self.world):      # same order on every rank: matched blocking send / recv pairs,
+            for dst in range(self.world):  # and for a given dst the pieces arrive in ascending global rows
+                lo, hi = max(old_off[src], new_off[dst]), min(old_off[src + 1], new_off[dst + 1])
+                if hi <= lo or self.rank not in (src, dst):
+                    continue
+                for a in range(lo, hi, slab):
+                    m = min(slab, hi - a)
+                    if self.rank == src:
+                        f, l = self.bank.export(a - old_off[src], m)
+                        if dst != src:
+                            dist.send(f.to(via), dst=dst)
+                            dist.send(l.to(via), dst=dst)
+                    if self.rank == dst:
+                        if dst != src:
+                            f = torch.empty((m, d), dtype=torch.float32, device=via)
+                            l = torch.empty((m, C), dtype=torch.float32, device=via)
+                            dist.recv(f, src=src)
+                            dist.recv(l, src=src)
+                        fresh.append_soft(f.to(self.device), l.to(self.device), normalise=False)
+        fresh.finalize()
+        self.bank.close()
+        self.bank = fresh
+        self.shard_counts = new
+        self.idx_offset = new_off[self.rank]
+        self.__dict__.pop("_export_cache", None)
+        self._create_nn(self.n_neighbours, nn_method=self.nn_method, **self.nn_params)
+
     def _sample_patches(self, mask: torch.Tensor, S: int, ps: int, num_classes: int) -> torch.Tensor:
         """Bounded-memory sampler, hbird_eval.py:447-517: per image keep the K patches with the
         smallest score*U(0,1) (hb_sample_patches).  U is drawn with the CPU generator in image order
@@ -367,6 +431,7 @@ class HbirdEvaluation:
         self.shard_counts, self.total_rows = counts, sum(counts)
         self.__dict__.pop("_export_cache", None)
         self._create_nn(self.n_neighbours, nn_method=self.nn_method, **self.nn_params)
+        self._balance_shards()
         return True
 
     @property
@@ -382,7 +447,7 @@ class HbirdEvaluation:
     def _create_nn(self, n_neighbours: int = 30, nn_method: str = "b200", **kwargs) -> None:
         """hbird_eval.py:267-281, through the registry."""
         if nn_method == "b200":
-            kw = {k: v for k, v in kwargs.items() if k in ("cta_group", "max_chunks", "idx_shard", "use_fp16")}
+            kw = {k: v for k, v in kwargs.items() if k in ("cta_group", "max_chunks", "idx_shard", "use_fp16")}  # engine-level names stay here
             measure = str(kwargs.get("distance_measure", "dot_product")).lower()
             if measure not in ("dot_product", "l2", "euclidean"):
                 raise ValueError(f"Unsupported distance measure: {measure}")  # search_faiss.py:48

@@ -264,6 +264,21 @@ class MemoryBank:
         check(lib.hb_search_rerank_time(self._h, ctypes.byref(ms), ctypes.byref(n)))
         return ms.value, n.value
 
+    def calibrate_search_ms(self, n_queries: int = 8192, k_prime: int = 64, repeats: int = 4) -> float:
+        """Mean duration (ms) of the tensor-core search kernel over this bank for n_queries random
+        queries: the per-GPU speed figure shard balancing is based on (distributed.balanced_counts)."""
+        dev = torch.device("cuda", self.device)
+        g = torch.Generator(device=dev).manual_seed(1234)
+        q = torch.randn((n_queries, self.d), generator=g, device=dev)
+        for _ in range(2):
+            self.search(q, 1, k_prime)
+        self.enable_kernel_timing(True)
+        for _ in range(repeats):
+            self.search(q, 1, k_prime)
+        ms, _ = self.kernel_time_ms()
+        self.enable_kernel_timing(False)
+        return ms
+
     def last_search_launches(self) -> int:
         return int(lib.hb_search_last_launches(self._h))
 

@@ -142,3 +142,20 @@ def test_per_rank_bank_capacity_covers_the_batches_a_rank_takes(L, W, aug, bound
         assert cap <= max(1, (dealt * B * per_image)) or W == 1
         if bounded and W > 1 and dealt:
             assert cap < total
+
+
+def test_balanced_shard_counts_equalise_the_search_time():
+    """distributed.balanced_counts: shard sizes proportional to measured speed, total preserved, shifts
+    bounded; degenerate inputs leave the shards alone."""
+    from hbird_b200.distributed import balanced_counts
+
+    counts = [1_280_000] * 8
+    times = [30.0, 30.5, 31.0, 29.5, 30.2, 30.1, 31.4, 29.9]
+    new = balanced_counts(counts, times)
+    assert sum(new) == sum(counts) and all(abs(n - c) <= 0.1 * c + 1 for n, c in zip(new, counts))
+    predicted = [t * n / c for t, n, c in zip(times, new, counts)]  # search time is linear in the rows
+    assert max(predicted) - min(predicted) < 0.02 * max(predicted)
+    assert max(predicted) < max(times)
+    assert balanced_counts([100, 100], [1.0, 5.0]) == [110, 90]          # clamped to +-10 %
+    assert balanced_counts([7], [3.0]) == [7] and balanced_counts([5, 5], [0.0, 1.0]) == [5, 5]
+    assert balanced_counts([3, 1_000_000], [1.0, 1.0]) == [3, 1_000_000]  # equal speed per row... stays within bounds

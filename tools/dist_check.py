@@ -66,6 +66,18 @@ for name in ("voc_tiny", "ade_tiny"):
         report[f"{name}_{mode}"] = {"miou": miou, "ref": float(g["miou"]), "shard_rows": rows,
                                     "fused_exchange": fused, "details_ok": bool(details_ok), "ok": bool(good)}
         ok = ok and good
+        if mode == "p2p":
+            # speed-balanced shards move rows between ranks (here: by hand, 37 rows from rank 0 to the last
+            # rank); global row ids stay, so the evaluation must not change by a single pixel
+            moved = list(rows)
+            moved[0] -= 37
+            moved[-1] += 37
+            ev.rebalance(moved)
+            miou_b = ev.evaluate(data.val_dataloader(), data.S, ignore_index=data.ignore_index)
+            same = ev.shard_counts == moved and ev.bank.rows == moved[rank] and bool((ev.last_confusion == conf).all()) \
+                and miou_b == miou
+            report[f"{name}_rebalanced"] = {"shard_rows": ev.shard_counts, "identical": bool(same)}
+            ok = ok and same
         ev.close()
     # memory files with a sharded bank: rank 0 writes ONE (N, d) / (N, C) pair (hbird_eval.py:371-378);
     # reloading re-shards it by contiguous row ranges and must reproduce the evaluation
