@@ -621,6 +621,7 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="headline workload only (no by_workload block)")
+    ap.add_argument("--no-balance", action="store_true", help="N > 1: keep equal row shards (no speed balancing)")
     ap.add_argument("--extras", default="", help="comma list of by_workload entries to run (default: all)")
     args = ap.parse_args()
 
@@ -683,13 +684,15 @@ def main():
                           "(CUDA IPC peer memory), a one-warp wait kernel polls the per-rank step flags, the merge + "
                           "label-transfer kernel follows; no NCCL call")
         # Shards sized by measured search speed, as the engine does (HbirdEvaluation._balance_shards): every
-        # step ends with everybody's shard results, so the job runs at the pace of the slowest GPU.
-        times = hdist.gather_floats(bank.calibrate_search_ms(k_prime=K_PRIME), device)
+        # step ends with everybody's shard results, so the job runs at the pace of the slowest GPU.  The
+        # speed figure is each rank's mean K2 time over a full-length run of the SAME steps on equal shards
+        # (sustained clocks); that run is reported next to the headline (`ms_per_step_equal_shards`).
+        eq, _ = measure_workload(torch, dist, ops, w, bank, table, ring, args.steps, warmup, world, peaks, shard)
+        times = hdist.gather_floats(eq["search_kernel_ms"], device)
         new_counts = hdist.balanced_counts(counts, times)
-        balance = {"search_ms_per_rank_equal_shards": times, "rows_per_gpu_equal": counts, "rows_per_gpu": counts}
-        if max(abs(n - o) / o for n, o in zip(new_counts, counts)) >= 0.01:
-            eq, _ = measure_workload(torch, dist, ops, w, bank, table, ring, max(4, args.steps // 4), 3, world, peaks, shard)
-            balance["ms_per_step_equal_shards"] = eq["ms_per_step"]
+        balance = {"search_ms_per_rank_equal_shards": times, "rows_per_gpu_equal": counts, "rows_per_gpu": counts,
+                   "ms_per_step_equal_shards": eq["ms_per_step"], "enabled": not args.no_balance}
+        if not args.no_balance and max(abs(n - o) / o for n, o in zip(new_counts, counts)) >= 0.01:
             bank.close()
             off = hdist.offsets_from_counts(new_counts)
             a, b = off[rank], off[rank] + new_counts[rank]

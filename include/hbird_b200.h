@@ -155,9 +155,12 @@ int hb_search_transfer(hb_bank_t* bank, const uint16_t* label_table_dev, int64_t
  * batch, whose CTAs take all but ~2 KB of it: the HBM-bound half of batch i hides under the
  * tensor-bound half of batch i+1.  A slot is reused only after its finish has run (enforced with an
  * event inside the library); q_dev must stay valid until the finish has executed; the scratch block is
- * sized for both slots by the first begin (it must not have to grow while a slot is in flight). */
+ * grows in stream order.  prepared_event: optional `cudaEvent_t` recorded between the query prep and
+ * K2 — a pipelined caller makes the previous batch's finish wait for it, so that the small kernels
+ * are released together with the search kernel (whose stream should have the higher priority)
+ * instead of flooding the SMs in the gap before it. */
 int hb_search_begin(hb_bank_t* bank, const float* q_dev, int64_t Q, int k_prime, int slot,
-                    float* out_qnorm_dev, void* stream);
+                    float* out_qnorm_dev, void* prepared_event, void* stream);
 int hb_search_finish(hb_bank_t* bank, int slot, const float* q_dev, int k, int64_t idx_offset,
                      const uint16_t* label_table_dev, int64_t table_rows, float beta,
                      float* out_scores_dev, int64_t* out_idx_dev, float* out_label_hat_dev,

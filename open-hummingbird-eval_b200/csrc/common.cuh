@@ -152,7 +152,7 @@ int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_t idx_o
                 cudaStream_t st, const Scatter* sc, const LabelOut* lo);
 // The two halves of search_impl (which is begin + finish of slot 0 on one stream).
 int search_begin_impl(Bank* b, const float* q, int64_t Q, int kp, int slot, float* out_qnorm, float* dump,
-                      int cg_override, cudaStream_t st);
+                      int cg_override, cudaStream_t st, cudaEvent_t prepared);
 int search_finish_impl(Bank* b, int slot, const float* q, int k, int64_t idx_offset, float* out_scores,
                        int64_t* out_idx, const Scatter* sc, const LabelOut* lo, cudaStream_t st);
 int rerank_launch(const Bank* b, const float* q, int64_t Q, int k, int kp, int n_chunks,

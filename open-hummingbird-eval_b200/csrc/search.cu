@@ -657,7 +657,7 @@ static bool stream_is_capturing(cudaStream_t st) {
 }
 
 int search_begin_impl(Bank* b, const float* q, int64_t Q, int kp, int slot, float* out_qnorm, float* dump,
-                      int cg_override, cudaStream_t st) {
+                      int cg_override, cudaStream_t st, cudaEvent_t prepared) {
   // measured on B200 (profiles/): CTA pairs (cta_group::2: half the B-operand shared-memory traffic
   // per SM) win at every bank size and feature dim; cta_group 1 stays selectable
   int cg = cg_override ? cg_override : (b->cfg_cta_group ? b->cfg_cta_group : 2);
@@ -729,6 +729,11 @@ int search_begin_impl(Bank* b, const float* q, int64_t Q, int kp, int slot, floa
   prep_queries_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(q, Q, b->d, b->dpad, (b->flags & HB_BANK_L2) ? 1 : 0, q_bf16, qnorm);
   HB_CHECK_CUDA(cudaGetLastError());
   b->last_launches++;
+  // A pipelined caller holds the previous batch's post-processing back until this point: released
+  // earlier, its small CTAs flood the SMs in the gap before the search kernel is launched and the
+  // search CTAs (which need a whole SM each) then wait for them to drain; released here, both are
+  // pending together and the search's higher stream priority places it first.
+  if (prepared != nullptr) HB_CHECK_CUDA(cudaEventRecord(prepared, st));
 
   CUtensorMap tmap_q;
   rc = make_tmap_2d_bf16(&tmap_q, q_bf16, Q, b->dpad, BM);
@@ -799,7 +804,7 @@ int search_finish_impl(Bank* b, int slot, const float* q, int k, int64_t idx_off
 int search_impl(Bank* b, const float* q, int64_t Q, int k, int kp, int64_t idx_offset,
                 float* out_scores, int64_t* out_idx, float* out_qnorm, float* dump, int cg_override,
                 cudaStream_t st, const Scatter* sc, const LabelOut* lo) {
-  int rc = search_begin_impl(b, q, Q, kp, 0, out_qnorm, dump, cg_override, st);
+  int rc = search_begin_impl(b, q, Q, kp, 0, out_qnorm, dump, cg_override, st, nullptr);
   if (rc != HB_OK || dump != nullptr) return rc;  // validation call: raw scores only
   return search_finish_impl(b, 0, q, k, idx_offset, out_scores, out_idx, sc, lo, st);
 }
@@ -870,7 +875,7 @@ int hb_search_transfer(hb_bank_t* bank, const uint16_t* label_table_dev, int64_t
 }
 
 int hb_search_begin(hb_bank_t* bank, const float* q_dev, int64_t Q, int k_prime, int slot, float* out_qnorm_dev,
-                    void* stream) {
+                    void* prepared_event, void* stream) {
   HB_REQUIRE(bank != nullptr, "hb_search_begin: bank is NULL");
   Bank* b = reinterpret_cast<Bank*>(bank);
   if (!b->finalized) {
@@ -887,7 +892,8 @@ int hb_search_begin(hb_bank_t* bank, const float* q_dev, int64_t Q, int k_prime,
     return HB_ERR_STATE;
   }
   HB_CHECK_CUDA(cudaSetDevice(b->device));
-  return hb::search_begin_impl(b, q_dev, Q, k_prime, slot, out_qnorm_dev, nullptr, 0, static_cast<cudaStream_t>(stream));
+  return hb::search_begin_impl(b, q_dev, Q, k_prime, slot, out_qnorm_dev, nullptr, 0, static_cast<cudaStream_t>(stream),
+                               static_cast<cudaEvent_t>(prepared_event));
 }
 
 int hb_search_finish(hb_bank_t* bank, int slot, const float* q_dev, int k, int64_t idx_offset,

@@ -45,7 +45,7 @@ _SIGNATURES = [
     ("hb_search", c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     ("hb_search_transfer", c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int64, c_float,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    ("hb_search_begin", c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    ("hb_search_begin", c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     ("hb_search_finish", c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_int64, c_float, c_void_p, c_void_p,
                                  c_void_p, c_void_p]),
     ("hb_search_abort", c_int, [c_void_p]),

@@ -66,15 +66,19 @@ def shard_bounds(n_rows: int, world: int, rank: int) -> Tuple[int, int]:
     return (n_rows * rank) // world, (n_rows * (rank + 1)) // world
 
 
-def balanced_counts(counts: List[int], times_ms: List[float], max_shift: float = 0.10) -> List[int]:
+def balanced_counts(counts: List[int], times_ms: List[float], max_shift: float = 0.10, gain: float = 1.0) -> List[int]:
     """Shard sizes proportional to each rank's measured search speed (rows per ms on its current
     shard), so that all ranks finish a batch together: with a row-sharded bank every step ends with
     everybody's results, i.e. the job runs at the pace of the slowest GPU, and GPUs under the same
     power cap differ by a few per cent.  Each shard stays within +-max_shift of its current size;
-    the total is preserved exactly.  Pure integer/float host logic."""
+    the total is preserved exactly.  gain < 1 applies only that fraction of the correction.  Pure
+    integer/float host logic."""
     total = sum(counts)
     if len(counts) < 2 or total == 0 or any(t <= 0 for t in times_ms) or any(c <= 0 for c in counts):
         return list(counts)
+    if gain != 1.0:  # damped correction: move only part of the way towards equal times
+        mean_t = sum(times_ms) / len(times_ms)
+        times_ms = [mean_t + gain * (t - mean_t) for t in times_ms]
     speed = [c / t for c, t in zip(counts, times_ms)]
     share = [v / sum(speed) for v in speed]
     want = [min(max(total * sh, c * (1.0 - max_shift)), c * (1.0 + max_shift)) for sh, c in zip(share, counts)]

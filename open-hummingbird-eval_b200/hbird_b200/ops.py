@@ -168,16 +168,24 @@ class MemoryBank:
                                      stream_ptr(q.device)))
         return lh, qn, scores, idx
 
-    def search_begin(self, q: torch.Tensor, k_prime: int = 64, slot: int = 0) -> torch.Tensor:
+    def search_begin(self, q: torch.Tensor, k_prime: int = 64, slot: int = 0,
+                     prepared: Optional[torch.cuda.Event] = None) -> torch.Tensor:
         """First half of a search on the CURRENT stream: query prep + K2 (tensor-core pass) into pipeline
         slot 0/1.  Returns the (Q,) query norms.  Pair with search_finish / ShardExchange.finish_scatter,
         which may run on another stream (ordered after this one by an event) while the next batch's
-        search_begin already executes — see hbird_b200.pipeline.EvalPipeline."""
+        search_begin already executes — see hbird_b200.pipeline.EvalPipeline.  prepared: an event the
+        library records between the query prep and K2 (the previous batch's finish is released there)."""
         q = _require_cuda(q, "q", torch.float32)
         if q.dim() != 2 or q.shape[1] != self.d:
             raise ValueError(f"queries must be (Q, {self.d}), got {tuple(q.shape)}")
         qn = torch.empty((q.shape[0],), dtype=torch.float32, device=q.device)
-        check(lib.hb_search_begin(self._h, ptr(q), q.shape[0], int(k_prime), int(slot), ptr(qn), stream_ptr(q.device)))
+        ev = None
+        if prepared is not None:
+            import ctypes
+
+            prepared.record(torch.cuda.current_stream(q.device))  # materialises the lazily created CUDA event
+            ev = ctypes.c_void_p(prepared.cuda_event)
+        check(lib.hb_search_begin(self._h, ptr(q), q.shape[0], int(k_prime), int(slot), ptr(qn), ev, stream_ptr(q.device)))
         return qn
 
     def search_finish(self, slot: int, q: torch.Tensor, k: int = 30, idx_offset: int = 0, beta: float = 0.02,
@@ -264,16 +272,28 @@ class MemoryBank:
         check(lib.hb_search_rerank_time(self._h, ctypes.byref(ms), ctypes.byref(n)))
         return ms.value, n.value
 
-    def calibrate_search_ms(self, n_queries: int = 8192, k_prime: int = 64, repeats: int = 4) -> float:
+    def calibrate_search_ms(self, n_queries: int = 8192, k_prime: int = 64, seconds: float = 1.5) -> float:
         """Mean duration (ms) of the tensor-core search kernel over this bank for n_queries random
-        queries: the per-GPU speed figure shard balancing is based on (distributed.balanced_counts)."""
+        queries, measured over ~`seconds` of back-to-back searches: the per-GPU speed figure shard
+        balancing is based on (distributed.balanced_counts).  It has to be a SUSTAINED figure — a short
+        burst runs above the power cap's steady clocks and ranks the GPUs differently (measured on an
+        8-GPU box: burst spread 8 %, sustained 3 %)."""
+        import time
+
         dev = torch.device("cuda", self.device)
         g = torch.Generator(device=dev).manual_seed(1234)
         q = torch.randn((n_queries, self.d), generator=g, device=dev)
-        for _ in range(2):
+        self.search(q, 1, k_prime)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        self.search(q, 1, k_prime)
+        torch.cuda.synchronize(dev)
+        once = max(time.perf_counter() - t0, 1e-4)
+        n = int(max(8, min(2000, seconds / once)))
+        for _ in range(max(1, n - 48)):   # settle the clocks; the event ring keeps the last 64 searches
             self.search(q, 1, k_prime)
         self.enable_kernel_timing(True)
-        for _ in range(repeats):
+        for _ in range(min(n, 48)):
             self.search(q, 1, k_prime)
         ms, _ = self.kernel_time_ms()
         self.enable_kernel_timing(False)

@@ -66,12 +66,15 @@ class EvalPipeline:
         slot = self.count & 1
         self.count += 1
         self.mma_stream.wait_event(ready)
+        prepared = torch.cuda.Event()
         with torch.cuda.stream(self.mma_stream):
-            qn = self.bank.search_begin(q, self.kp, slot)
+            qn = self.bank.search_begin(q, self.kp, slot, prepared)
             searched = torch.cuda.Event()
             searched.record(self.mma_stream)
         if self.pending is not None:
-            self._post(self.pending)  # issued after the next K2, executes under it
+            # released together with this batch's search kernel (not in the gap before it), runs under it
+            self.post_stream.wait_event(prepared)
+            self._post(self.pending)
         self.pending = (slot, q, y, qn, n_images, searched, ready)
         for t in (q, y):
             t.record_stream(self.mma_stream)
