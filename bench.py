@@ -357,7 +357,7 @@ def sample_queries(w, ring_host, n_q):
     return pick, np.ascontiguousarray(q_all[pick]), y_all[:1]
 
 
-def parity_block(torch, dist, ops, O, w, bank, table, ring, world, rank, offset, n_q, n_img, cpu_time=False):
+def parity_block(torch, dist, ops, O, w, bank, table, ring, world, rank, offset, n_q, n_img, cpu_time=False, shard=None):
     """The timed inputs through the CUDA path against the oracle.
     (1) n_q queries sampled from the first validation batch: the CPU oracle's exact search runs on
         every rank's host against that rank's rows of the bank (exported from HBM) and the per-shard
@@ -433,9 +433,23 @@ def parity_block(torch, dist, ops, O, w, bank, table, ring, world, rank, offset,
         pred = ops.predict_score(lh[:n_img * per].contiguous(), n_img, S, H, H, conf, y=y0[:n_img], ignore_index=w["ignore"],
                                  return_pred=True)
         lh_img = lh[:n_img * per]
+    elif shard is not None and shard.get("xchg") is not None:
+        # row-sharded, THE TIMED PATH: per-shard K2, shard exchange over NVLink (threshold exchange or full
+        # re-rank, as configured), merge with the label transfer fused in on the rank that owns the query;
+        # the per-rank slices are then collected for the comparison
+        xc, qsp = shard["xchg"], shard["qsplit"]
+        qn = xc.search_scatter(bank, q0, qsp, k, K_PRIME, offset)
+        a, b = qsp[rank], qsp[rank + 1]
+        lh_s, s_s, i_s = xc.merge_transfer(table, w["ps"] ** 2, qn[a:b].contiguous(), BETA, True)
+        xc.check_status()
+        cnt = [qsp[r + 1] - qsp[r] for r in range(world)]
+        lh, s_all, i_all = (hdist.all_gather_rows(t, cnt) for t in (lh_s, s_s, i_s))
+        got_s, got_i = s_all[torch.from_numpy(pick).to(dev)].cpu().numpy(), i_all[torch.from_numpy(pick).to(dev)].cpu().numpy()
+        pred = ops.predict_score(lh[:n_img * per].contiguous(), n_img, S, H, H, conf, y=y0[:n_img], ignore_index=w["ignore"],
+                                 return_pred=True)
+        lh_img = lh[:n_img * per]
     else:
-        # row-sharded: per-shard K2/K2b, NCCL all-gather, merge with the label transfer fused in (the
-        # fused NVLink exchange is bit-identical to this path: tests/test_gpu_fused.py, tools/dist_check.py)
+        # row-sharded without peer memory: per-shard K2/K2b, NCCL all-gather, merge with the label transfer fused in
         s, i, qn = bank.search(q0, k, K_PRIME, offset)
         ags2, agi2 = hdist.all_gather_topk(s, i)
         lh, s_all, i_all = ops.merge_topk_transfer(ags2, agi2, table, w["ps"] ** 2, qn, BETA, True)
@@ -622,6 +636,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="headline workload only (no by_workload block)")
     ap.add_argument("--no-balance", action="store_true", help="N > 1: keep equal row shards (no speed balancing)")
+    ap.add_argument("--exchange", default="threshold", choices=["threshold", "full"],
+                    help="N > 1: shards re-rank only candidates above the cross-shard bound (default), or their whole top-k'")
     ap.add_argument("--extras", default="", help="comma list of by_workload entries to run (default: all)")
     args = ap.parse_args()
 
@@ -676,13 +692,19 @@ def main():
         table = hdist.all_gather_rows(bank.label_table(), counts)
         shard = {"offset": hdist.offsets_from_counts(counts)[rank], "world": world, "rank": rank}
         per_rank = -(-w["B"] // world) * w["S"] ** 2
-        xchg = hdist.connect_shard_exchange(per_rank, K_NEIGH, device)
+        xchg = hdist.connect_shard_exchange(per_rank, K_NEIGH, device, threshold_exchange=args.exchange == "threshold")
         collective = "NCCL all-gather of (score f32, idx i64)[Q,k] + k-way merge kernel with the label transfer fused in"
         if xchg is not None:
             shard["xchg"], shard["qsplit"] = xchg, hdist.query_split(w["B"], w["S"] ** 2, world)
             collective = ("fused exchange: K2b stores each query's shard top-k into the owner rank's window over NVLink "
                           "(CUDA IPC peer memory), a one-warp wait kernel polls the per-rank step flags, the merge + "
                           "label-transfer kernel follows; no NCCL call")
+            if args.exchange == "threshold":
+                collective = ("threshold exchange over NVLink peer memory (CUDA IPC), no NCCL call: a shortlist kernel merges each "
+                              "query's candidate lists and stores four order statistics of its bf16 top-k' into every rank's "
+                              "window; after a one-warp wait every shard derives the same bound of the global k'-th best score "
+                              "and gathers fp32 rows only for its candidates above it (instead of k' per query and shard); K2b "
+                              "stores the shard top-k into the owner rank's window; wait; merge + label-transfer kernel")
         # Shards sized by measured search speed, as the engine does (HbirdEvaluation._balance_shards): every
         # step ends with everybody's shard results, so the job runs at the pace of the slowest GPU.  The
         # speed figure is each rank's mean K2 time over a full-length run of the SAME steps on equal shards
@@ -709,7 +731,10 @@ def main():
     clocks = sampler.stop()
     ms_per_step = head["ms_per_step"]
     value = Q / (ms_per_step * 1e-3)  # world == 1: this GPU; world > 1: all ranks work on the same Q queries
-    launches_per_step = 4 if world == 1 else 5
+    xchg_used = xchg is not None
+    # world == 1: prep, K2, K2b+K4a, tail.  Sharded: prep, K2, K2b-scatter, wait, merge+K4a, tail (6); with the
+    # threshold exchange the K2b is a shortlist kernel + a wait + the re-rank of the survivors (8); NCCL path: 6
+    launches_per_step = 4 if world == 1 else (8 if (xchg_used and args.exchange == "threshold") else 6)
 
     nccl_ms = None
     if world > 1 and xchg is not None:
@@ -761,7 +786,7 @@ def main():
     # ------------------------------------------------------------------ parity vs the oracle (+ CPU baseline at N = 1)
     par_q = 256 if w["N"] > 2_000_000 else 1024
     parity, _ = parity_block(torch, dist, ops, O, w, bank, table, ring, world, rank, 0 if shard is None else shard["offset"],
-                             n_q=par_q, n_img=2)
+                             n_q=par_q, n_img=2, shard=shard)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         rows = bank.rows
@@ -815,7 +840,8 @@ def main():
             cts = hdist.gather_counts(bk.rows, device)
             tb = hdist.all_gather_rows(bk.label_table(), cts)
             sh = {"offset": hdist.offsets_from_counts(cts)[rank], "world": world, "rank": rank}
-            xc = hdist.connect_shard_exchange(-(-ww["B"] // world) * ww["S"] ** 2, K_NEIGH, device)
+            xc = hdist.connect_shard_exchange(-(-ww["B"] // world) * ww["S"] ** 2, K_NEIGH, device,
+                                              threshold_exchange=args.exchange == "threshold")
             if xc is not None:
                 sh["xchg"], sh["qsplit"] = xc, hdist.query_split(ww["B"], ww["S"] ** 2, world)
         m, _ = measure_workload(torch, dist, ops, ww, bk, tb, rg, few, 3, world, peaks, sh, graph=graph)
@@ -917,6 +943,7 @@ def main():
         if world > 1:
             line["sharded"] = {"value": value, "unit": "patch-queries/s", "ms_per_step": ms_per_step, "scaling": "strong",
                                "bank_rows_total": w["N"], "bank_rows_per_gpu": per_gpu_rows, "collective": collective,
+                               "exchange": (args.exchange if xchg_used else "nccl"),
                                "nccl_path_ms_per_step": nccl_ms, "parity": parity, "balance": balance}
         print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:

@@ -190,6 +190,15 @@ int hb_search_config(hb_bank_t* bank, int cta_group, int max_chunks);
  * ablate is a MEASUREMENT-ONLY switch (results are wrong when it is non-zero): 1 = the epilogue
  * releases accumulators unread (pure GEMM pipeline), 2 = it scans but never inserts. */
 int hb_search_tune(hb_bank_t* bank, int prefetch_tiles, int ablate);
+/* Co-residency of the post-processing with a RUNNING search kernel (hb_search_begin / _finish on
+ * two streams).  A CTA becomes resident on an SM only if every one of its warps finds registers on
+ * the sub-partition it is assigned to (warp id mod 4), and the search CTA's ten 168-register warps
+ * fill two of the four sub-partitions.  lean_search != 0 selects a 128-register build of the search
+ * kernel (k' = 64, CTA pairs), which leaves 4096 registers free on every sub-partition;
+ * rerank_warps_per_cta = queries per K2b CTA (1, 2 or 4; 0 = default 4); rerank_shared_carveout =
+ * preferred shared-memory carve-out of K2b in per cent (-1 = driver default; 100 = the search
+ * kernel's own configuration, so that an SM need not drain to switch). */
+int hb_coresidency_config(hb_bank_t* bank, int lean_search, int rerank_warps_per_cta, int rerank_shared_carveout);
 /* Diagnostics: when stats_dev (device, zeroed, 148*8*8 uint64) is non-NULL, hb_search runs an
  * instrumented build that accumulates per-epilogue-warp cycle counters {wait, tmem load, slow path,
  * post-release folds, slow-path entries, folds, tiles, -}.  NULL switches it off. */
@@ -291,6 +300,21 @@ int64_t hb_exchange_slice_rows(const hb_exchange_t* xchg);
  * HB_ERR_STATE (message: which rank, which step) if a merge since the last call timed out, HB_OK
  * otherwise. */
 int hb_exchange_set_timeout(hb_exchange_t* xchg, int64_t timeout_ms);
+/* How much every shard re-ranks.  mode 0 (default): each shard re-ranks its own whole bf16 top-k'
+ * (what faiss.IndexShards' per-shard exact search amounts to), one exchange hop.  mode 1, the
+ * THRESHOLD EXCHANGE: hb_search_scatter / hb_search_finish_scatter stop after a first kernel that
+ * merges a query's chunk lists into its sorted bf16 top-k' and stores four order statistics of it
+ * (the scores at ranks k', k'/2, k'/4, k'/8) into every rank's window; once all peers' statistics
+ * have arrived (second flag array, same bounded wait), every shard derives the SAME lower bound of
+ * the global k'-th best bf16 score — if j shards hold k'/j candidates >= x each, k' rows score >= x —
+ * and gathers fp32 rows only for its candidates at or above it (on average ~k'/G + a few instead of
+ * k' per query and shard: the G-fold redundant row gather of mode 0 disappears, and the candidate
+ * set is a superset of the unsharded search's).  That second phase is issued by hb_exchange_rerank,
+ * or implicitly by the next hb_exchange_merge*.  All ranks must use the same mode. */
+int hb_exchange_config(hb_exchange_t* xchg, int mode);
+/* mode 1 only: issue phase 2 (wait for the peers' statistics, re-rank the survivors, scatter the
+ * results) of the exchange begun by the last scatter call.  No-op when nothing is pending. */
+int hb_exchange_rerank(hb_exchange_t* xchg, void* stream);
 int hb_exchange_status(hb_exchange_t* xchg, void* stream);
 
 /* ---- K4: label transfer ------------------------------------------------------------------

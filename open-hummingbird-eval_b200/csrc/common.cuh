@@ -71,10 +71,14 @@ struct Bank {
   int cfg_max_chunks = 0;
   int cfg_prefetch_tiles = -1;  // -1 = auto
   int cfg_ablate = 0;
+  // co-residency of the post-processing kernels with a running search kernel (hb_coresidency_config)
+  bool cfg_lean_search = false;  // 128-register build of the search kernel
+  int cfg_rerank_warps = 4;      // warps (= queries) per CTA of the re-rank kernel
+  int cfg_rerank_carveout = -1;  // preferred shared-memory carve-out (%) of the re-rank kernel, -1 = driver default
   unsigned long long* cfg_stats = nullptr;  // instrumented-build counters (hb_search_stats)
   bool cfg_pace = true;         // L2 pacing window of the search kernel
   int last_launches = 0;
-  int fit_cache[2][3][5] = {};  // co-resident clusters per (cta_group, k', kernel variant); 0 = unknown
+  int fit_cache[2][3][6] = {};  // co-resident clusters per (cta_group, k', kernel variant); 0 = unknown
   // optional kernel timing (hb_search_timing)
   bool timing = false;
   int timing_count = 0;
@@ -100,6 +104,20 @@ struct Scatter {
   int64_t* idx[kMaxPeers] = {};
   uint32_t* flag[kMaxPeers] = {};    // peer p: arrival flag of source `rank`
   unsigned int* done_ctas = nullptr; // local counter of finished CTAs
+  // Threshold exchange (hb_exchange_config mode 1), two phases instead of one re-rank of the shard's
+  // whole top-k':  phase 1 = shortlist_kernel merges the chunk lists of a query into its sorted bf16
+  // top-k' and broadcasts four order statistics of it to every peer; phase 2 = after all peers'
+  // statistics have arrived, every shard derives the same lower bound of the GLOBAL k'-th best bf16
+  // score and re-ranks (fp32 row gather) only its candidates at or above it.
+  int phase = 0;
+  uint4* stats[kMaxPeers] = {};      // peer p: statistics buffer (step & 1), source slot `rank`, one uint4 per query
+  uint32_t* flag2[kMaxPeers] = {};   // peer p: arrival flag of this rank's statistics
+  const uint4* stats_in = nullptr;   // own window, statistics buffer (step & 1): [source][q_cap]
+  const uint32_t* flags2_in = nullptr;  // own window: statistics arrival flags
+  int64_t q_cap = 0;                 // queries per source slot of the statistics buffer
+  unsigned int* done_ctas2 = nullptr;
+  unsigned int* timeout_flag = nullptr;
+  unsigned long long timeout_ns = 0;
 };
 
 // Optional fused label transfer (K4a) at the end of K2b / K3 / K3x: when `table` is set, the warp
@@ -115,8 +133,9 @@ struct LabelOut {
 };
 
 // One rank's end of the exchange: a cudaMalloc'ed window other ranks map through CUDA IPC.
-//   window = [flags: kMaxPeers x u32, padded to 256 B]
+//   window = [result flags: kMaxPeers x u32 | statistics flags: kMaxPeers x u32, padded to 256 B]
 //            2 x [scores: world x cap x kmax f32][idx: world x cap x kmax i64]
+//            2 x [statistics: world x (world * cap) x uint4]
 struct Exchange {
   int device = 0, rank = 0, world = 1;
   int64_t cap = 0;  // rows per slot
@@ -131,6 +150,23 @@ struct Exchange {
   unsigned int* done_ctas = nullptr;
   unsigned int* timeout_flag = nullptr;
   unsigned long long timeout_ms = 600000;  // bound of the merge kernel's wait for a peer
+  int mode = 0;             // 0: every shard re-ranks its whole top-k'; 1: threshold exchange (see Scatter)
+  // phase 2 of a threshold exchange that has been started (hb_search_scatter) but not yet issued
+  struct Pending {
+    bool active = false;
+    Bank* bank = nullptr;
+    int slot = 0;
+    const float* q = nullptr;
+    int64_t Q = 0, q_pad = 0, idx_offset = 0;
+    int k = 0, kp = 0;
+    const uint64_t* cand = nullptr;
+    Scatter sc;
+  } pending;
+  int64_t q_cap() const { return cap * world; }
+  size_t stats_off(int parity) const {
+    return 256 + 2 * buffer_bytes() + static_cast<size_t>(parity) * sizeof(uint4) * static_cast<size_t>(q_cap()) * world;
+  }
+  size_t window_bytes() const { return stats_off(2); }
   size_t scores_off(int parity) const { return 256 + static_cast<size_t>(parity) * buffer_bytes(); }
   size_t idx_off(int parity) const { return scores_off(parity) + sizeof(float) * slot_elems() * world; }
   size_t slot_elems() const { return static_cast<size_t>(cap) * kmax; }

@@ -36,11 +36,12 @@ int hb_exchange_create(int device, int rank, int world, int64_t slice_capacity, 
   x->world = world;
   x->cap = slice_capacity;
   x->kmax = max_k;
-  x->bytes = 256 + 2 * x->buffer_bytes();
+  x->bytes = x->window_bytes();
   cudaError_t e = cudaMalloc(&x->window[rank], x->bytes);
   if (e == cudaSuccess) e = cudaMemset(x->window[rank], 0, 256);
-  if (e == cudaSuccess) e = cudaMalloc(&x->done_ctas, 2 * sizeof(unsigned int));
-  if (e == cudaSuccess) e = cudaMemset(x->done_ctas, 0, 2 * sizeof(unsigned int));
+  // [0] CTAs done with the result scatter, [1] timeout flag, [2] CTAs done with the statistics broadcast
+  if (e == cudaSuccess) e = cudaMalloc(&x->done_ctas, 4 * sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(x->done_ctas, 0, 4 * sizeof(unsigned int));
   if (e != cudaSuccess) {
     hb::set_error("hb_exchange_create: allocating a %zu-byte window failed: %s", x->bytes, cudaGetErrorString(e));
     (void)cudaGetLastError();
@@ -168,7 +169,55 @@ static int prepare_scatter(Bank* b, Exchange* x, int64_t Q, int k, int k_prime, 
     sc->scores[p] = reinterpret_cast<float*>(win + x->scores_off(parity)) + x->slot_elems() * x->rank;
     sc->idx[p] = reinterpret_cast<int64_t*>(win + x->idx_off(parity)) + x->slot_elems() * x->rank;
     sc->flag[p] = reinterpret_cast<uint32_t*>(win) + x->rank;
+    sc->stats[p] = reinterpret_cast<uint4*>(win + x->stats_off(parity)) + x->q_cap() * x->rank;
+    sc->flag2[p] = reinterpret_cast<uint32_t*>(win) + hb::kMaxPeers + x->rank;
   }
+  sc->phase = x->mode == 1 ? 1 : 0;
+  sc->stats_in = reinterpret_cast<const uint4*>(x->window[x->rank] + x->stats_off(parity));
+  sc->flags2_in = reinterpret_cast<const uint32_t*>(x->window[x->rank]) + hb::kMaxPeers;
+  sc->q_cap = x->q_cap();
+  sc->done_ctas2 = x->done_ctas + 2;
+  sc->timeout_flag = x->timeout_flag;
+  sc->timeout_ns = x->timeout_ms * 1000000ull;
+  return HB_OK;
+}
+
+// Threshold exchange: remember what phase 2 needs (the slot's candidate buffer now holds the sorted
+// shortlists) until hb_exchange_rerank / hb_exchange_merge* issues it.
+static void remember_phase2(Exchange* x, Bank* b, int slot, const float* q, int k, int64_t idx_offset, const hb::Scatter& sc) {
+  const hb::PipeSlot& ps = b->pipe[slot];
+  Exchange::Pending& pd = x->pending;
+  pd.active = true;
+  pd.bank = b;
+  pd.slot = slot;
+  pd.q = q;
+  pd.Q = ps.Q;
+  pd.q_pad = ps.q_pad;
+  pd.idx_offset = idx_offset;
+  pd.k = k;
+  pd.kp = ps.kp;
+  pd.cand = ps.cand;
+  pd.sc = sc;
+  pd.sc.phase = 2;
+}
+
+static int issue_phase2(Exchange* x, cudaStream_t st) {
+  Exchange::Pending& pd = x->pending;
+  if (!pd.active) return HB_OK;
+  pd.active = false;
+  Bank* b = pd.bank;
+  int rc = hb::rerank_launch(b, pd.q, pd.Q, pd.k, pd.kp, 1, pd.q_pad, pd.cand, pd.idx_offset, nullptr, nullptr, &pd.sc,
+                             nullptr, st);
+  if (rc != HB_OK) return rc;
+  // the slot's candidate buffer is free for the next search only now
+  hb::PipeSlot& ps = b->pipe[pd.slot];
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) (void)cudaGetLastError();
+  if (cap == cudaStreamCaptureStatusNone) {
+    if (ps.done == nullptr) HB_CHECK_CUDA(cudaEventCreateWithFlags(&ps.done, cudaEventDisableTiming));
+    HB_CHECK_CUDA(cudaEventRecord(ps.done, st));
+  }
+  b->last_launches += 2;
   return HB_OK;
 }
 
@@ -186,9 +235,11 @@ int hb_search_scatter(hb_bank_t* bank, hb_exchange_t* xchg, const float* q_dev, 
   int rc = prepare_scatter(b, x, Q, k, k_prime, qsplit_host, step, &sc, "hb_search_scatter");
   if (rc != HB_OK) return rc;
   HB_CHECK_CUDA(cudaSetDevice(b->device));
+  x->pending.active = false;  // a phase 2 that was never issued belongs to an abandoned batch (error recovery)
   rc = hb::search_impl(b, q_dev, Q, k, k_prime, idx_offset, nullptr, nullptr, out_qnorm_dev, nullptr, 0,
                        static_cast<cudaStream_t>(stream), &sc, nullptr);
   if (rc != HB_OK) return rc;
+  if (sc.phase == 1) remember_phase2(x, b, 0, q_dev, k, idx_offset, sc);
   x->step = step;
   x->last_rows = qsplit_host[x->rank + 1] - qsplit_host[x->rank];
   x->last_k = k;
@@ -211,8 +262,10 @@ int hb_search_finish_scatter(hb_bank_t* bank, hb_exchange_t* xchg, int slot, con
   int rc = prepare_scatter(b, x, b->pipe[slot].Q, k, b->pipe[slot].kp, qsplit_host, step, &sc, "hb_search_finish_scatter");
   if (rc != HB_OK) return rc;
   HB_CHECK_CUDA(cudaSetDevice(b->device));
+  x->pending.active = false;  // a phase 2 that was never issued belongs to an abandoned batch (error recovery)
   rc = hb::search_finish_impl(b, slot, q_dev, k, idx_offset, nullptr, nullptr, &sc, nullptr, static_cast<cudaStream_t>(stream));
   if (rc != HB_OK) return rc;
+  if (sc.phase == 1) remember_phase2(x, b, slot, q_dev, k, idx_offset, sc);
   x->step = step;
   x->last_rows = qsplit_host[x->rank + 1] - qsplit_host[x->rank];
   x->last_k = k;
@@ -228,10 +281,31 @@ int hb_exchange_merge(hb_exchange_t* xchg, float* out_scores_dev, int64_t* out_i
   }
   HB_REQUIRE(x->last_rows == 0 || (out_scores_dev && out_idx_dev), "hb_exchange_merge: NULL output");
   HB_CHECK_CUDA(cudaSetDevice(x->device));
+  int rc = issue_phase2(x, static_cast<cudaStream_t>(stream));
+  if (rc != HB_OK) return rc;
   const int k = x->last_k;
   x->last_k = 0;  // one merge per scatter
   return hb::merge_window_launch(x, x->step, x->last_rows, k, out_scores_dev, out_idx_dev, nullptr,
                                  static_cast<cudaStream_t>(stream));
+}
+
+int hb_exchange_config(hb_exchange_t* xchg, int mode) {
+  HB_REQUIRE(xchg != nullptr, "hb_exchange_config: exchange is NULL");
+  HB_REQUIRE(mode == 0 || mode == 1, "hb_exchange_config: mode=%d not in {0, 1}", mode);
+  Exchange* x = reinterpret_cast<Exchange*>(xchg);
+  if (x->pending.active) {
+    hb::set_error("hb_exchange_config: an exchange is in flight");
+    return HB_ERR_STATE;
+  }
+  x->mode = mode;
+  return HB_OK;
+}
+
+int hb_exchange_rerank(hb_exchange_t* xchg, void* stream) {
+  HB_REQUIRE(xchg != nullptr, "hb_exchange_rerank: exchange is NULL");
+  Exchange* x = reinterpret_cast<Exchange*>(xchg);
+  HB_CHECK_CUDA(cudaSetDevice(x->device));
+  return issue_phase2(x, static_cast<cudaStream_t>(stream));
 }
 
 int hb_exchange_merge_transfer(hb_exchange_t* xchg, const uint16_t* label_table_dev, int64_t table_rows, int C,
@@ -256,6 +330,8 @@ int hb_exchange_merge_transfer(hb_exchange_t* xchg, const uint16_t* label_table_
   lo.beta = beta;
   lo.qnorm = qnorm_slice_dev;
   lo.out = out_label_hat_dev;
+  int rc = issue_phase2(x, static_cast<cudaStream_t>(stream));
+  if (rc != HB_OK) return rc;
   const int k = x->last_k;
   x->last_k = 0;  // one merge per scatter
   return hb::merge_window_launch(x, x->step, x->last_rows, k, out_scores_dev, out_idx_dev,

@@ -122,20 +122,25 @@ label_transfer_lanes(const LabelOut& lo, int64_t qi, int64_t out_row, int k, con
   }
 }
 
-template <int R, bool L2, bool LABEL>
-__device__ __forceinline__ void
-rerank_query(const float* __restrict__ q, const float* __restrict__ bank_f32,
-             const __nv_bfloat16* __restrict__ bank_bf16, const uint64_t* __restrict__ cand,
-             int n_chunks, int64_t q_pad, int64_t Q, int d, int dpad, int k, int64_t idx_offset,
-             float* __restrict__ out_scores, int64_t* __restrict__ out_idx, const Scatter& sc,
-             const LabelOut& lo) {
-  constexpr int KP = 32 * R;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t qi = static_cast<int64_t>(blockIdx.x) * 4 + warp;
-  if (qi >= Q) return;
+// j-th largest (j counted from 1) of the values held by lanes 0 .. G-1; 0 when G < j.  Warp-uniform result.
+__device__ __forceinline__ uint32_t nth_largest(uint32_t v, int G, int j, int lane) {
+  if (G < j) return 0u;
+  int rank = 0;  // lanes whose (value, lane) pair is greater than this lane's
+  for (int s = 0; s < G; ++s) {
+    const uint32_t o = __shfl_sync(0xffffffffu, v, s);
+    rank += (o > v || (o == v && s < lane)) ? 1 : 0;
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, lane < G && rank == j - 1);
+  return __shfl_sync(0xffffffffu, v, __ffs(m) - 1);
+}
 
-  // ---- union of the per-chunk candidate lists -> best k' by the bf16-pass score ----
-  uint64_t top[R];
+// The bf16-pass candidates of query qi, all chunks merged: its best k' keys, sorted descending over
+// (register r, lane) = element r*32 + lane.
+template <int R>
+__device__ __forceinline__ void
+merge_chunk_lists(const uint64_t* __restrict__ cand, int n_chunks, int64_t q_pad, int64_t qi, int lane,
+                  uint64_t (&top)[R]) {
+  constexpr int KP = 32 * R;
 #pragma unroll
   for (int r = 0; r < R; ++r) top[r] = cand[qi * KP + r * 32 + lane];
   warp_bitonic_sort<R, true>(top, lane);
@@ -150,6 +155,45 @@ rerank_query(const float* __restrict__ q, const float* __restrict__ bank_f32,
     for (int r = 0; r < R; ++r) top[r] = top[r] > nxt[r] ? top[r] : nxt[r];
     warp_bitonic_sort<R, true>(top, lane);
   }
+}
+
+// SUBSET = phase 2 of the threshold exchange: `cand` holds the query's sorted shortlist (written by
+// shortlist_kernel), and only its entries at or above the cross-shard bound are re-ranked.
+template <int R, bool L2, bool LABEL, bool SUBSET>
+__device__ __forceinline__ void
+rerank_query(const float* __restrict__ q, const float* __restrict__ bank_f32,
+             const __nv_bfloat16* __restrict__ bank_bf16, const uint64_t* __restrict__ cand,
+             int n_chunks, int64_t q_pad, int64_t Q, int d, int dpad, int k, int64_t idx_offset,
+             float* __restrict__ out_scores, int64_t* __restrict__ out_idx, const Scatter& sc,
+             const LabelOut& lo) {
+  constexpr int KP = 32 * R;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t qi = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + warp;  // 1, 2 or 4 warps per CTA
+  if (qi >= Q) return;
+
+  // ---- union of the per-chunk candidate lists -> best k' by the bf16-pass score ----
+  uint64_t top[R];
+  int n_keep = KP;  // leading entries of the sorted list that are re-ranked (warp-uniform)
+  if (SUBSET) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) top[r] = __ldcg(cand + qi * KP + r * 32 + lane);
+    // Every shard published the scores at ranks k', k'/2, k'/4, k'/8 of its own sorted list.  If j
+    // shards each hold k'/j candidates scoring >= x, then k' bank rows score >= x: the j-th largest of
+    // the rank-k'/j statistics is a lower bound of the global k'-th best bf16 score, for j = 1, 2, 4, 8,
+    // and every shard computes the same bound.  0 = "that shard has fewer candidates" (prunes nothing).
+    uint4 st = make_uint4(0u, 0u, 0u, 0u);
+    if (lane < sc.world) st = __ldcg(sc.stats_in + static_cast<int64_t>(lane) * sc.q_cap + qi);
+    uint32_t bound = nth_largest(st.x, sc.world, 1, lane);
+    bound = max(bound, nth_largest(st.y, sc.world, 2, lane));
+    bound = max(bound, nth_largest(st.z, sc.world, 4, lane));
+    bound = max(bound, nth_largest(st.w, sc.world, 8, lane));
+    n_keep = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      n_keep += __popc(__ballot_sync(0xffffffffu, top[r] != 0ull && static_cast<uint32_t>(top[r] >> 32) >= bound));
+  } else {
+    merge_chunk_lists<R>(cand, n_chunks, q_pad, qi, lane, top);
+  }
 
   // ---- exact fp32 scores of the k' candidates ----
   const float4* q4 = reinterpret_cast<const float4*>(q + qi * d);
@@ -159,13 +203,14 @@ rerank_query(const float* __restrict__ q, const float* __restrict__ bank_f32,
   for (int r = 0; r < R; ++r) {
     exact[r] = 0ull;
     for (int c0 = 0; c0 < 32; c0 += 4) {
+      if (SUBSET && r * 32 + c0 >= n_keep) break;  // the list is sorted: nothing further passes the bound
       uint32_t rows[4];
       bool valid[4];
       float acc[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const uint64_t key = __shfl_sync(0xffffffffu, top[r], c0 + u);
-        valid[u] = key != 0ull;
+        valid[u] = key != 0ull && (!SUBSET || r * 32 + c0 + u < n_keep);
         rows[u] = valid[u] ? key_row(key) : 0u;
         acc[u] = 0.f;
       }
@@ -241,14 +286,15 @@ rerank_query(const float* __restrict__ q, const float* __restrict__ bank_f32,
 // LABEL = with the fused label transfer.  No variant owns shared memory, so one of these CTAs fits
 // on an SM beside a resident search CTA (which takes all but ~2 KB of the shared memory and 82 % of
 // the registers): K2b of one batch runs under the K2 of the next one (hb_search_begin / _finish).
-template <int R, bool L2, bool LABEL>
+template <int R, bool L2, bool LABEL, bool SUBSET = false>
 __global__ void __launch_bounds__(128)
 rerank_kernel(const float* __restrict__ q, const float* __restrict__ bank_f32,
               const __nv_bfloat16* __restrict__ bank_bf16, const uint64_t* __restrict__ cand,
               int n_chunks, int64_t q_pad, int64_t Q, int d, int dpad, int k, int64_t idx_offset,
               float* __restrict__ out_scores, int64_t* __restrict__ out_idx,
               const __grid_constant__ Scatter sc, const LabelOut lo) {
-  rerank_query<R, L2, LABEL>(q, bank_f32, bank_bf16, cand, n_chunks, q_pad, Q, d, dpad, k, idx_offset,
+  if (SUBSET && __ldcg(sc.timeout_flag) != 0u) return;  // a peer's statistics never arrived (whole grid returns)
+  rerank_query<R, L2, LABEL, SUBSET>(q, bank_f32, bank_bf16, cand, n_chunks, q_pad, Q, d, dpad, k, idx_offset,
                              out_scores, out_idx, sc, lo);
   if (sc.world) {
     // Fused exchange: every thread's peer stores are ordered before the CTA counts itself done;
@@ -266,22 +312,92 @@ rerank_kernel(const float* __restrict__ q, const float* __restrict__ bank_f32,
   }
 }
 
+// Phase 1 of the threshold exchange: one warp per query merges the chunk lists into the sorted bf16
+// top-k', stores it back over the query's chunk-0 list (the only reader of the other chunks is this
+// warp) and writes the list's order statistics into every rank's window; the last CTA publishes the
+// step on every peer's statistics flag (same protocol as the result scatter).
+template <int R>
+__global__ void __launch_bounds__(128)
+shortlist_kernel(uint64_t* __restrict__ cand, int n_chunks, int64_t q_pad, int64_t Q,
+                 const __grid_constant__ Scatter sc) {
+  constexpr int KP = 32 * R;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t qi = static_cast<int64_t>(blockIdx.x) * 4 + warp;
+  if (qi < Q) {
+    uint64_t top[R];
+    merge_chunk_lists<R>(cand, n_chunks, q_pad, qi, lane, top);
+#pragma unroll
+    for (int r = 0; r < R; ++r) cand[qi * KP + r * 32 + lane] = top[r];
+    // ordered bf16 score at ranks k', k'/2, k'/4, k'/8 (element rank-1 of the list; 0 = no such candidate)
+    constexpr int e0 = KP - 1, e1 = KP / 2 - 1, e2 = KP / 4 - 1, e3 = KP / 8 - 1;
+    uint4 st;
+    st.x = static_cast<uint32_t>(__shfl_sync(0xffffffffu, top[e0 / 32], e0 % 32) >> 32);
+    st.y = static_cast<uint32_t>(__shfl_sync(0xffffffffu, top[e1 / 32], e1 % 32) >> 32);
+    st.z = static_cast<uint32_t>(__shfl_sync(0xffffffffu, top[e2 / 32], e2 % 32) >> 32);
+    st.w = static_cast<uint32_t>(__shfl_sync(0xffffffffu, top[e3 / 32], e3 % 32) >> 32);
+    if (lane < sc.world) sc.stats[lane][qi] = st;  // lane p stores into rank p's window
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(sc.done_ctas2, 1u);
+    if (prev == gridDim.x - 1) {
+      *sc.done_ctas2 = 0u;
+      __threadfence_system();
+      for (int p = 0; p < sc.world; ++p) st_release_sys(sc.flag2[p], sc.step);
+    }
+  }
+}
+
+__global__ void exchange_wait_kernel(const uint32_t* flags, uint32_t step, int G, unsigned long long timeout_ns,
+                                     unsigned int* timeout_flag);
+
 int rerank_launch(const Bank* b, const float* q, int64_t Q, int k, int kp,
                   int n_chunks, int64_t q_pad, const uint64_t* cand, int64_t idx_offset,
                   float* out_scores, int64_t* out_idx, const Scatter* sc, const LabelOut* lo,
                   cudaStream_t st) {
-  const unsigned blocks = static_cast<unsigned>(ceil_div64(Q, 4));
+  const int wpb = (b->cfg_rerank_warps == 1 || b->cfg_rerank_warps == 2) ? b->cfg_rerank_warps : 4;
+  const unsigned blocks = static_cast<unsigned>(ceil_div64(Q, wpb));
+  const unsigned threads = 32u * static_cast<unsigned>(wpb);
   const Scatter scatter = sc ? *sc : Scatter();
   const LabelOut label = lo ? *lo : LabelOut();
+  if (scatter.world && scatter.phase == 1) {  // threshold exchange, phase 1: shortlist + statistics broadcast
+    const unsigned sblocks = static_cast<unsigned>(ceil_div64(Q, 4));
+    uint64_t* cw = const_cast<uint64_t*>(cand);
+    if (kp == 32) shortlist_kernel<1><<<sblocks, 128, 0, st>>>(cw, n_chunks, q_pad, Q, scatter);
+    else if (kp == 64) shortlist_kernel<2><<<sblocks, 128, 0, st>>>(cw, n_chunks, q_pad, Q, scatter);
+    else if (kp == 128) shortlist_kernel<4><<<sblocks, 128, 0, st>>>(cw, n_chunks, q_pad, Q, scatter);
+    else {
+      set_error("rerank: k_prime=%d not in {32, 64, 128}", kp);
+      return HB_ERR_INVALID;
+    }
+    HB_CHECK_CUDA(cudaGetLastError());
+    return HB_OK;
+  }
+  if (scatter.world && scatter.phase == 2) {  // phase 2: wait for every peer's statistics, re-rank the survivors
+    exchange_wait_kernel<<<1, 32, 0, st>>>(scatter.flags2_in, scatter.step, scatter.world, scatter.timeout_ns,
+                                           scatter.timeout_flag);
+    HB_CHECK_CUDA(cudaGetLastError());
+    if (kp == 32) rerank_kernel<1, false, false, true><<<blocks, threads, 0, st>>>(q, b->feat_f32, b->feat_bf16, cand, 1, q_pad, Q, b->d, b->dpad, k, idx_offset, out_scores, out_idx, scatter, label);
+    else if (kp == 64) rerank_kernel<2, false, false, true><<<blocks, threads, 0, st>>>(q, b->feat_f32, b->feat_bf16, cand, 1, q_pad, Q, b->d, b->dpad, k, idx_offset, out_scores, out_idx, scatter, label);
+    else rerank_kernel<4, false, false, true><<<blocks, threads, 0, st>>>(q, b->feat_f32, b->feat_bf16, cand, 1, q_pad, Q, b->d, b->dpad, k, idx_offset, out_scores, out_idx, scatter, label);
+    HB_CHECK_CUDA(cudaGetLastError());
+    return HB_OK;
+  }
 #define HB_RERANK_ARGS q, b->feat_f32, b->feat_bf16, cand, n_chunks, q_pad, Q, b->d, b->dpad, k, idx_offset, out_scores, out_idx, scatter, label
+#define HB_RERANK_ONE(R, L2, LABEL)                                                               \
+  do {                                                                                            \
+    if (b->cfg_rerank_carveout >= 0)                                                              \
+      HB_CHECK_CUDA(cudaFuncSetAttribute(rerank_kernel<R, L2, LABEL>,                             \
+                                         cudaFuncAttributePreferredSharedMemoryCarveout,          \
+                                         b->cfg_rerank_carveout));                                \
+    rerank_kernel<R, L2, LABEL><<<blocks, threads, 0, st>>>(HB_RERANK_ARGS);                      \
+  } while (0)
 #define HB_RERANK(R)                                                                              \
   do {                                                                                            \
-    if (b->flags & HB_BANK_L2)                                                                    \
-      rerank_kernel<R, true, false><<<blocks, 128, 0, st>>>(HB_RERANK_ARGS);                      \
-    else if (label.table != nullptr)                                                              \
-      rerank_kernel<R, false, true><<<blocks, 128, 0, st>>>(HB_RERANK_ARGS);                      \
-    else                                                                                          \
-      rerank_kernel<R, false, false><<<blocks, 128, 0, st>>>(HB_RERANK_ARGS);                     \
+    if (b->flags & HB_BANK_L2) HB_RERANK_ONE(R, true, false);                                     \
+    else if (label.table != nullptr) HB_RERANK_ONE(R, false, true);                               \
+    else HB_RERANK_ONE(R, false, false);                                                          \
   } while (0)
   if (kp == 32) HB_RERANK(1);
   else if (kp == 64) HB_RERANK(2);
@@ -291,6 +407,7 @@ int rerank_launch(const Bank* b, const float* q, int64_t Q, int k, int kp,
     return HB_ERR_INVALID;
   }
 #undef HB_RERANK
+#undef HB_RERANK_ONE
 #undef HB_RERANK_ARGS
   HB_CHECK_CUDA(cudaGetLastError());
   return HB_OK;
@@ -373,7 +490,7 @@ merge_topk_kernel(const float* __restrict__ ss, const int64_t* __restrict__ si, 
 // hb_exchange_status() turns the flag into an error on the host.
 // merge_window_kernel — stream-ordered after it: merges the G lists of each query of the local slice
 // (+ fused label transfer); writes nothing if the wait gave up.
-__global__ void __launch_bounds__(32)
+__global__ void
 exchange_wait_kernel(const uint32_t* flags, uint32_t step, int G, unsigned long long timeout_ns,
                      unsigned int* timeout_flag) {
   if (threadIdx.x < G) {

@@ -173,8 +173,12 @@ __device__ __forceinline__ void fold_queue(float (&ls)[KL], uint32_t* rows, cons
   for (int j = 0; j < KL; ++j) rows[j * kEpiThreads] = lr[j];
 }
 
-template <int CG, int STAGES, int KP, int MODE>
-__global__ void __launch_bounds__(kSearchThreads, 1)
+// LB = the thread count the register budget is derived from (__launch_bounds__): kSearchThreads gives
+// ptxas the whole register file (168 registers per thread); 512 caps it at 128, which leaves room on
+// every SM sub-partition for a warp of another kernel (see hb_coresidency_config).  The launch is
+// always kSearchThreads wide.
+template <int CG, int STAGES, int KP, int MODE, int LB>
+__global__ void __launch_bounds__(LB, 1)
 search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
                    const __grid_constant__ CUtensorMap tmap_bank, const SearchParams p) {
   using L = SearchSmem<CG, STAGES, KP>;
@@ -583,11 +587,11 @@ prep_queries_kernel(const float* __restrict__ q, int64_t Q, int d, int dpad, int
 // Launch (or, with probe != nullptr, only size) the persistent search grid.  The kernel's CTAs wait
 // for each other (pair barriers, L2 pacing), so every CTA must be resident at once: the grid is
 // min(SMs / CG, work items, what the driver says fits) clusters.
-template <int CG, int STAGES, int KP, int MODE = 0>
+template <int CG, int STAGES, int KP, int MODE = 0, int LB = kSearchThreads>
 static int launch_search(const Bank* b, const CUtensorMap& tmap_q, const SearchParams& p,
                          cudaStream_t st, int* probe, int n_clusters) {
   using L = SearchSmem<CG, STAGES, KP>;
-  auto kern = search_topk_kernel<CG, STAGES, KP, MODE>;
+  auto kern = search_topk_kernel<CG, STAGES, KP, MODE, LB>;
   HB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic));
   cudaLaunchConfig_t cfg{};
   cfg.blockDim = dim3(kSearchThreads);
@@ -630,6 +634,8 @@ static int dispatch_search(const Bank* b, int cg, int kp, const CUtensorMap& tma
     if (cg == 2) return launch_search<2, 5, 64, 2>(b, tmap_q, p, st, probe, n_clusters);
     return launch_search<1, 3, 64, 2>(b, tmap_q, p, st, probe, n_clusters);
   }
+  if (cg == 2 && kp == 64 && b->cfg_lean_search)  // 128-register build of the default configuration
+    return launch_search<2, 5, 64, 0, 512>(b, tmap_q, p, st, probe, n_clusters);
   if (cg == 2) {
     if (kp == 32) return launch_search<2, 5, 32>(b, tmap_q, p, st, probe, n_clusters);
     if (kp == 64) return launch_search<2, 5, 64>(b, tmap_q, p, st, probe, n_clusters);
@@ -673,7 +679,7 @@ int search_begin_impl(Bank* b, const float* q, int64_t Q, int kp, int slot, floa
   if (ps.done != nullptr && !capturing) HB_CHECK_CUDA(cudaStreamWaitEvent(st, ps.done, 0));
 
   int n_units_used = 1;
-  const int variant = dump ? 1 : (b->cfg_ablate ? 2 + b->cfg_ablate : (b->cfg_stats ? 2 : 0));
+  const int variant = dump ? 1 : (b->cfg_ablate ? 2 + b->cfg_ablate : (b->cfg_stats ? 2 : (b->cfg_lean_search ? 5 : 0)));
   int& cached_fit = b->fit_cache[cg - 1][kp == 128 ? 2 : (kp == 64 ? 1 : 0)][variant];
   const int want_units = std::max(1, std::min(b->num_sms / cg, plan.n_qblocks * plan.n_chunks));
   if (cached_fit > 0) {
@@ -964,6 +970,19 @@ int hb_search_tune(hb_bank_t* bank, int prefetch_tiles, int ablate) {
   HB_REQUIRE(ablate >= 0 && ablate <= 2, "hb_search_tune: ablate=%d not in {0,1,2}", ablate);
   reinterpret_cast<Bank*>(bank)->cfg_prefetch_tiles = prefetch_tiles;
   reinterpret_cast<Bank*>(bank)->cfg_ablate = ablate;
+  return HB_OK;
+}
+
+int hb_coresidency_config(hb_bank_t* bank, int lean_search, int rerank_warps_per_cta, int rerank_shared_carveout) {
+  HB_REQUIRE(bank != nullptr, "hb_coresidency_config: bank is NULL");
+  HB_REQUIRE(rerank_warps_per_cta == 0 || rerank_warps_per_cta == 1 || rerank_warps_per_cta == 2 || rerank_warps_per_cta == 4,
+             "hb_coresidency_config: rerank_warps_per_cta=%d not in {0, 1, 2, 4}", rerank_warps_per_cta);
+  HB_REQUIRE(rerank_shared_carveout >= -1 && rerank_shared_carveout <= 100,
+             "hb_coresidency_config: rerank_shared_carveout=%d not in [-1, 100]", rerank_shared_carveout);
+  Bank* b = reinterpret_cast<Bank*>(bank);
+  b->cfg_lean_search = lean_search != 0;
+  b->cfg_rerank_warps = rerank_warps_per_cta ? rerank_warps_per_cta : 4;
+  b->cfg_rerank_carveout = rerank_shared_carveout;
   return HB_OK;
 }
 

@@ -49,6 +49,7 @@ _SIGNATURES = [
     ("hb_search_finish", c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_int64, c_float, c_void_p, c_void_p,
                                  c_void_p, c_void_p]),
     ("hb_search_abort", c_int, [c_void_p]),
+    ("hb_coresidency_config", c_int, [c_void_p, c_int, c_int, c_int]),
     ("hb_eval_step", c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
                              c_int64, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     ("hb_search_config", c_int, [c_void_p, c_int, c_int]),
@@ -77,6 +78,8 @@ _SIGNATURES = [
                                            c_void_p, c_void_p]),
     ("hb_exchange_slice_rows", c_int64, [c_void_p]),
     ("hb_exchange_set_timeout", c_int, [c_void_p, c_int64]),
+    ("hb_exchange_config", c_int, [c_void_p, c_int]),
+    ("hb_exchange_rerank", c_int, [c_void_p, c_void_p]),
     ("hb_exchange_status", c_int, [c_void_p, c_void_p]),
     ("hb_label_transfer", c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p]),
     ("hb_upsample_argmax", c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -182,10 +182,13 @@ def query_split(n_images: int, queries_per_image: int, world: int) -> List[int]:
         [n_images * queries_per_image]
 
 
-def connect_shard_exchange(slice_capacity: int, max_k: int, device: torch.device, group=None):
+def connect_shard_exchange(slice_capacity: int, max_k: int, device: torch.device, group=None,
+                           threshold_exchange: bool = True):
     """Create this rank's ShardExchange window and map every peer's (CUDA IPC handles travel by
     all-gather).  Returns None — on ALL ranks — if any rank cannot map its peers, in which case the
-    caller uses the NCCL all-gather + merge path."""
+    caller uses the NCCL all-gather + merge path.  threshold_exchange (same on all ranks): shards swap
+    order statistics of their bf16 shortlists and re-rank only the candidates at or above the common
+    bound (ops.ShardExchange.configure), instead of their whole top-k' each."""
     from . import ops
 
     rank, world = dist_info(group)
@@ -205,6 +208,7 @@ def connect_shard_exchange(slice_capacity: int, max_k: int, device: torch.device
         if xchg is not None:
             xchg.close()
         return None
+    xchg.configure(bool(threshold_exchange))
     return xchg
 
 

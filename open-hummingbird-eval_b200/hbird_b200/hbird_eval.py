@@ -485,8 +485,8 @@ class HbirdEvaluation:
         """The ShardExchange, (re)built when a batch needs a larger window.  Every rank sees the
         same batches, so every rank takes the same decision here."""
         mode = str(self.nn_params.get("exchange", "p2p")).lower()
-        if mode not in ("p2p", "nccl"):
-            raise ValueError(f"nn_params['exchange']={mode!r} must be 'p2p' or 'nccl'")
+        if mode not in ("p2p", "p2p_full", "nccl"):
+            raise ValueError(f"nn_params['exchange']={mode!r} must be 'p2p', 'p2p_full' or 'nccl'")
         if mode == "nccl" or getattr(self, "_xchg_failed", False):
             return None
         per_img = n_queries // n_images
@@ -496,7 +496,10 @@ class HbirdEvaluation:
             if xchg is not None:
                 # peers still map the old window: keep it alive instead of freeing it under them
                 self._retired_xchg = getattr(self, "_retired_xchg", []) + [xchg]
-            self._xchg = hdist.connect_shard_exchange(need, self.n_neighbours, self.device)
+            # 'p2p': threshold exchange (shards re-rank only what can reach the global top-k');
+            # 'p2p_full': every shard re-ranks its whole top-k' (one hop less, G-fold redundant gathers)
+            self._xchg = hdist.connect_shard_exchange(need, self.n_neighbours, self.device,
+                                                      threshold_exchange=(mode == "p2p"))
             if self._xchg is None:
                 logger.warning("peer-memory exchange unavailable; using NCCL all-gather + merge")
                 self._xchg_failed = True

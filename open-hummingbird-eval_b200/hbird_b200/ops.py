@@ -241,6 +241,13 @@ class MemoryBank:
                                ptr(scores), ptr(idx), stream_ptr(q.device)))
         return label_hat
 
+    def configure_coresidency(self, lean_search: bool = False, rerank_warps_per_cta: int = 0,
+                              rerank_shared_carveout: int = -1) -> None:
+        """How the search kernel and the re-rank kernel share an SM when the latter is issued under the
+        former (pipeline.py): see hb_coresidency_config."""
+        check(lib.hb_coresidency_config(self._h, int(bool(lean_search)), int(rerank_warps_per_cta),
+                                        int(rerank_shared_carveout)))
+
     def tune_search(self, prefetch_tiles: int = -1, ablate: int = 0) -> None:
         """ablate != 0 is for measurement only (wrong results): 1 = GEMM pipeline alone, 2 = scan only."""
         check(lib.hb_search_tune(self._h, int(prefetch_tiles), int(ablate)))
@@ -352,6 +359,17 @@ class ShardExchange:
     def set_timeout(self, timeout_ms: int) -> None:
         """Bound of a merge kernel's wait for its peers (default 10 min)."""
         check(lib.hb_exchange_set_timeout(self._h, int(timeout_ms)))
+
+    def configure(self, threshold_exchange: bool) -> None:
+        """False (default): every shard re-ranks its whole bf16 top-k' (one hop).  True: the threshold
+        exchange — shards first swap order statistics of their shortlists and then re-rank only the
+        candidates at or above the common bound (hb_exchange_config mode 1).  Same setting on all ranks."""
+        check(lib.hb_exchange_config(self._h, 1 if threshold_exchange else 0))
+
+    def rerank(self) -> None:
+        """Threshold exchange only: issue phase 2 of the last scatter on the current stream now (the next
+        merge would do it implicitly).  The queries passed to the scatter must still be alive."""
+        check(lib.hb_exchange_rerank(self._h, stream_ptr(torch.device("cuda", self.device))))
 
     def check_status(self) -> None:
         """Synchronise the current stream and raise RuntimeError if a merge since the last check gave up

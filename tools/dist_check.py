@@ -1,7 +1,8 @@
 """Run under torchrun (one rank per GPU): the multi-GPU engine must reproduce the reference's golden
 result (tests/golden) in both of the reference's faiss layouts (search_faiss.py:53-74):
-row shards (nn_params idx_shard=True: per-shard search, shard exchange — fused peer-memory exchange
-and the NCCL all-gather + K3 merge path, which must agree bit for bit — replicated label table,
+row shards (nn_params idx_shard=True: per-shard search, shard exchange — the peer-memory threshold
+exchange, the peer-memory exchange with a full per-shard re-rank and the NCCL all-gather + K3 merge path,
+which must agree bit for bit — replicated label table,
 features extracted once across the ranks and all-gathered) and replicas (idx_shard=False, the
 default: full bank on every rank, validation batches dealt round-robin); all-reduced confusion
 matrix in both.  Also: augmentation epochs with a loader length that does not divide by the world
@@ -40,7 +41,7 @@ for name in ("voc_tiny", "ade_tiny"):
     cfg, g = load_golden(name)
     data = SyntheticSegmentationData(**cfg)
     confs = {}
-    for mode in ("p2p", "nccl", "replicas"):
+    for mode in ("p2p", "p2p_full", "nccl", "replicas"):
         fe = FeatureExtractorSimple(data.model, data.ftr_extr_fn, data.S, data.d)
         nn_params = {"idx_shard": False} if mode == "replicas" else {"idx_shard": True, "exchange": mode}
         ev = HbirdEvaluation(fe, data.train_dataloader(), num_classes=data.C, n_neighbours=30,
@@ -61,7 +62,7 @@ for name in ("voc_tiny", "ade_tiny"):
         fused = getattr(ev, "_xchg", None) is not None
         good = abs(miou - float(g["miou"])) <= 5e-4 and conf.sum() == g["conf"].sum() and \
             np.abs(conf - g["conf"]).sum() <= 2e-4 * conf.sum() and sum(rows) == g["feature_memory"].shape[0] and \
-            len(rows) == (1 if mode == "replicas" else world) and fused == (mode == "p2p") and bool(details_ok) and \
+            len(rows) == (1 if mode == "replicas" else world) and fused == (mode in ("p2p", "p2p_full")) and bool(details_ok) and \
             ev.bank.rows == (sum(rows) if mode == "replicas" else rows[rank])
         report[f"{name}_{mode}"] = {"miou": miou, "ref": float(g["miou"]), "shard_rows": rows,
                                     "fused_exchange": fused, "details_ok": bool(details_ok), "ok": bool(good)}
@@ -103,7 +104,8 @@ for name in ("voc_tiny", "ade_tiny"):
                                    "shard_rows": ev.shard_counts}
     ok = ok and bool(files_ok) and reload_ok
     ev.close()
-    same = bool((confs["p2p"] == confs["nccl"]).all()) and bool((confs["p2p"] == confs["replicas"]).all())
+    same = bool((confs["p2p"] == confs["nccl"]).all()) and bool((confs["p2p"] == confs["replicas"]).all()) and \
+        bool((confs["p2p"] == confs["p2p_full"]).all())
     report[f"{name}_paths_identical"] = same
     ok = ok and same
 # augmentation epochs x a loader whose length does not divide by the world size: the batch counter runs

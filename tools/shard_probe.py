@@ -52,6 +52,7 @@ def k2_only(bank, ring, label):
 
     def fn():
         bank.search_begin(ring[i[0] % len(ring)][0], bench.K_PRIME, 0)
+        bank.search_abort()  # host-side flag only: the slot may be begun again
         i[0] += 1
 
     bank.enable_kernel_timing(True)
