@@ -150,12 +150,12 @@ int hb_search_transfer(hb_bank_t* bank, const uint16_t* label_table_dev, int64_t
 /* Split form of hb_search / hb_search_transfer for software pipelining across batches.  begin =
  * query prep + K2 (the tensor-core pass) into pipeline slot `slot` (0 or 1) on `stream`; finish = K2b
  * (exact re-rank, outputs as hb_search / hb_search_transfer: give out_scores/out_idx, out_label_hat,
- * or all three) from that slot on ANY stream that is ordered after the begin (event).  The plain and
- * the scatter re-rank kernels own no shared memory, so they run on the SMs under the K2 of the NEXT
- * batch, whose CTAs take all but ~2 KB of it: the HBM-bound half of batch i hides under the
- * tensor-bound half of batch i+1.  A slot is reused only after its finish has run (enforced with an
- * event inside the library); q_dev must stay valid until the finish has executed; the scratch block is
- * grows in stream order.  prepared_event: optional `cudaEvent_t` recorded between the query prep and
+ * or all three) from that slot on ANY stream that is ordered after the begin (event).  With the
+ * finish of batch i on a second stream and the begin of batch i+1 on a higher-priority one, the
+ * post-processing fills the SMs the search CTAs vacate as they finish and the launch gaps between two
+ * search kernels (it is not co-resident with the default search build: hb_coresidency_config).  A
+ * slot is reused only after its finish has run (enforced with an event inside the library); q_dev
+ * must stay valid until the finish has executed; the scratch block grows in stream order.  prepared_event: optional `cudaEvent_t` recorded between the query prep and
  * K2 — a pipelined caller makes the previous batch's finish wait for it, so that the small kernels
  * are released together with the search kernel (whose stream should have the higher priority)
  * instead of flooding the SMs in the gap before it. */

@@ -90,8 +90,8 @@ label_transfer_lanes(const LabelOut& lo, int64_t qi, int64_t out_row, int k, con
   }
   sum = warp_sum(sum);
   // softmax weight and table row of element e = r*32 + lane stay in this lane's registers and are
-  // broadcast with shuffles below: no shared memory, so these kernels fit beside a resident search
-  // CTA.  A missing neighbour keeps weight 0 and reads row 0 (no branch in the gather loop).
+  // broadcast with shuffles below: the kernels stay free of shared memory.  A missing neighbour keeps
+  // weight 0 and reads row 0 (no branch in the gather loop).
   float w[R];
   int64_t row[R];
 #pragma unroll
@@ -283,9 +283,13 @@ rerank_query(const float* __restrict__ q, const float* __restrict__ bank_f32,
   if (LABEL && !L2) label_transfer_lanes<R>(lo, qi, qi, k, fs, fi);
 }
 
-// LABEL = with the fused label transfer.  No variant owns shared memory, so one of these CTAs fits
-// on an SM beside a resident search CTA (which takes all but ~2 KB of the shared memory and 82 % of
-// the registers): K2b of one batch runs under the K2 of the next one (hb_search_begin / _finish).
+// LABEL = with the fused label transfer.  No variant owns shared memory.  Issued on a second stream
+// while the next batch's search runs (hb_search_begin / _finish), these CTAs fill the SMs the search
+// kernel's CTAs vacate as they finish, and the launch gaps; they are NOT co-resident with a search
+// CTA of the default build: its ten 168-register warps fill the register file of two of the four SM
+// sub-partitions, and a CTA is placed only if every one of its warps finds room (measured:
+// tools/pipe_timeline.py; hb_coresidency_config selects a 128-register search build beside which
+// they do run, which does not pay under the power cap).
 template <int R, bool L2, bool LABEL, bool SUBSET = false>
 __global__ void __launch_bounds__(128)
 rerank_kernel(const float* __restrict__ q, const float* __restrict__ bank_f32,
@@ -483,8 +487,8 @@ merge_topk_kernel(const float* __restrict__ ss, const int64_t* __restrict__ si, 
 // K3x: the receiving half of the fused exchange, in two launches.
 // exchange_wait_kernel — ONE warp polls the G step flags of this rank's window until every source rank
 // has published `step` (the rows were stored by the peers' K2b kernels over NVLink; acquire at system
-// scope).  A single polling warp instead of a wait at the head of every merge CTA: the merge usually
-// runs under the next batch's search (pipeline.py), and hundreds of resident CTAs polling peer-visible
+// scope).  A single polling warp instead of a wait at the head of every merge CTA: the merge is usually
+// issued while the next batch's search runs (pipeline.py), and hundreds of CTAs polling peer-visible
 // memory slowed that search by several per cent.  The wait is bounded: after `timeout_ns` the kernel
 // records which rank is missing in `timeout_flag` — no trap, the context stays usable;
 // hb_exchange_status() turns the flag into an error on the host.

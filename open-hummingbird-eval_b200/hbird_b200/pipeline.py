@@ -2,13 +2,22 @@
 
 A batch has a tensor-bound half (query prep + K2, the tcgen05 pass over the whole bank shard) and an
 HBM/latency-bound half (K2b exact re-rank with the label transfer fused in — or, with a row-sharded
-bank, K2b scatter -> exchange wait -> merge + label transfer — and the fused tail).  The second half
-of batch i does not feed the first half of batch i+1, so the two run on different streams: K2 of
-batch i+1 on a high-priority stream, the post-processing of batch i on a second one.  The re-rank
-and merge kernels own no shared memory and few registers, so one of their CTAs fits on every SM
-beside the resident search CTA: the HBM-bound work executes UNDER the tensor-core pass instead of
-after it, and with a sharded bank a rank that is ahead of its peers starts the next search instead of
-idling in the exchange.  (Same arithmetic as the one-call step: tests/test_gpu_fused.py.)
+bank, shortlist / K2b scatter -> exchange wait -> merge + label transfer — and the fused tail).  The
+second half of batch i does not feed the first half of batch i+1, so the two are issued on different
+streams: K2 of batch i+1 on a high-priority stream, the post-processing of batch i on a second one.
+
+What that buys, measured (tools/pipe_timeline.py, tools/ab_pipeline.py; profiles/r02_pipeline_timeline_*,
+r02_ab_pipeline.json): the post-processing kernels are NOT co-resident with a search CTA — its ten
+168-register warps fill the register file of two of an SM's four sub-partitions and a CTA is placed only
+if all its warps find room — so K2b of batch i makes little progress while K2 of batch i+1 runs and
+completes as that kernel's CTAs finish; the gain is the ramp-down of one search kernel and the launch
+gap before the next one being filled with useful work (interleaved A/B: cfg1 1.334 -> 1.299 ms per step,
+cfg2 8.00 -> 7.91, a 1.28 M x 768 shard 31.81 -> 31.67; with the threshold exchange on 8 GPUs 31.95 ->
+31.33).  A 128-register build of the search kernel (MemoryBank.configure_coresidency) does run K2b beside
+it (5.5 ms instead of 30 ms under a 31 ms search) and gains nothing: the step is power-bound, and the
+4.3 GB row gather costs the same energy wherever it is scheduled.  With a sharded bank a rank that is
+ahead of its peers starts the next search instead of idling in the exchange.  (Same arithmetic as the
+one-call step: tests/test_gpu_fused.py.)
 """
 from __future__ import annotations
 
@@ -22,10 +31,10 @@ from . import ops
 
 # When is the second stream worth it?  The post-processing of a batch costs ~k'*4d bytes of HBM gather
 # per query, the search 2*rows*d flop per query: their ratio is ~28 600 / rows on a B200, independent of
-# d.  Running the gather under the search slows the search by ~0.8 % (measured at cfg3: 238.3 -> 240.2
-# ms; issue slots and power), so the overlap pays only where the post-processing is more than a few
-# per cent of a step: banks (or bank shards) of up to ~2 M rows per GPU.  Measured on B200: 1.02 M
-# rows (cfg2) 7.64 -> 7.22 ms per step, 512 k-row shards 4.22 -> 3.82 ms, 10.24 M rows 239.5 -> 240.4 ms.
+# d.  Issuing the gather beside the search costs the search ~0.8 % (measured at cfg3: 238.3 -> 240.2 ms;
+# power), so it pays only where the post-processing and the launch gaps are more than a few per cent of
+# a step: banks (or bank shards) of up to ~2 M rows per GPU.  Measured on B200: 10.24 M rows 239.5 ->
+# 240.4 ms; smaller banks gain 0.5 - 3 % (module docstring).
 MAX_ROWS_PER_GPU = 1 << 21
 
 
@@ -72,7 +81,7 @@ class EvalPipeline:
             searched = torch.cuda.Event()
             searched.record(self.mma_stream)
         if self.pending is not None:
-            # released together with this batch's search kernel (not in the gap before it), runs under it
+            # released together with this batch's search kernel (not in the gap before it)
             self.post_stream.wait_event(prepared)
             self._post(self.pending)
         self.pending = (slot, q, y, qn, n_images, searched, ready)
