@@ -48,6 +48,52 @@ __device__ __forceinline__ void warp_bitonic_sort(uint64_t (&a)[R], int lane) {
   }
 }
 
+// Sort a BITONIC sequence of 32*R keys (same layout): the last pass of the network above, log2(32R) stages.
+template <int R, bool DESC>
+__device__ __forceinline__ void warp_bitonic_merge(uint64_t (&a)[R], int lane) {
+  constexpr int n = 32 * R;
+#pragma unroll
+  for (int j = n >> 1; j > 0; j >>= 1) {
+    if (j < 32) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const uint64_t other = __shfl_xor_sync(0xffffffffu, a[r], j);
+        const bool lower = (lane & j) == 0;
+        const uint64_t lo = a[r] < other ? a[r] : other;
+        const uint64_t hi = a[r] < other ? other : a[r];
+        a[r] = (lower != DESC) ? lo : hi;
+      }
+    } else {
+      const int jr = j >> 5;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if ((r & jr) == 0) {
+          const int r2 = r | jr;
+          const uint64_t lo = a[r] < a[r2] ? a[r] : a[r2];
+          const uint64_t hi = a[r] < a[r2] ? a[r2] : a[r];
+          a[r] = DESC ? hi : lo;
+          a[r2] = DESC ? lo : hi;
+        }
+      }
+    }
+  }
+}
+
+// One (query, chunk) block of the search kernel's candidate buffer is two runs of k'/2 keys, each sorted
+// by descending score (the two register lists of an epilogue row, search.cu; empty entries are key 0 at the
+// end).  Read with the second run backwards the block is a bitonic sequence, which one merge pass sorts —
+// no full sort.  (Equal scores may sit in any row order inside a run: the merge then still orders by score,
+// which is all the selection needs; the exact re-rank sorts its own keys from scratch.)
+template <int R>
+__device__ __forceinline__ void load_chunk_bitonic(const uint64_t* __restrict__ src, int lane, uint64_t (&a)[R]) {
+  constexpr int KP = 32 * R, KL = KP / 2;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int e = r * 32 + lane;
+    a[r] = src[e < KL ? e : KP - 1 - (e - KL)];
+  }
+}
+
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -141,19 +187,17 @@ __device__ __forceinline__ void
 merge_chunk_lists(const uint64_t* __restrict__ cand, int n_chunks, int64_t q_pad, int64_t qi, int lane,
                   uint64_t (&top)[R]) {
   constexpr int KP = 32 * R;
-#pragma unroll
-  for (int r = 0; r < R; ++r) top[r] = cand[qi * KP + r * 32 + lane];
-  warp_bitonic_sort<R, true>(top, lane);
+  load_chunk_bitonic<R>(cand + qi * KP, lane, top);
+  warp_bitonic_merge<R, true>(top, lane);
   for (int c = 1; c < n_chunks; ++c) {
     uint64_t nxt[R];
-    const uint64_t* src = cand + (static_cast<int64_t>(c) * q_pad + qi) * KP;
-#pragma unroll
-    for (int r = 0; r < R; ++r) nxt[r] = src[r * 32 + lane];
-    warp_bitonic_sort<R, false>(nxt, lane);
-    // top descending, nxt ascending: the element-wise max holds the k' largest of the union
+    load_chunk_bitonic<R>(cand + (static_cast<int64_t>(c) * q_pad + qi) * KP, lane, nxt);
+    warp_bitonic_merge<R, false>(nxt, lane);
+    // top descending, nxt ascending: the element-wise max holds the k' largest of the union, as a
+    // bitonic sequence again
 #pragma unroll
     for (int r = 0; r < R; ++r) top[r] = top[r] > nxt[r] ? top[r] : nxt[r];
-    warp_bitonic_sort<R, true>(top, lane);
+    warp_bitonic_merge<R, true>(top, lane);
   }
 }
 
