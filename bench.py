@@ -923,10 +923,10 @@ def main():
                                f"rank post-processes its image slice",
                 "collective": collective,
                 "path": PATH,
-                "pipelining": ("two streams: K2 of batch i+1 (high priority) over the re-rank / exchange / merge / tail of "
-                               "batch i (shared-memory-free kernels co-resident with the search CTAs); every batch is complete "
-                               "inside the timed region") if head["pipelined"] else
-                              "none: one blocking call sequence per batch (the engine pipelines banks of <= 2M rows per GPU only)",
+                "pipelining": ("two streams: K2 of batch i+1 (high priority) issued beside the re-rank / exchange / merge / tail "
+                               "of batch i, which fill the search kernel's ramp-down and the launch gaps; every batch is "
+                               "complete inside the timed region") if head["pipelined"] else
+                              "none: one blocking call sequence per batch (the engine pipelines banks of <= 8.4M rows per GPU only)",
                 "l2": f"inputs larger than L2: bf16 bank shard {per_gpu_rows * w['d'] * 2 / 1e6:.0f} MB streamed every step, "
                       f"{RING} distinct query batches cycled",
             },

@@ -596,10 +596,10 @@ class HbirdEvaluation:
         conf = metric.confusion_buffer()
         details = []  # per batch: (batch number, knns, knns_labels, knns_ca_labels) CPU tensors
         replicas = self.world > 1 and not self.idx_shard
-        # Banks (or shards) of up to ~2 M rows per GPU go through a two-stream pipeline (pipeline.py):
-        # the tensor-core search of batch i+1 runs over the HBM-bound post-processing of batch i.
-        # Larger ones, and return_knn_details (every batch's neighbours go to the host), take the
-        # one-call-per-batch path below.
+        # Banks (or shards) of up to ~8 M rows per GPU go through a two-stream pipeline (pipeline.py):
+        # the tensor-core search of batch i+1 is issued beside the HBM-bound post-processing of batch i,
+        # which fills the search kernel's ramp-down and the launch gaps.  Larger ones, and
+        # return_knn_details (every batch's neighbours go to the host), take the one-call-per-batch path.
         pipe = None
         if self.nn_method == "b200" and not return_knn_details and hpipe.worthwhile(self.bank):
             if getattr(self, "_pipe_streams", None) is None:

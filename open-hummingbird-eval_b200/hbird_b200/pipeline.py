@@ -31,11 +31,12 @@ from . import ops
 
 # When is the second stream worth it?  The post-processing of a batch costs ~k'*4d bytes of HBM gather
 # per query, the search 2*rows*d flop per query: their ratio is ~28 600 / rows on a B200, independent of
-# d.  Issuing the gather beside the search costs the search ~0.8 % (measured at cfg3: 238.3 -> 240.2 ms;
-# power), so it pays only where the post-processing and the launch gaps are more than a few per cent of
-# a step: banks (or bank shards) of up to ~2 M rows per GPU.  Measured on B200: 10.24 M rows 239.5 ->
-# 240.4 ms; smaller banks gain 0.5 - 3 % (module docstring).
-MAX_ROWS_PER_GPU = 1 << 21
+# d, so the possible gain shrinks with the bank.  Interleaved A/B on B200 (tools/ab_pipeline.py; one-call
+# -> pipelined, ms per step): 102 k rows 1.334 -> 1.299, 1.02 M 8.00 -> 7.91, 1.28 M x 768 31.81 -> 31.67,
+# 2.56 M 61.40 -> 61.31, 5.12 M 121.04 -> 120.64.  Never a loss where measured that way (an earlier
+# sequential comparison at 10.24 M rows, 239.5 -> 240.4 ms, was within the clock drift); the bound below
+# covers the measured range.
+MAX_ROWS_PER_GPU = 1 << 23
 
 
 def make_streams(device):
