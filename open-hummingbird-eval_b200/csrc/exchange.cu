@@ -172,7 +172,7 @@ static int prepare_scatter(Bank* b, Exchange* x, int64_t Q, int k, int k_prime, 
     sc->stats[p] = reinterpret_cast<uint4*>(win + x->stats_off(parity)) + x->q_cap() * x->rank;
     sc->flag2[p] = reinterpret_cast<uint32_t*>(win) + hb::kMaxPeers + x->rank;
   }
-  sc->phase = x->mode == 1 ? 1 : 0;
+  sc->phase = (x->mode == 1 && x->world > 1) ? 1 : 0;  // a single shard has nobody to swap statistics with
   sc->stats_in = reinterpret_cast<const uint4*>(x->window[x->rank] + x->stats_off(parity));
   sc->flags2_in = reinterpret_cast<const uint32_t*>(x->window[x->rank]) + hb::kMaxPeers;
   sc->q_cap = x->q_cap();

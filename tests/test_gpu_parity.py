@@ -595,6 +595,17 @@ def test_search_tuning_knobs_do_not_change_results():
         bank.tune_search(prefetch_tiles=pf)
         s, i, _ = bank.search(q.to(DEV), 30, 64)
         assert torch.equal(s, base_s) and torch.equal(i, base_i), (cg, pace, pf, chunks)
+    # co-residency knobs: the 128-register build of the search kernel and the re-rank kernel's CTA shape /
+    # shared-memory carve-out preference
+    bank.configure_search(0, 0), bank.set_pacing(True), bank.tune_search(-1)
+    for lean, wpb, carve in [(True, 4, -1), (True, 2, 100), (False, 1, 100), (False, 0, -1)]:
+        bank.configure_coresidency(lean, wpb, carve)
+        s, i, _ = bank.search(q.to(DEV), 30, 64)
+        assert torch.equal(s, base_s) and torch.equal(i, base_i), (lean, wpb, carve)
+    with pytest.raises(ValueError, match="rerank_warps_per_cta"):
+        bank.configure_coresidency(False, 3, -1)
+    with pytest.raises(ValueError, match="rerank_shared_carveout"):
+        bank.configure_coresidency(False, 4, 101)
     bank.close()
 
 
