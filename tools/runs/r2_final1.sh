@@ -1,6 +1,6 @@
 #!/bin/bash
 # final lines, 1 GPU: default bench (as the driver runs it) + reference arm (driver's K/W)
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 SECONDS=0
 timeout 1500 python bench.py > gpurun_out/final_bench_cfg3_n1.json 2> gpurun_out/final_bench_cfg3_n1.err

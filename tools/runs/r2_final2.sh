@@ -1,6 +1,6 @@
 #!/bin/bash
 # final lines, N GPUs (N = number of visible GPUs; with 8 also N=4): the driver's torchrun commands
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 NG=$(nvidia-smi -L | wc -l)
 for N in $NG $( [ "$NG" = "8" ] && echo 4 ); do

@@ -1,6 +1,6 @@
 #!/bin/bash
 # 1 GPU: the whole GPU test suite, the default bench line (cfg3 + by_workload), smoke, ncu of the exchange kernels
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?"; tail -3 gpurun_out/pytest_gpu.log

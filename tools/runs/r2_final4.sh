@@ -1,6 +1,6 @@
 #!/bin/bash
 # 2 GPUs, exactly what the driver runs at N = 2 (all by_workload extras), plus the GPU test suite
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_n2.log 2>&1
 echo "pytest exit $?"; tail -2 gpurun_out/pytest_gpu_n2.log

@@ -1,6 +1,6 @@
 #!/bin/bash
 # 8 GPUs: N=8 headline with the one-warp exchange wait, pipelined vs one-call in the same run
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 SECONDS=0
 timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29571 bench.py --gpus 8 --steps 20 --warmup 3 --extras cfg2,cfg5 > gpurun_out/bench_cfg3_n8.json 2> gpurun_out/bench_cfg3_n8.err

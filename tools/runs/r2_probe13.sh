@@ -1,6 +1,6 @@
 #!/bin/bash
 # 8 GPUs: equal vs speed-balanced shards, full-length runs in the same process
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 SECONDS=0
 timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29601 bench.py --gpus 8 --steps 20 --warmup 3 > gpurun_out/final_bench_cfg3_n8.json 2> gpurun_out/final_bench_cfg3_n8.err

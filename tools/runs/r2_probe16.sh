@@ -1,7 +1,7 @@
 #!/bin/bash
 # 2 GPUs: engine check in every layout / exchange mode, then the bench with the threshold exchange and,
 # for comparison, with the full per-shard re-rank (headline only)
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_multi.py -x -q -m gpu -k "matches_reference" > gpurun_out/pytest_multi.log 2>&1
 echo "pytest multi exit $?"; tail -3 gpurun_out/pytest_multi.log

@@ -1,7 +1,7 @@
 #!/bin/bash
 # N GPUs (default 8): headline only, threshold exchange vs full per-shard re-rank on the same box
 N=${1:-8}
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 for mode in threshold full; do
   SECONDS=0

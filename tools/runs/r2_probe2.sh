@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call 2: GPU test-suite, default bench line (cfg3) with wall time, reference arm at cfg3, K2 probe
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > gpurun_out/smi.txt 2>&1
 nproc > gpurun_out/host.txt; free -g >> gpurun_out/host.txt

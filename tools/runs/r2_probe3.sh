@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call 3 (2 GPUs): multi-GPU engine check (both layouts), bench at N=2, reference arm under torchrun
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name,memory.total --format=csv > gpurun_out/smi2.txt 2>&1
 timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -x -q > gpurun_out/pytest_multi.log 2>&1

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call 5 (8 GPUs): the driver's scaling command at N=8, reduced extras
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 SECONDS=0
 timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 8 --steps 20 --warmup 3 > gpurun_out/bench_cfg3_n8.json 2> gpurun_out/bench_cfg3_n8.err

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call 6 (2 GPUs): pipelined path — GPU tests on one GPU, engine check + bench on two
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log

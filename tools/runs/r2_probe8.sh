@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call 8 (8 GPUs): the driver's scaling commands at N=8 and N=4 (4 of the 8 GPUs)
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 for N in 8 4; do
   SECONDS=0

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call 9 (1 GPU): GPU test-suite after the exchange / pipeline changes, ncu of the final K2b+K4a
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
