@@ -310,8 +310,9 @@ int hb_exchange_set_timeout(hb_exchange_t* xchg, int64_t timeout_ms);
  * and gathers fp32 rows only for its candidates at or above it (on average ~k'/G + a few instead of
  * k' per query and shard: the G-fold redundant row gather of mode 0 disappears, and the candidate
  * set is a superset of the unsharded search's).  That second phase is issued by hb_exchange_rerank,
- * or implicitly by the next hb_exchange_merge*; the bank and the query buffer given to the scatter
- * must stay alive until then.  All ranks must use the same mode; with world = 1 the mode is moot. */
+ * or implicitly by the next hb_exchange_merge*, on the stream of THAT call (which must be the
+ * scatter's stream or ordered after it); the bank and the query buffer given to the scatter must stay
+ * alive until then.  All ranks must use the same mode; with world = 1 the mode is moot. */
 int hb_exchange_config(hb_exchange_t* xchg, int mode);
 /* mode 1 only: issue phase 2 (wait for the peers' statistics, re-rank the survivors, scatter the
  * results) of the exchange begun by the last scatter call.  No-op when nothing is pending. */
