@@ -188,6 +188,24 @@ def merge_shards(shard_idx: np.ndarray, shard_dist: np.ndarray, k: int) -> Tuple
     return np.take_along_axis(ai, order, axis=1), np.take_along_axis(ad, order, axis=1)
 
 
+def shortlist_bound(shard_scores_desc: np.ndarray, kp: int) -> np.ndarray:
+    """The bound the threshold exchange derives on every shard (rerank.cu, rerank_query<SUBSET>): from the
+    scores at ranks kp, kp/2, kp/4, kp/8 of each shard's sorted candidate list — if j shards hold kp/j
+    candidates >= x each, the union holds kp candidates >= x — take the largest such x over j = 1, 2, 4, 8.
+    shard_scores_desc: (G, Q, kp) per-shard candidate scores, descending, -inf where a shard has fewer.
+    Returns (Q,) lower bounds of the kp-th best score of the union (-inf = no bound).  What
+    faiss.IndexShards (search_faiss.py:53-63) needs from a shard is only its candidates at or above it."""
+    G = shard_scores_desc.shape[0]
+    bound = np.full(shard_scores_desc.shape[1], -np.inf, dtype=F32)
+    for j in (1, 2, 4, 8):
+        if G < j or kp // j < 1:
+            continue
+        stat = shard_scores_desc[:, :, kp // j - 1]           # (G, Q): every shard's (kp/j)-th best
+        jth = -np.sort(-stat, axis=0)[j - 1]                  # j-th largest over the shards
+        bound = np.maximum(bound, jth.astype(F32))
+    return bound
+
+
 # ------------------------------------------------------------------ label transfer (A7-A8)
 def l2_normalize(x: np.ndarray, eps: float = 1e-12) -> np.ndarray:
     """torch.nn.functional.normalize(dim=-1): x / max(||x||, eps)."""

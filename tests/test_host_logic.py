@@ -159,3 +159,26 @@ def test_balanced_shard_counts_equalise_the_search_time():
     assert balanced_counts([100, 100], [1.0, 5.0]) == [110, 90]          # clamped to +-10 %
     assert balanced_counts([7], [3.0]) == [7] and balanced_counts([5, 5], [0.0, 1.0]) == [5, 5]
     assert balanced_counts([3, 1_000_000], [1.0, 1.0]) == [3, 1_000_000]  # equal speed per row... stays within bounds
+
+
+@pytest.mark.parametrize("G,kp", [(2, 64), (4, 64), (8, 64), (8, 32), (3, 128), (16, 64)])
+def test_threshold_exchange_bound_never_prunes_the_global_top_kprime(G, kp):
+    """The rule behind hb_exchange_config mode 1, on the oracle's restatement of it: the bound is never
+    above the kp-th best score of the union of the shards' candidate lists, so re-ranking only the
+    candidates at or above it keeps a superset of the global top-kp; and it is tight enough to matter
+    (far fewer than G*kp survivors) whether the neighbours are spread evenly or sit in one shard."""
+    rng = np.random.default_rng(100 * G + kp)
+    Q, per = 200, 3000
+    scores = rng.standard_normal((G, Q, per)).astype(np.float32)
+    scores[0, :50, :2 * kp] += 6.0    # 50 queries whose best 2*kp rows all live in shard 0
+    scores[1, 50:60, kp // 2:] = -np.inf   # a shard with fewer than kp candidates for some queries
+    top = -np.sort(-scores, axis=2)[:, :, :kp]
+    bound = O.shortlist_bound(top, kp)
+    union = -np.sort(-top.transpose(1, 0, 2).reshape(Q, -1), axis=1)
+    kth = union[:, kp - 1]
+    assert (bound <= kth).all()
+    kept = (top >= bound[None, :, None]).sum(axis=(0, 2))
+    assert (kept >= kp).all()
+    assert kept[:50].mean() <= 1.5 * kp            # concentrated: about one shard's list
+    if G >= 4:
+        assert kept[60:].mean() <= 0.45 * G * kp   # spread out: a fraction of the G lists
